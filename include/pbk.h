@@ -1,0 +1,156 @@
+/* pbk.h -- C ABI of libpbk.so: B200 (sm_100a) kernels for pulsarbat's FFT baseband hot path.
+ *
+ * The reference (theXYZT/pulsarbat) is pure Python and has no FFI of its own;
+ * the seams it offers are function-level.  Every entry point below names the reference
+ * interface it stands in for (paths relative to /root/reference/pulsarbat).  INTEGRATION.md
+ * shows the ctypes stub a pulsarbat maintainer would add at each seam.
+ *
+ * Conventions
+ *  - Every function returns 0 (PBK_OK) or a negative pbk_status; nothing throws or aborts.
+ *    pbk_last_error() returns a thread-local message for the last failure on this thread.
+ *  - Arrays are C-ordered with time slowest: (nsamp, nchan, npol) complex64 = float pairs
+ *    (core.py:36-39, 392-394, 786-787).  npol is the product of all axes after frequency.
+ *  - The caller owns every data pointer.  The library owns plans and their workspaces.
+ *  - *_host entry points take HOST pointers (pageable or pinned), copy in, run, copy out and
+ *    synchronise before returning; they may be called concurrently from several threads (a
+ *    plan serialises its own executions).  *_device entry points take DEVICE pointers on the
+ *    plan's device, enqueue on `stream` (a cudaStream_t cast to void*, NULL = legacy default
+ *    stream) and do not synchronise.
+ *  - There is no CPU fallback: without a CUDA device every call fails with PBK_ERR_CUDA.
+ */
+#ifndef PBK_H_
+#define PBK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBK_VERSION 100
+
+typedef struct pbk_plan pbk_plan;
+
+enum pbk_status {
+  PBK_OK = 0,
+  PBK_ERR_INVALID = -1,     /* bad argument */
+  PBK_ERR_UNSUPPORTED = -2, /* valid request this build cannot run (e.g. non power-of-two nsamp) */
+  PBK_ERR_CUDA = -3,        /* CUDA runtime error / no device */
+  PBK_ERR_NOMEM = -4
+};
+
+enum pbk_dtype { PBK_C64 = 0, PBK_I8X2 = 1 /* interleaved (re, im) int8 pairs */ };
+
+enum pbk_out_kind {
+  PBK_OUT_C64 = 0,       /* dedispersed voltages, complex64                              */
+  PBK_OUT_INTENSITY = 1, /* re^2+im^2 per pol, float32      (core.py:766-774)            */
+  PBK_OUT_STOKES_I = 2   /* |A|^2+|B|^2, float32, npol == 2 (core.py:944-948, 956-960)   */
+};
+
+int pbk_version(void);
+const char* pbk_last_error(void);
+const char* pbk_status_string(int status);
+int pbk_device_count(int* count);
+
+/* ---- coherent dedispersion ---------------------------------------------------------------
+ * Replaces transforms/dedispersion.py:81-133 `coherent_dedispersion` for numpy/dask blocks and
+ * device buffers, including the chirp of dedispersion.py:19-23/59-75, which is generated inside
+ * the kernel (FP64 phase) and never stored.  crop_start/crop_stop are computed by the CALLER
+ * exactly as dedispersion.py:127-131 so that the integer crop is bit-identical to the reference;
+ * pass (0, nsamp) for the uncropped circular result.
+ *   out_kind C64:        out is (crop_stop-crop_start, nchan, npol) complex64
+ *   out_kind INTENSITY:  out is (rows, nchan, npol) float32
+ *   out_kind STOKES_I:   out is (rows, nchan) float32
+ * with rows = (crop_stop-crop_start) / downsample when downsample > 1 (time sum of `downsample`
+ * consecutive samples, tail dropped; builder-defined; only for float outputs).
+ */
+typedef struct pbk_dedisp_desc {
+  int64_t nsamp;              /* N: power of two, >= 16 */
+  int64_t nchan;              /* C */
+  int64_t npol;               /* P */
+  int32_t in_dtype;           /* pbk_dtype */
+  int32_t out_kind;           /* pbk_out_kind */
+  double dm;                  /* pc / cm^3 */
+  double sample_rate_hz;      /* per-channel sample rate == channel bandwidth (core.py:761) */
+  double ref_freq_hz;         /* may be +inf */
+  const double* chan_freq_hz; /* [nchan] channel centre frequencies (core.py:569-574) */
+  int64_t crop_start;
+  int64_t crop_stop;
+  int64_t downsample;         /* 1 = none */
+  int32_t explicit_chirp;     /* 1: a (nsamp, nchan) complex64 chirp is passed at execution
+                                 (dedispersion.py:121-124, `chirp=` argument) */
+  int32_t device;             /* CUDA device ordinal */
+} pbk_dedisp_desc;
+
+int pbk_dedisp_plan_create(const pbk_dedisp_desc* desc, pbk_plan** plan);
+/* rows of the output, elements per row, bytes per element */
+int pbk_dedisp_out_shape(const pbk_plan* plan, int64_t* rows, int64_t* row_elems,
+                         int64_t* elem_bytes);
+int pbk_dedisp_exec_host(pbk_plan* plan, const void* in, void* out, const void* chirp);
+int pbk_dedisp_exec_device(pbk_plan* plan, const void* d_in, void* d_out, const void* d_chirp,
+                           void* stream);
+
+/* ---- axis-0 complex FFT --------------------------------------------------------------------
+ * Replaces fft.py:30-48 `pb.fft.fft` / `pb.fft.ifft` with axis=0 for complex64 data (scipy
+ * "backward" normalisation: forward unscaled, inverse 1/n), natural-order output.
+ * Data is (outer, n, inner) complex64, transform along n.  n must be a power of two >= 2.
+ */
+int pbk_fft_plan_create(int64_t outer, int64_t n, int64_t inner, int32_t inverse, int32_t device,
+                        pbk_plan** plan);
+
+/* ---- channelize / unchannelize -------------------------------------------------------------
+ * Replaces contrib/misc.py:17-55 `stft` and :58-93 `istft` (boxcar, no overlap):
+ *   forward:  in (nseg*nperseg, nchan, npol) -> out (nseg, nchan*nperseg, npol),
+ *             out[s, c*n + ((k + n/2) mod n), p] = (1/n) sum_t in[s*n+t, c, p] e^{-2 pi i k t/n}
+ *   inverse:  in (nseg, nchan_out*nperseg, npol) -> out (nseg*nperseg, nchan_out, npol)
+ * nperseg must be a power of two >= 2 (other lengths: PBK_ERR_UNSUPPORTED).  The input is never
+ * modified (the reference's istft scales its input in place, misc.py:82-83).
+ */
+int pbk_stft_plan_create(int64_t nseg, int64_t nperseg, int64_t nchan, int64_t npol,
+                         int32_t inverse, int32_t device, pbk_plan** plan);
+
+/* execution for FFT and STFT plans */
+int pbk_fft_exec_host(pbk_plan* plan, const void* in, void* out);
+int pbk_fft_exec_device(pbk_plan* plan, const void* d_in, void* d_out, void* stream);
+
+/* ---- detection / integration ---------------------------------------------------------------
+ * pbk_detect:     float32 power from complex64 voltages (core.py:766-774; Stokes I core.py:948).
+ *                 in (nsamp, nchan, npol) c64 -> out (nsamp/downsample, nchan[, npol]) f32
+ * pbk_downsample: out[j] = sum_{m<M} in[j*M+m] over time on float32 (builder-defined, row R).
+ * Both take device pointers when `on_device` != 0, host pointers otherwise.
+ */
+int pbk_detect(const void* in, void* out, int64_t nsamp, int64_t nchan, int64_t npol,
+               int32_t out_kind, int64_t downsample, int32_t on_device, int32_t device,
+               void* stream);
+int pbk_downsample(const void* in, void* out, int64_t nsamp, int64_t row_elems,
+                   int64_t factor, int32_t on_device, int32_t device, void* stream);
+
+/* ---- folding (builder-defined; phase model = pulsar/predictor.py:149-160) --
+ * ph_n = polyval((n0+n)/sample_rate_hz) with numpy's Horner order in FP64 without FMA
+ * contraction; bin = floor((ph - floor(ph)) * nbin) mod nbin;
+ * profile[bin, j] += in[n, j] (float32 atomics), counts[bin] += 1 (exact).
+ * profile (nbin, row_elems) float32 and counts (nbin) int64 are ACCUMULATED into (zero them
+ * first); bins_out, if non-NULL, receives the int32 bin of every sample (for bit-exact checks).
+ */
+int pbk_fold(const void* in, int64_t nsamp, int64_t row_elems, const double* coeffs,
+             int32_t ncoef, double sample_rate_hz, int64_t n0, int32_t nbin, void* profile,
+             void* counts, void* bins_out, int32_t on_device, int32_t device, void* stream);
+
+void pbk_plan_destroy(pbk_plan* plan);
+
+/* plan introspection for benchmarks: number of kernel launches per execution, workspace bytes */
+int pbk_plan_info(const pbk_plan* plan, int32_t* launches, int64_t* workspace_bytes,
+                  int32_t* levels, int32_t* level_log2 /* [3] */);
+
+/* raw device-memory helpers so a ctypes caller needs no other CUDA binding */
+int pbk_malloc(void** dptr, size_t bytes, int32_t device);
+int pbk_free(void* dptr, int32_t device);
+int pbk_memcpy_h2d(void* dst, const void* src, size_t bytes, int32_t device);
+int pbk_memcpy_d2h(void* dst, const void* src, size_t bytes, int32_t device);
+int pbk_device_sync(int32_t device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBK_H_ */

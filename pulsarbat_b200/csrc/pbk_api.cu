@@ -1,0 +1,839 @@
+// pbk_api.cu -- host side of libpbk.so: plans, pass scheduling and the C ABI of include/pbk.h.
+//
+// A plan turns one reference call into a short fixed list of kernel launches:
+//   coherent_dedispersion (transforms/dedispersion.py:81-133), N = L1*..*Lm:
+//       FWD(L1) .. FWD(Lm-1)  ->  MID(Lm: fft, chirp, ifft)  ->  INV(Lm-1) .. INV(L1)+epilogue
+//   pb.fft.fft/ifft axis 0 (fft.py:30-48), stft/istft (contrib/misc.py:17-93):
+//       FWD(L1) .. FWD(Lm) with a natural-order (optionally fftshift-ed) store in the last pass.
+// All index arithmetic the reference does with reshape/swapaxes/fftshift is folded into the
+// AddrMap of the first and last pass, so no transposed copy is ever made.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/pbk.h"
+#include "pbk_fft.cuh"
+#include "pbk_misc.cuh"
+
+using namespace pbk;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                 \
+  do {                                                                                 \
+    cudaError_t e__ = (expr);                                                          \
+    if (e__ != cudaSuccess)                                                            \
+      return fail(e__ == cudaErrorMemoryAllocation ? PBK_ERR_NOMEM : PBK_ERR_CUDA,     \
+                  "%s failed: %s", #expr, cudaGetErrorString(e__));                    \
+  } while (0)
+
+extern "C" const char* pbk_last_error(void) { return g_err; }
+extern "C" int pbk_version(void) { return PBK_VERSION; }
+extern "C" const char* pbk_status_string(int s) {
+  switch (s) {
+    case PBK_OK: return "ok";
+    case PBK_ERR_INVALID: return "invalid argument";
+    case PBK_ERR_UNSUPPORTED: return "unsupported";
+    case PBK_ERR_CUDA: return "CUDA error";
+    case PBK_ERR_NOMEM: return "out of memory";
+  }
+  return "unknown";
+}
+extern "C" int pbk_device_count(int* count) {
+  if (!count) return fail(PBK_ERR_INVALID, "count is NULL");
+  *count = 0;
+  CUDA_TRY(cudaGetDeviceCount(count));
+  return PBK_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------
+enum Role { ROLE_USER_IN = 0, ROLE_SCRATCH = 1, ROLE_USER_OUT = 2, ROLE_TMPF = 3 };
+enum PlanKind { PLAN_DEDISP = 0, PLAN_FFT = 1 };
+
+struct Pass {
+  int mode = MODE_FWD;
+  bool fast = false;
+  bool signinv = false;
+  int in_role = ROLE_USER_IN, out_role = ROLE_SCRATCH;
+  PassArgs a;
+  unsigned grid = 0;
+  size_t smem = 0;
+  int tw_table = -1;  // index into plan tables (by log2L)
+};
+
+struct pbk_plan {
+  int kind = PLAN_DEDISP;
+  int device = 0;
+  std::mutex mu;
+  std::vector<Pass> passes;
+  int nlevels = 0;
+  int level_log2[3] = {0, 0, 0};
+  // device resources owned by the plan
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+  float2* d_tw = nullptr;
+  double* d_chanfreq = nullptr;
+  void* d_tmpf = nullptr;       // pre-downsample float buffer
+  size_t tmpf_bytes = 0;
+  // lazily allocated staging buffers for *_host execution
+  void* h_din = nullptr;
+  void* h_dout = nullptr;
+  void* h_dchirp = nullptr;
+  size_t in_bytes = 0, out_bytes = 0, chirp_bytes = 0;
+  // dedisp description
+  pbk_dedisp_desc desc{};
+  int64_t out_rows = 0, row_elems = 0, elem_bytes = 0, full_rows = 0;
+  int launches = 0;
+};
+
+static int ilog2_exact(int64_t v) {
+  if (v <= 0 || (v & (v - 1))) return -1;
+  int l = 0;
+  while ((1ll << l) < v) ++l;
+  return l;
+}
+
+struct TableSet {
+  std::vector<float2> host;
+  int off_by_log2L[16][kMaxStages];
+  bool have[16];
+  TableSet() { memset(have, 0, sizeof(have)); memset(off_by_log2L, 0, sizeof(off_by_log2L)); }
+  void ensure(int log2L) {
+    if (have[log2L]) return;
+    have[log2L] = true;
+    const int ns = (log2L + 3) / 4;
+    const int log2r1 = log2L - 4 * (ns - 1);
+    const long long Lt = 1ll << log2L;
+    for (int s = 0; s + 1 < ns; ++s) {
+      const int R = s == 0 ? (1 << log2r1) : 16;
+      const long long M = s == 0 ? Lt : (1ll << (4 * (ns - s)));
+      const long long S = M / R;
+      off_by_log2L[log2L][s] = (int)host.size();
+      for (long long q = 0; q < S; ++q)
+        for (int m = 0; m < R; ++m) {
+          const long long e = (q * m) % M;
+          const double ang = -2.0 * M_PI * (double)e / (double)M;
+          host.push_back(make_float2((float)cos(ang), (float)sin(ang)));
+        }
+      while (host.size() % 2) host.push_back(make_float2(0.f, 0.f));  // keep 16 B alignment
+    }
+  }
+};
+
+static AddrMap plain_map(long long Lt, long long R, long long I, long long P) {
+  AddrMap m;
+  m.a_o = 0;  // filled by caller (elements per o_orig)
+  m.a_kp = Lt * R * I;
+  m.a_kl = 0;
+  m.a_n = I;
+  m.a_c = P;
+  m.a_p = 1;
+  m.a_row = R * I;
+  return m;
+}
+
+static bool map_even(const AddrMap& m, long long P) {
+  if ((m.a_o | m.a_kp | m.a_kl | m.a_n | m.a_row) & 1) return false;
+  if (P % 2 == 0) return m.a_p == 1 && (m.a_c % 2 == 0);
+  return P == 1 && m.a_c == 1;
+}
+
+static void set_geometry(Pass& ps, int log2L, long long Q, long long RI, int I, int P,
+                         int log2Kprev) {
+  PassArgs& a = ps.a;
+  a.Q = Q;
+  a.RI = RI;
+  a.I = I;
+  a.P = P;
+  a.log2L = log2L;
+  a.nstages = (log2L + 3) / 4;
+  a.log2r1 = log2L - 4 * (a.nstages - 1);
+  int lpw = std::min(7, std::max(0, 12 - log2L));
+  const long long pairs = (Q + 1) / 2;
+  while (lpw > 0 && (1ll << (lpw - 1)) >= pairs) --lpw;
+  a.log2pw = lpw;
+  a.log2Kprev = log2Kprev;
+  ps.smem = a.nstages > 1 ? ((size_t)1 << (log2L + lpw)) * sizeof(float4) : 0;
+  const long long W = 2ll << lpw;
+  ps.grid = (unsigned)((Q + W - 1) / W);
+}
+
+static void defaults(PassArgs& a) {
+  memset(&a, 0, sizeof(a));
+  a.sign = -1;
+  a.scale = 1.0f;
+  a.load_kind = LOAD_C64;
+  a.epi_kind = EPI_C64;
+  a.crop_start = 0;
+  a.crop_stop = LLONG_MAX;
+  a.n_mul = 0;
+  a.chirp_kind = CHIRP_NONE;
+}
+
+static void set_klow(PassArgs& a, int level /*1-based*/, const int* l) {
+  a.kl_sa = 0; a.kl_mb = 0; a.kl_sb = 0;
+  if (level == 3) { a.kl_sa = l[1]; a.kl_mb = (1 << l[1]) - 1; a.kl_sb = l[0]; }
+}
+
+static int choose_levels(int n, int* l, bool need_mid16) {
+  int m;
+  if (n <= 12) m = 1;
+  else if (n <= 24) m = 2;
+  else if (n <= 36) m = 3;
+  else return 0;
+  if (m == 1) { l[0] = n; }
+  else if (m == 2) { l[0] = n / 2; l[1] = n - l[0]; }
+  else { l[0] = n / 3; l[1] = n / 3; l[2] = n - l[0] - l[1]; }
+  if (need_mid16 && l[m - 1] < 4) return 0;
+  return m;
+}
+
+template <int MODE, bool FAST, bool SIGNINV>
+static cudaError_t launch_variant(const Pass& ps, cudaStream_t st) {
+  auto kern = pass_kernel<MODE, FAST, SIGNINV>;
+  static bool attr_done[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 16 && !attr_done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         200 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_done[dev] = true;
+  }
+  kern<<<ps.grid, kThreads, ps.smem, st>>>(ps.a);
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_pass(const Pass& ps, bool fast, cudaStream_t st) {
+  switch (ps.mode) {
+    case MODE_FWD:
+      if (ps.signinv) return fast ? launch_variant<MODE_FWD, true, true>(ps, st)
+                                  : launch_variant<MODE_FWD, false, true>(ps, st);
+      return fast ? launch_variant<MODE_FWD, true, false>(ps, st)
+                  : launch_variant<MODE_FWD, false, false>(ps, st);
+    case MODE_MID:
+      return fast ? launch_variant<MODE_MID, true, false>(ps, st)
+                  : launch_variant<MODE_MID, false, false>(ps, st);
+    default:
+      return fast ? launch_variant<MODE_INV, true, false>(ps, st)
+                  : launch_variant<MODE_INV, false, false>(ps, st);
+  }
+}
+
+static int upload_tables(pbk_plan* pl, TableSet& ts) {
+  if (ts.host.empty()) ts.host.push_back(make_float2(1.f, 0.f));
+  CUDA_TRY(cudaMalloc(&pl->d_tw, ts.host.size() * sizeof(float2)));
+  CUDA_TRY(cudaMemcpy(pl->d_tw, ts.host.data(), ts.host.size() * sizeof(float2),
+                      cudaMemcpyHostToDevice));
+  for (auto& ps : pl->passes) {
+    ps.a.stage_tw = pl->d_tw;
+    for (int s = 0; s < kMaxStages; ++s) ps.a.stage_tw_off[s] = ts.off_by_log2L[ps.a.log2L][s];
+  }
+  return PBK_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// dedispersion plan
+// ------------------------------------------------------------------------------------------
+extern "C" int pbk_dedisp_plan_create(const pbk_dedisp_desc* d, pbk_plan** out) {
+  if (!d || !out) return fail(PBK_ERR_INVALID, "NULL argument");
+  *out = nullptr;
+  if (d->nsamp <= 0 || d->nchan <= 0 || d->npol <= 0)
+    return fail(PBK_ERR_INVALID, "shape must be positive");
+  if (!d->chan_freq_hz) return fail(PBK_ERR_INVALID, "chan_freq_hz is NULL");
+  if (!(d->sample_rate_hz > 0)) return fail(PBK_ERR_INVALID, "sample_rate_hz must be > 0");
+  if (d->in_dtype != PBK_C64 && d->in_dtype != PBK_I8X2)
+    return fail(PBK_ERR_INVALID, "unknown in_dtype %d", d->in_dtype);
+  if (d->out_kind < PBK_OUT_C64 || d->out_kind > PBK_OUT_STOKES_I)
+    return fail(PBK_ERR_INVALID, "unknown out_kind %d", d->out_kind);
+  if (d->out_kind == PBK_OUT_STOKES_I && d->npol != 2)
+    return fail(PBK_ERR_INVALID, "Stokes I needs npol == 2, got %lld", (long long)d->npol);
+  if (d->downsample < 1) return fail(PBK_ERR_INVALID, "downsample must be >= 1");
+  if (d->downsample > 1 && d->out_kind == PBK_OUT_C64)
+    return fail(PBK_ERR_INVALID, "downsample applies to float outputs only");
+  if (d->crop_start < 0 || d->crop_stop > d->nsamp)
+    return fail(PBK_ERR_INVALID, "crop [%lld, %lld) outside [0, %lld]", (long long)d->crop_start,
+                (long long)d->crop_stop, (long long)d->nsamp);
+  const int n = ilog2_exact(d->nsamp);
+  if (n < 4)
+    return fail(PBK_ERR_UNSUPPORTED,
+                "nsamp = %lld: this build handles power-of-two lengths >= 16 only",
+                (long long)d->nsamp);
+  int l[3] = {0, 0, 0};
+  const int m = choose_levels(n, l, true);
+  if (m == 0) return fail(PBK_ERR_UNSUPPORTED, "nsamp = 2^%d is too long", n);
+  const long long I = d->nchan * d->npol;
+  if (I > INT_MAX / 2) return fail(PBK_ERR_UNSUPPORTED, "nchan*npol too large");
+
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (d->device < 0 || d->device >= ndev)
+    return fail(PBK_ERR_CUDA, "device %d not available (%d CUDA devices)", d->device, ndev);
+  CUDA_TRY(cudaSetDevice(d->device));
+
+  pbk_plan* pl = new pbk_plan();
+  pl->kind = PLAN_DEDISP;
+  pl->device = d->device;
+  pl->desc = *d;
+  pl->desc.chan_freq_hz = nullptr;
+  pl->nlevels = m;
+  for (int i = 0; i < m; ++i) pl->level_log2[i] = l[i];
+
+  const long long N = d->nsamp;
+  const int P = (int)d->npol;
+  const long long C = d->nchan;
+  const long long crop_rows = std::max<long long>(0, d->crop_stop - d->crop_start);
+  pl->full_rows = crop_rows;
+  pl->out_rows = d->downsample > 1 ? crop_rows / d->downsample : crop_rows;
+  pl->row_elems = d->out_kind == PBK_OUT_STOKES_I ? C : I;
+  pl->elem_bytes = d->out_kind == PBK_OUT_C64 ? 8 : 4;
+  pl->in_bytes = (size_t)N * I * (d->in_dtype == PBK_C64 ? 8 : 2);
+  pl->out_bytes = (size_t)pl->out_rows * pl->row_elems * pl->elem_bytes;
+  pl->chirp_bytes = d->explicit_chirp ? (size_t)N * C * 8 : 0;
+
+  TableSet ts;
+  const bool fast_ok = (I % 2 == 0) && (P % 2 == 0);
+  long long Kprev[3], R[3];
+  {
+    long long k = 1;
+    for (int i = 0; i < m; ++i) { Kprev[i] = k; k <<= l[i]; }
+    long long r = 1;
+    for (int i = m - 1; i >= 0; --i) { R[i] = r; r <<= l[i]; }
+  }
+  auto log2ll = [](long long v) { int s = 0; while ((1ll << s) < v) ++s; return s; };
+
+  auto final_epilogue = [&](Pass& ps, int level0) {
+    PassArgs& a = ps.a;
+    a.epi_kind = d->out_kind;
+    a.crop_start = d->crop_start;
+    a.crop_stop = d->crop_stop;
+    a.n_mul = R[level0];
+    if (d->out_kind == PBK_OUT_STOKES_I) {
+      a.mout.a_o = 0; a.mout.a_kp = 0; a.mout.a_kl = 0;
+      a.mout.a_n = C; a.mout.a_c = 1; a.mout.a_p = 0; a.mout.a_row = R[level0] * C;
+    }
+    ps.out_role = d->downsample > 1 ? ROLE_TMPF : ROLE_USER_OUT;
+  };
+
+  // forward levels 1..m-1
+  for (int i = 0; i + 1 < m; ++i) {
+    Pass ps;
+    defaults(ps.a);
+    ps.mode = MODE_FWD;
+    set_geometry(ps, l[i], Kprev[i] * R[i] * I, R[i] * I, (int)I, P, log2ll(Kprev[i]));
+    ps.a.min = plain_map(1ll << l[i], R[i], I, P);
+    ps.a.mout = ps.a.min;
+    ps.a.log2M = l[i] + log2ll(R[i]);
+    set_klow(ps.a, i + 1, l);
+    ps.in_role = i == 0 ? ROLE_USER_IN : ROLE_SCRATCH;
+    ps.out_role = ROLE_SCRATCH;
+    if (i == 0) ps.a.load_kind = d->in_dtype == PBK_I8X2 ? LOAD_I8X2 : LOAD_C64;
+    ps.fast = fast_ok;
+    ts.ensure(l[i]);
+    pl->passes.push_back(ps);
+  }
+  // middle
+  {
+    const int i = m - 1;
+    Pass ps;
+    defaults(ps.a);
+    ps.mode = MODE_MID;
+    set_geometry(ps, l[i], Kprev[i] * I, I, (int)I, P, log2ll(Kprev[i]));
+    ps.a.min = plain_map(1ll << l[i], 1, I, P);
+    ps.a.mout = ps.a.min;
+    set_klow(ps.a, i + 1, l);
+    ps.a.log2Kmul = log2ll(Kprev[i]);
+    ps.a.chirp_kind = d->explicit_chirp ? CHIRP_ARRAY : CHIRP_COMPUTED;
+    ps.a.N = N;
+    {
+      const double dt = 1.0 / d->sample_rate_hz;      // Signal.dt, core.py:250-253
+      ps.a.df = 1.0 / ((double)N * dt);               // numpy fftfreq: val = 1/(n*d)
+      if (std::isinf(d->ref_freq_hz)) { ps.a.fr_sub = 0; ps.a.inv_fr = 0; ps.a.a0 = -1.0; }
+      else { ps.a.fr_sub = d->ref_freq_hz; ps.a.inv_fr = 1.0 / d->ref_freq_hz; ps.a.a0 = 0; }
+      ps.a.D = (1.0 / 2.41e-4) * d->dm * 1e12;        // dedispersion.py:30,46 in Hz^2 s
+    }
+    ps.a.scale = (float)(1.0 / (double)N);
+    ps.a.chirp_sk = C;
+    ps.a.chirp_sc = 1;
+    ps.in_role = m == 1 ? ROLE_USER_IN : ROLE_SCRATCH;
+    ps.out_role = ROLE_SCRATCH;
+    if (m == 1) {
+      ps.a.load_kind = d->in_dtype == PBK_I8X2 ? LOAD_I8X2 : LOAD_C64;
+      final_epilogue(ps, 0);
+    }
+    ps.fast = fast_ok;
+    ts.ensure(l[i]);
+    pl->passes.push_back(ps);
+  }
+  // inverse levels m-1..1
+  for (int i = m - 2; i >= 0; --i) {
+    Pass ps;
+    defaults(ps.a);
+    ps.mode = MODE_INV;
+    set_geometry(ps, l[i], Kprev[i] * R[i] * I, R[i] * I, (int)I, P, log2ll(Kprev[i]));
+    ps.a.min = plain_map(1ll << l[i], R[i], I, P);
+    ps.a.mout = ps.a.min;
+    ps.a.log2M = l[i] + log2ll(R[i]);
+    set_klow(ps.a, i + 1, l);
+    ps.in_role = ROLE_SCRATCH;
+    ps.out_role = ROLE_SCRATCH;
+    if (i == 0) final_epilogue(ps, 0);
+    ps.fast = fast_ok;
+    pl->passes.push_back(ps);
+  }
+
+  int rc = PBK_OK;
+  auto cleanup = [&](int code) { pbk_plan_destroy(pl); return code; };
+  if ((rc = upload_tables(pl, ts)) != PBK_OK) return cleanup(rc);
+  {
+    cudaError_t e = cudaMalloc(&pl->d_chanfreq, (size_t)C * sizeof(double));
+    if (e == cudaSuccess)
+      e = cudaMemcpy(pl->d_chanfreq, d->chan_freq_hz, (size_t)C * sizeof(double),
+                     cudaMemcpyHostToDevice);
+    if (e != cudaSuccess)
+      return cleanup(fail(PBK_ERR_CUDA, "chan_freq upload: %s", cudaGetErrorString(e)));
+  }
+  if (m > 1) {
+    pl->scratch_bytes = (size_t)N * I * 8;
+    cudaError_t e = cudaMalloc(&pl->scratch, pl->scratch_bytes);
+    if (e != cudaSuccess)
+      return cleanup(fail(PBK_ERR_NOMEM, "scratch (%zu bytes): %s", pl->scratch_bytes,
+                          cudaGetErrorString(e)));
+  }
+  if (d->downsample > 1 && crop_rows > 0) {
+    pl->tmpf_bytes = (size_t)crop_rows * pl->row_elems * 4;
+    cudaError_t e = cudaMalloc(&pl->d_tmpf, pl->tmpf_bytes);
+    if (e != cudaSuccess)
+      return cleanup(fail(PBK_ERR_NOMEM, "downsample buffer (%zu bytes): %s", pl->tmpf_bytes,
+                          cudaGetErrorString(e)));
+  }
+  for (auto& ps : pl->passes) ps.a.chan_freq = pl->d_chanfreq;
+  pl->launches = (int)pl->passes.size() + (d->downsample > 1 ? 1 : 0);
+  *out = pl;
+  return PBK_OK;
+}
+
+extern "C" int pbk_dedisp_out_shape(const pbk_plan* pl, int64_t* rows, int64_t* row_elems,
+                                    int64_t* elem_bytes) {
+  if (!pl || pl->kind != PLAN_DEDISP) return fail(PBK_ERR_INVALID, "not a dedispersion plan");
+  if (rows) *rows = pl->out_rows;
+  if (row_elems) *row_elems = pl->row_elems;
+  if (elem_bytes) *elem_bytes = pl->elem_bytes;
+  return PBK_OK;
+}
+
+static void* role_ptr(const pbk_plan* pl, int role, const void* uin, void* uout) {
+  switch (role) {
+    case ROLE_USER_IN: return const_cast<void*>(uin);
+    case ROLE_SCRATCH: return pl->scratch;
+    case ROLE_USER_OUT: return uout;
+    default: return pl->d_tmpf;
+  }
+}
+
+static int run_passes(pbk_plan* pl, const void* d_in, void* d_out, const void* d_chirp,
+                      cudaStream_t st) {
+  for (auto& ps : pl->passes) {
+    Pass p = ps;
+    p.a.in = role_ptr(pl, ps.in_role, d_in, d_out);
+    p.a.out = role_ptr(pl, ps.out_role, d_in, d_out);
+    p.a.chirp_arr = reinterpret_cast<const float2*>(d_chirp);
+    const bool aligned = (((uintptr_t)p.a.in | (uintptr_t)p.a.out) & 15) == 0;
+    cudaError_t e = launch_pass(p, ps.fast && aligned, st);
+    if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
+  }
+  return PBK_OK;
+}
+
+extern "C" int pbk_dedisp_exec_device(pbk_plan* pl, const void* d_in, void* d_out,
+                                      const void* d_chirp, void* stream) {
+  if (!pl || pl->kind != PLAN_DEDISP) return fail(PBK_ERR_INVALID, "not a dedispersion plan");
+  if (!d_in) return fail(PBK_ERR_INVALID, "input pointer is NULL");
+  if (pl->desc.explicit_chirp && !d_chirp) return fail(PBK_ERR_INVALID, "plan expects a chirp");
+  if (pl->out_rows == 0) return PBK_OK;  // empty crop (dedispersion.py:130-133 returns no rows)
+  if (!d_out) return fail(PBK_ERR_INVALID, "output pointer is NULL");
+  CUDA_TRY(cudaSetDevice(pl->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = run_passes(pl, d_in, d_out, d_chirp, st);
+  if (rc != PBK_OK) return rc;
+  if (pl->desc.downsample > 1) {
+    cudaError_t e = launch_downsample(reinterpret_cast<const float*>(pl->d_tmpf),
+                                      reinterpret_cast<float*>(d_out), pl->out_rows,
+                                      pl->row_elems, pl->desc.downsample, st);
+    if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "downsample launch: %s", cudaGetErrorString(e));
+  }
+  return PBK_OK;
+}
+
+static int ensure_buf(void** p, size_t bytes) {
+  if (*p || bytes == 0) return PBK_OK;
+  CUDA_TRY(cudaMalloc(p, bytes));
+  return PBK_OK;
+}
+
+extern "C" int pbk_dedisp_exec_host(pbk_plan* pl, const void* in, void* out, const void* chirp) {
+  if (!pl || pl->kind != PLAN_DEDISP) return fail(PBK_ERR_INVALID, "not a dedispersion plan");
+  if (!in) return fail(PBK_ERR_INVALID, "input pointer is NULL");
+  if (pl->desc.explicit_chirp && !chirp) return fail(PBK_ERR_INVALID, "plan expects a chirp");
+  if (pl->out_rows == 0) return PBK_OK;
+  if (!out) return fail(PBK_ERR_INVALID, "output pointer is NULL");
+  std::lock_guard<std::mutex> lock(pl->mu);
+  CUDA_TRY(cudaSetDevice(pl->device));
+  int rc;
+  if ((rc = ensure_buf(&pl->h_din, pl->in_bytes)) != PBK_OK) return rc;
+  if ((rc = ensure_buf(&pl->h_dout, pl->out_bytes)) != PBK_OK) return rc;
+  if ((rc = ensure_buf(&pl->h_dchirp, pl->chirp_bytes)) != PBK_OK) return rc;
+  cudaStream_t st = cudaStreamPerThread;
+  CUDA_TRY(cudaMemcpyAsync(pl->h_din, in, pl->in_bytes, cudaMemcpyHostToDevice, st));
+  if (pl->chirp_bytes)
+    CUDA_TRY(cudaMemcpyAsync(pl->h_dchirp, chirp, pl->chirp_bytes, cudaMemcpyHostToDevice, st));
+  rc = pbk_dedisp_exec_device(pl, pl->h_din, pl->h_dout, pl->h_dchirp, st);
+  if (rc != PBK_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(out, pl->h_dout, pl->out_bytes, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return PBK_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// FFT / STFT plans (forward-structured passes only)
+// ------------------------------------------------------------------------------------------
+struct ExtMap {  // external array addressing: o*eo + idx*ei + c*ec + p*ep
+  long long eo, ei, ec, ep;
+};
+
+static int build_fft_plan(long long O, long long n, long long C, long long P, bool inverse,
+                          ExtMap in, ExtMap outm, float scale, bool shift_out, bool shift_in,
+                          int device, pbk_plan** out) {
+  *out = nullptr;
+  const int ln = ilog2_exact(n);
+  if (ln < 1)
+    return fail(PBK_ERR_UNSUPPORTED,
+                "transform length %lld: this build handles power-of-two lengths >= 2 only",
+                (long long)n);
+  int l[3] = {0, 0, 0};
+  const int m = choose_levels(ln, l, false);
+  if (m == 0) return fail(PBK_ERR_UNSUPPORTED, "transform length 2^%d is too long", ln);
+  const long long I = C * P;
+  if (I > INT_MAX / 2 || O <= 0 || I <= 0) return fail(PBK_ERR_INVALID, "bad batch shape");
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev)
+    return fail(PBK_ERR_CUDA, "device %d not available (%d CUDA devices)", device, ndev);
+  CUDA_TRY(cudaSetDevice(device));
+
+  pbk_plan* pl = new pbk_plan();
+  pl->kind = PLAN_FFT;
+  pl->device = device;
+  pl->nlevels = m;
+  for (int i = 0; i < m; ++i) pl->level_log2[i] = l[i];
+  pl->in_bytes = (size_t)O * n * I * 8;
+  pl->out_bytes = pl->in_bytes;
+  TableSet ts;
+  long long Kprev[3], R[3];
+  {
+    long long k = 1;
+    for (int i = 0; i < m; ++i) { Kprev[i] = k; k <<= l[i]; }
+    long long r = 1;
+    for (int i = m - 1; i >= 0; --i) { R[i] = r; r <<= l[i]; }
+  }
+  auto log2ll = [](long long v) { int s = 0; while ((1ll << s) < v) ++s; return s; };
+  for (int i = 0; i < m; ++i) {
+    Pass ps;
+    defaults(ps.a);
+    ps.mode = MODE_FWD;
+    ps.signinv = inverse;
+    ps.a.sign = inverse ? +1 : -1;
+    set_geometry(ps, l[i], O * Kprev[i] * R[i] * I, R[i] * I, (int)I, (int)P, log2ll(Kprev[i]));
+    AddrMap pm = plain_map(1ll << l[i], R[i], I, P);
+    pm.a_o = n * I;
+    ps.a.min = pm;
+    ps.a.mout = pm;
+    if (i == 0) {
+      AddrMap& a = ps.a.min;
+      a.a_o = in.eo; a.a_kp = 0; a.a_kl = 0; a.a_n = in.ei; a.a_c = in.ec; a.a_p = in.ep;
+      a.a_row = R[0] * in.ei;
+      if (shift_in) ps.a.fxor = 1 << (l[0] - 1);
+    }
+    if (i == m - 1) {
+      AddrMap& a = ps.a.mout;
+      a.a_o = outm.eo; a.a_kp = 0; a.a_kl = outm.ei; a.a_n = 0; a.a_c = outm.ec; a.a_p = outm.ep;
+      a.a_row = Kprev[i] * outm.ei;
+      ps.a.scale = scale;
+      if (shift_out) ps.a.kxor = 1 << (l[i] - 1);
+    }
+    ps.a.log2M = i == m - 1 ? 0 : l[i] + log2ll(R[i]);
+    set_klow(ps.a, i + 1, l);
+    ps.in_role = i == 0 ? ROLE_USER_IN : ROLE_SCRATCH;
+    ps.out_role = i == m - 1 ? ROLE_USER_OUT : ROLE_SCRATCH;
+    ps.fast = (I % 2 == 0) && map_even(ps.a.min, P) && map_even(ps.a.mout, P) &&
+              ((O * Kprev[i] * R[i] * I) % 2 == 0);
+    ts.ensure(l[i]);
+    pl->passes.push_back(ps);
+  }
+  int rc = upload_tables(pl, ts);
+  if (rc != PBK_OK) { pbk_plan_destroy(pl); return rc; }
+  if (m > 1) {
+    pl->scratch_bytes = (size_t)O * n * I * 8;
+    cudaError_t e = cudaMalloc(&pl->scratch, pl->scratch_bytes);
+    if (e != cudaSuccess) {
+      pbk_plan_destroy(pl);
+      return fail(PBK_ERR_NOMEM, "scratch (%zu bytes): %s", (size_t)O * n * I * 8,
+                  cudaGetErrorString(e));
+    }
+  }
+  pl->launches = (int)pl->passes.size();
+  *out = pl;
+  return PBK_OK;
+}
+
+extern "C" int pbk_fft_plan_create(int64_t outer, int64_t n, int64_t inner, int32_t inverse,
+                                   int32_t device, pbk_plan** plan) {
+  if (!plan) return fail(PBK_ERR_INVALID, "plan is NULL");
+  if (outer <= 0 || n <= 0 || inner <= 0) return fail(PBK_ERR_INVALID, "shape must be positive");
+  ExtMap in{n * inner, inner, 1, 0};
+  ExtMap om{n * inner, inner, 1, 0};
+  const float scale = inverse ? (float)(1.0 / (double)n) : 1.0f;
+  return build_fft_plan(outer, n, inner, 1, inverse != 0, in, om, scale, false, false, device,
+                        plan);
+}
+
+extern "C" int pbk_stft_plan_create(int64_t nseg, int64_t nperseg, int64_t nchan, int64_t npol,
+                                    int32_t inverse, int32_t device, pbk_plan** plan) {
+  if (!plan) return fail(PBK_ERR_INVALID, "plan is NULL");
+  if (nseg <= 0 || nperseg <= 0 || nchan <= 0 || npol <= 0)
+    return fail(PBK_ERR_INVALID, "shape must be positive");
+  const long long n = nperseg, C = nchan, P = npol;
+  if (!inverse) {
+    // in[(s*n + t), c, p] ; out[s, c*n + shift(k), p] ; scale 1/n   (misc.py:41-52)
+    ExtMap in{n * C * P, C * P, P, 1};
+    ExtMap om{C * n * P, P, n * P, 1};
+    return build_fft_plan(nseg, n, C, P, false, in, om, (float)(1.0 / (double)n), true, false,
+                          device, plan);
+  }
+  // in[s, c*n + k', p] with ifftshift ; out[(s*n + t), c, p] ; (x*n) then ifft => unit scale
+  ExtMap in{C * n * P, P, n * P, 1};
+  ExtMap om{n * C * P, C * P, P, 1};
+  return build_fft_plan(nseg, n, C, P, true, in, om, 1.0f, false, true, device, plan);
+}
+
+extern "C" int pbk_fft_exec_device(pbk_plan* pl, const void* d_in, void* d_out, void* stream) {
+  if (!pl || pl->kind != PLAN_FFT) return fail(PBK_ERR_INVALID, "not an FFT plan");
+  if (!d_in || !d_out) return fail(PBK_ERR_INVALID, "NULL data pointer");
+  if (d_in == d_out && pl->passes.size() == 1)
+    return fail(PBK_ERR_INVALID, "single-pass transforms cannot run in place");
+  CUDA_TRY(cudaSetDevice(pl->device));
+  return run_passes(pl, d_in, d_out, nullptr, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int pbk_fft_exec_host(pbk_plan* pl, const void* in, void* out) {
+  if (!pl || pl->kind != PLAN_FFT) return fail(PBK_ERR_INVALID, "not an FFT plan");
+  if (!in || !out) return fail(PBK_ERR_INVALID, "NULL data pointer");
+  std::lock_guard<std::mutex> lock(pl->mu);
+  CUDA_TRY(cudaSetDevice(pl->device));
+  int rc;
+  if ((rc = ensure_buf(&pl->h_din, pl->in_bytes)) != PBK_OK) return rc;
+  if ((rc = ensure_buf(&pl->h_dout, pl->out_bytes)) != PBK_OK) return rc;
+  cudaStream_t st = cudaStreamPerThread;
+  CUDA_TRY(cudaMemcpyAsync(pl->h_din, in, pl->in_bytes, cudaMemcpyHostToDevice, st));
+  rc = pbk_fft_exec_device(pl, pl->h_din, pl->h_dout, st);
+  if (rc != PBK_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(out, pl->h_dout, pl->out_bytes, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return PBK_OK;
+}
+
+extern "C" void pbk_plan_destroy(pbk_plan* pl) {
+  if (!pl) return;
+  cudaSetDevice(pl->device);
+  cudaFree(pl->scratch);
+  cudaFree(pl->d_tw);
+  cudaFree(pl->d_chanfreq);
+  cudaFree(pl->d_tmpf);
+  cudaFree(pl->h_din);
+  cudaFree(pl->h_dout);
+  cudaFree(pl->h_dchirp);
+  delete pl;
+}
+
+extern "C" int pbk_plan_info(const pbk_plan* pl, int32_t* launches, int64_t* workspace_bytes,
+                             int32_t* levels, int32_t* level_log2) {
+  if (!pl) return fail(PBK_ERR_INVALID, "plan is NULL");
+  if (launches) *launches = pl->launches;
+  if (workspace_bytes) *workspace_bytes = (int64_t)(pl->scratch_bytes + pl->tmpf_bytes);
+  if (levels) *levels = pl->nlevels;
+  if (level_log2)
+    for (int i = 0; i < 3; ++i) level_log2[i] = pl->level_log2[i];
+  return PBK_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// detection, downsample, fold
+// ------------------------------------------------------------------------------------------
+struct DevBuf {  // RAII staging for the host-pointer variants
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+};
+
+extern "C" int pbk_detect(const void* in, void* out, int64_t nsamp, int64_t nchan, int64_t npol,
+                          int32_t out_kind, int64_t downsample, int32_t on_device, int32_t device,
+                          void* stream) {
+  if (!in || !out) return fail(PBK_ERR_INVALID, "NULL data pointer");
+  if (nsamp <= 0 || nchan <= 0 || npol <= 0 || downsample < 1)
+    return fail(PBK_ERR_INVALID, "bad shape");
+  if (out_kind != PBK_OUT_INTENSITY && out_kind != PBK_OUT_STOKES_I)
+    return fail(PBK_ERR_INVALID, "out_kind must be INTENSITY or STOKES_I");
+  if (out_kind == PBK_OUT_STOKES_I && npol != 2) return fail(PBK_ERR_INVALID, "Stokes I needs npol == 2");
+  CUDA_TRY(cudaSetDevice(device));
+  const long long rows = nsamp / downsample;
+  const long long relems = out_kind == PBK_OUT_STOKES_I ? nchan : nchan * npol;
+  if (rows == 0) return PBK_OK;
+  if (on_device) {
+    cudaError_t e = launch_detect(reinterpret_cast<const float2*>(in), reinterpret_cast<float*>(out),
+                                  rows, nchan * npol, out_kind == PBK_OUT_STOKES_I, downsample,
+                                  reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "detect launch: %s", cudaGetErrorString(e));
+    return PBK_OK;
+  }
+  DevBuf di, dout;
+  const size_t ib = (size_t)rows * downsample * nchan * npol * 8, ob = (size_t)rows * relems * 4;
+  CUDA_TRY(cudaMalloc(&di.p, ib));
+  CUDA_TRY(cudaMalloc(&dout.p, ob));
+  cudaStream_t st = cudaStreamPerThread;
+  CUDA_TRY(cudaMemcpyAsync(di.p, in, ib, cudaMemcpyHostToDevice, st));
+  cudaError_t e = launch_detect(reinterpret_cast<const float2*>(di.p), reinterpret_cast<float*>(dout.p),
+                                rows, nchan * npol, out_kind == PBK_OUT_STOKES_I, downsample, st);
+  if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "detect launch: %s", cudaGetErrorString(e));
+  CUDA_TRY(cudaMemcpyAsync(out, dout.p, ob, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return PBK_OK;
+}
+
+extern "C" int pbk_downsample(const void* in, void* out, int64_t nsamp, int64_t row_elems,
+                              int64_t factor, int32_t on_device, int32_t device, void* stream) {
+  if (!in || !out) return fail(PBK_ERR_INVALID, "NULL data pointer");
+  if (nsamp <= 0 || row_elems <= 0 || factor < 1) return fail(PBK_ERR_INVALID, "bad shape");
+  CUDA_TRY(cudaSetDevice(device));
+  const long long rows = nsamp / factor;
+  if (rows == 0) return PBK_OK;
+  if (on_device) {
+    cudaError_t e = launch_downsample(reinterpret_cast<const float*>(in), reinterpret_cast<float*>(out),
+                                      rows, row_elems, factor, reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "downsample launch: %s", cudaGetErrorString(e));
+    return PBK_OK;
+  }
+  DevBuf di, dout;
+  const size_t ib = (size_t)rows * factor * row_elems * 4, ob = (size_t)rows * row_elems * 4;
+  CUDA_TRY(cudaMalloc(&di.p, ib));
+  CUDA_TRY(cudaMalloc(&dout.p, ob));
+  cudaStream_t st = cudaStreamPerThread;
+  CUDA_TRY(cudaMemcpyAsync(di.p, in, ib, cudaMemcpyHostToDevice, st));
+  cudaError_t e = launch_downsample(reinterpret_cast<const float*>(di.p), reinterpret_cast<float*>(dout.p),
+                                    rows, row_elems, factor, st);
+  if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "downsample launch: %s", cudaGetErrorString(e));
+  CUDA_TRY(cudaMemcpyAsync(out, dout.p, ob, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return PBK_OK;
+}
+
+extern "C" int pbk_fold(const void* in, int64_t nsamp, int64_t row_elems, const double* coeffs,
+                        int32_t ncoef, double sample_rate_hz, int64_t n0, int32_t nbin,
+                        void* profile, void* counts, void* bins_out, int32_t on_device,
+                        int32_t device, void* stream) {
+  if (!in || !profile || !counts || !coeffs) return fail(PBK_ERR_INVALID, "NULL pointer");
+  if (nsamp <= 0 || row_elems <= 0 || nbin <= 0) return fail(PBK_ERR_INVALID, "bad shape");
+  if (ncoef < 1 || ncoef > kFoldMaxCoef)
+    return fail(PBK_ERR_INVALID, "ncoef must be in [1, %d]", kFoldMaxCoef);
+  if (!(sample_rate_hz > 0)) return fail(PBK_ERR_INVALID, "sample_rate_hz must be > 0");
+  CUDA_TRY(cudaSetDevice(device));
+  FoldArgs fa;
+  memset(&fa, 0, sizeof(fa));
+  for (int i = 0; i < ncoef; ++i) fa.coef[i] = coeffs[i];
+  fa.ncoef = ncoef;
+  fa.sample_rate = sample_rate_hz;
+  fa.n0 = n0;
+  fa.nbin = nbin;
+  fa.nsamp = nsamp;
+  fa.row_elems = row_elems;
+  if (on_device) {
+    fa.in = reinterpret_cast<const float*>(in);
+    fa.profile = reinterpret_cast<float*>(profile);
+    fa.counts = reinterpret_cast<unsigned long long*>(counts);
+    fa.bins_out = reinterpret_cast<int*>(bins_out);
+    cudaError_t e = launch_fold(fa, reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "fold launch: %s", cudaGetErrorString(e));
+    return PBK_OK;
+  }
+  DevBuf di, dp, dc, db;
+  const size_t ib = (size_t)nsamp * row_elems * 4, pb = (size_t)nbin * row_elems * 4,
+               cb = (size_t)nbin * 8, bb = (size_t)nsamp * 4;
+  CUDA_TRY(cudaMalloc(&di.p, ib));
+  CUDA_TRY(cudaMalloc(&dp.p, pb));
+  CUDA_TRY(cudaMalloc(&dc.p, cb));
+  if (bins_out) CUDA_TRY(cudaMalloc(&db.p, bb));
+  cudaStream_t st = cudaStreamPerThread;
+  CUDA_TRY(cudaMemcpyAsync(di.p, in, ib, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(dp.p, profile, pb, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(dc.p, counts, cb, cudaMemcpyHostToDevice, st));
+  fa.in = reinterpret_cast<const float*>(di.p);
+  fa.profile = reinterpret_cast<float*>(dp.p);
+  fa.counts = reinterpret_cast<unsigned long long*>(dc.p);
+  fa.bins_out = reinterpret_cast<int*>(db.p);
+  cudaError_t e = launch_fold(fa, st);
+  if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "fold launch: %s", cudaGetErrorString(e));
+  CUDA_TRY(cudaMemcpyAsync(profile, dp.p, pb, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(counts, dc.p, cb, cudaMemcpyDeviceToHost, st));
+  if (bins_out) CUDA_TRY(cudaMemcpyAsync(bins_out, db.p, bb, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return PBK_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// raw memory helpers
+// ------------------------------------------------------------------------------------------
+extern "C" int pbk_malloc(void** dptr, size_t bytes, int32_t device) {
+  if (!dptr) return fail(PBK_ERR_INVALID, "dptr is NULL");
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaMalloc(dptr, bytes ? bytes : 1));
+  return PBK_OK;
+}
+extern "C" int pbk_free(void* dptr, int32_t device) {
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaFree(dptr));
+  return PBK_OK;
+}
+extern "C" int pbk_memcpy_h2d(void* dst, const void* src, size_t bytes, int32_t device) {
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+  return PBK_OK;
+}
+extern "C" int pbk_memcpy_d2h(void* dst, const void* src, size_t bytes, int32_t device) {
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  return PBK_OK;
+}
+extern "C" int pbk_device_sync(int32_t device) {
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  return PBK_OK;
+}

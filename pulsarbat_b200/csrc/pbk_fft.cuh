@@ -1,0 +1,732 @@
+// pbk_fft.cuh -- sm_100a tile-FFT pass kernels for the pulsarbat baseband hot path.
+//
+// What this replaces in the reference (paths under /root/reference/pulsarbat):
+//   transforms/dedispersion.py:125   x = ifft(fft(z.data, axis=0) * chirp, axis=0)
+//   transforms/dedispersion.py:19-23 _transfer_function (the chirp; here generated in registers)
+//   fft.py:30-48                      pb.fft.fft / ifft (axis-0, batch-innermost c64 transforms)
+//   contrib/misc.py:43-52, 81-91      stft / istft (segment FFT + fftshift + scale)
+//   core.py:766-774, 944-948          re^2+im^2 and Stokes I (fused into the last inverse pass)
+//
+// Design:
+//  * A length-N transform (N = 2^n) along the slow axis of a (O, N, I) array is split into
+//    m levels N = L1*L2*..*Lm.  Level l transforms the index with the largest remaining stride;
+//    each CTA owns one tile = L points x W adjacent "lanes" (lanes = flattened (outer, inner)
+//    index, adjacent lanes are adjacent in memory), so every global access is a W*8-byte chunk.
+//  * Forward levels are decimation-in-frequency (butterfly, then twiddle), the inverse levels
+//    are the mirrored decimation-in-time graph (conj twiddle, then butterfly).  Because the
+//    graphs are mirrors, nothing is ever reordered: the last forward stage leaves 16 spectral
+//    points in registers, the chirp is applied there, and the first inverse stage consumes the
+//    same registers.  fft * H * ifft for a tile is ONE kernel (MODE_MID).
+//  * Each thread owns a PAIR of adjacent lanes and keeps (re0,re1) and (im0,im1) in aligned
+//    64-bit register pairs, so every add/mul/fma is a packed FADD2/FMUL2/FFMA2 (sm_100 needs
+//    the packed forms to reach its FP32 rate); twiddles are shared by both lanes when the pair
+//    is "uniform" (same inner time offset / same channel), which is the case for pol pairs.
+//  * Stages are radix-16 (first stage radix 2/4/8/16 to absorb log2(L) mod 4); between stages
+//    the tile lives in shared memory as float4 {re0,re1,im0,im1} with an XOR swizzle that makes
+//    every LDS.128/STS.128 conflict-free for all strides.
+//  * The chirp phase is evaluated in FP64 in cycles with the cancellation-free form
+//    D*((f-fr)/fr)^2/f, reduced mod 1 exactly (phi - rint(phi)), then sincospif in FP32.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pbk {
+
+enum { MODE_FWD = 0, MODE_MID = 1, MODE_INV = 2 };
+enum { LOAD_C64 = 0, LOAD_I8X2 = 1 };
+enum { EPI_C64 = 0, EPI_INTENSITY = 1, EPI_STOKES_I = 2 };
+enum { CHIRP_NONE = 0, CHIRP_COMPUTED = 1, CHIRP_ARRAY = 2 };
+
+constexpr int kThreads = 256;
+constexpr int kMaxStages = 4;
+
+// element index = o_orig*a_o + kprev*a_kp + klow*a_kl + nrest*a_n + (col / P)*a_c + (col % P)*a_p
+//                 + row * a_row
+struct AddrMap {
+  long long a_o, a_kp, a_kl, a_n, a_c, a_p, a_row;
+};
+
+struct PassArgs {
+  const void* in;
+  void* out;
+  AddrMap min, mout;
+  long long Q;        // number of lanes = O_level * RI
+  long long RI;       // inner extent at this level (R * I)
+  int I;              // innermost batch (nchan * npol)
+  int P;              // npol (channel = col / P)
+  int log2L;          // tile transform length
+  int nstages;        // ceil(log2L / 4)
+  int log2r1;         // radix of the first stage (others are 16)
+  int log2pw;         // lane pairs per tile
+  int log2Kprev;      // o = (o_orig << log2Kprev) | kprev
+  int kl_sa, kl_mb, kl_sb;  // klow = (kprev >> kl_sa) + ((kprev & kl_mb) << kl_sb)
+  int log2M;          // inter-level twiddle modulus (0 = none): W_M^(nrest * k)
+  int sign;           // FWD mode only: -1 forward, +1 inverse exponent
+  const float2* stage_tw;           // per-stage twiddle tables, (cos, -sin)
+  int stage_tw_off[kMaxStages];     // offsets (in float2) of each stage's table
+  float scale;        // applied with the chirp (MID) or at the store (FWD)
+  int load_kind, epi_kind;
+  int fxor, kxor;     // ifftshift on load rows / fftshift on store rows (tile-level index xor)
+  long long crop_start, crop_stop, n_mul;   // epilogue: n = row*n_mul + nrest, keep [start,stop)
+  // chirp
+  int chirp_kind;
+  int log2Kmul;       // kfull = klow + (k << log2Kmul)
+  long long N;        // full transform length (for fftfreq sign wrap)
+  const double* chan_freq;   // Hz, per channel
+  double df, fr_sub, inv_fr, a0, D;
+  const float2* chirp_arr;
+  long long chirp_sk, chirp_sc;
+};
+
+// ------------------------------------------------------------------------------------------
+// packed pair arithmetic
+// ------------------------------------------------------------------------------------------
+struct c2 {
+  float2 re, im;
+};
+
+__device__ __forceinline__ float2 p_add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 p_sub(float2 a, float2 b) {
+  return __fadd2_rn(a, make_float2(-b.x, -b.y));
+}
+__device__ __forceinline__ float2 p_mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 p_fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 p_neg(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 p_bc(float a) { return make_float2(a, a); }
+
+__device__ __forceinline__ c2 operator+(c2 a, c2 b) { return {p_add(a.re, b.re), p_add(a.im, b.im)}; }
+__device__ __forceinline__ c2 operator-(c2 a, c2 b) { return {p_sub(a.re, b.re), p_sub(a.im, b.im)}; }
+
+// x * (c + i s) with per-lane (c, s)
+__device__ __forceinline__ c2 cmul(c2 x, float2 c, float2 s) {
+  c2 r;
+  r.re = p_fma(x.re, c, p_neg(p_mul(x.im, s)));
+  r.im = p_fma(x.im, c, p_mul(x.re, s));
+  return r;
+}
+
+template <bool INV>
+__device__ __forceinline__ void bf4(c2& x0, c2& x1, c2& x2, c2& x3) {
+  c2 a0 = x0 + x2, a1 = x0 - x2, a2 = x1 + x3, a3 = x1 - x3;
+  x0 = a0 + a2;
+  x2 = a0 - a2;
+  if (!INV) {  // a3 * (-i)
+    x1.re = p_add(a1.re, a3.im); x1.im = p_sub(a1.im, a3.re);
+    x3.re = p_sub(a1.re, a3.im); x3.im = p_add(a1.im, a3.re);
+  } else {     // a3 * (+i)
+    x1.re = p_sub(a1.re, a3.im); x1.im = p_add(a1.im, a3.re);
+    x3.re = p_add(a1.re, a3.im); x3.im = p_sub(a1.im, a3.re);
+  }
+}
+
+template <bool INV>
+__device__ __forceinline__ c2 mul_const(c2 x, float c, float s_fwd) {
+  // s_fwd is the imaginary part for the forward sign; inverse conjugates
+  const float s = INV ? -s_fwd : s_fwd;
+  return cmul(x, p_bc(c), p_bc(s));
+}
+
+template <int R, bool INV>
+struct Butterfly;
+
+template <bool INV>
+struct Butterfly<2, INV> {
+  static __device__ __forceinline__ void run(c2* v) {
+    c2 t = v[0];
+    v[0] = t + v[1];
+    v[1] = t - v[1];
+  }
+};
+
+template <bool INV>
+struct Butterfly<4, INV> {
+  static __device__ __forceinline__ void run(c2* v) { bf4<INV>(v[0], v[1], v[2], v[3]); }
+};
+
+template <bool INV>
+struct Butterfly<8, INV> {
+  static __device__ __forceinline__ void run(c2* v) {
+    constexpr float h = 0.70710678118654752440f;
+    bf4<INV>(v[0], v[2], v[4], v[6]);  // E0..E3 in v0,v2,v4,v6
+    bf4<INV>(v[1], v[3], v[5], v[7]);  // O0..O3 in v1,v3,v5,v7
+    c2 o1 = mul_const<INV>(v[3], h, -h);
+    c2 o2;
+    if (!INV) { o2.re = v[5].im; o2.im = p_neg(v[5].re); }
+    else      { o2.re = p_neg(v[5].im); o2.im = v[5].re; }
+    c2 o3 = mul_const<INV>(v[7], -h, -h);
+    c2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1];
+    v[0] = e0 + o0; v[4] = e0 - o0;
+    v[1] = e1 + o1; v[5] = e1 - o1;
+    v[2] = e2 + o2; v[6] = e2 - o2;
+    v[3] = e3 + o3; v[7] = e3 - o3;
+  }
+};
+
+template <bool INV>
+struct Butterfly<16, INV> {
+  static __device__ __forceinline__ void run(c2* v) {
+    constexpr float C1 = 0.92387953251128675613f;  // cos(pi/8)
+    constexpr float S1 = 0.38268343236508977173f;  // sin(pi/8)
+    constexpr float h = 0.70710678118654752440f;
+    // x[4a+b]: DFT4 over a for each b -> t[b][c] at v[4c+b]
+#pragma unroll
+    for (int b = 0; b < 4; ++b) bf4<INV>(v[b], v[4 + b], v[8 + b], v[12 + b]);
+    // twiddle t[b][c] *= w16^(b*c)
+    v[4 * 1 + 1] = mul_const<INV>(v[4 * 1 + 1], C1, -S1);   // e=1
+    v[4 * 2 + 1] = mul_const<INV>(v[4 * 2 + 1], h, -h);     // e=2
+    v[4 * 3 + 1] = mul_const<INV>(v[4 * 3 + 1], S1, -C1);   // e=3
+    v[4 * 1 + 2] = mul_const<INV>(v[4 * 1 + 2], h, -h);     // e=2
+    {                                                       // e=4 : -i (fwd) / +i (inv)
+      c2 t = v[4 * 2 + 2];
+      if (!INV) { v[4 * 2 + 2].re = t.im; v[4 * 2 + 2].im = p_neg(t.re); }
+      else      { v[4 * 2 + 2].re = p_neg(t.im); v[4 * 2 + 2].im = t.re; }
+    }
+    v[4 * 3 + 2] = mul_const<INV>(v[4 * 3 + 2], -h, -h);    // e=6
+    v[4 * 1 + 3] = mul_const<INV>(v[4 * 1 + 3], S1, -C1);   // e=3
+    v[4 * 2 + 3] = mul_const<INV>(v[4 * 2 + 3], -h, -h);    // e=6
+    v[4 * 3 + 3] = mul_const<INV>(v[4 * 3 + 3], -C1, S1);   // e=9
+    // DFT4 over b for each c -> y[c + 4d] at v[4c+d]
+#pragma unroll
+    for (int c = 0; c < 4; ++c) bf4<INV>(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    // transpose to natural order: out[c + 4d] = v[4c + d]
+    c2 t[16];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int d = 0; d < 4; ++d) t[c + 4 * d] = v[4 * c + d];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = t[i];
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// exact twiddle  w = exp(-2*pi*i * e / 2^log2M)  -> (cos, -sin)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 unit_root(unsigned long long e, int log2M) {
+  const long long M = 1ll << log2M;
+  long long es = (long long)(e & (unsigned long long)(M - 1));
+  if (es >= (M >> 1)) es -= M;
+  // x = 2*es/M in [-1, 1): exact for |es| < 2^24, 1 ulp of the index otherwise
+  const float x = (float)es * __int_as_float((127 - (log2M - 1)) << 23);
+  float s, c;
+  sincospif(x, &s, &c);
+  return make_float2(c, -s);
+}
+
+__device__ __forceinline__ float2 cmul1(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// ------------------------------------------------------------------------------------------
+// per-thread lane context
+// ------------------------------------------------------------------------------------------
+struct LaneCtx {
+  long long bin[2], bout[2];   // element offsets (without the row term)
+  unsigned int nrest[2];
+  int chan[2];
+  unsigned int klow;           // same for both lanes when FAST; generic path recomputes per lane
+  unsigned int klow1;
+  bool valid[2];
+};
+
+__device__ __forceinline__ long long map_base(const AddrMap& m, long long o_orig, long long kprev,
+                                              long long klow, long long nrest, int col, int P) {
+  return o_orig * m.a_o + kprev * m.a_kp + klow * m.a_kl + nrest * m.a_n +
+         (long long)(col / P) * m.a_c + (long long)(col % P) * m.a_p;
+}
+
+template <bool FAST>
+__device__ __forceinline__ void lane_setup(const PassArgs& p, LaneCtx& L, int pr) {
+  const long long q0 = ((long long)blockIdx.x << (p.log2pw + 1)) + 2 * pr;
+#pragma unroll
+  for (int l = 0; l < 2; ++l) {
+    long long q = q0 + l;
+    bool ok = q < p.Q;
+    if (!ok) q = 0;
+    const long long o = q / p.RI;
+    const long long r = q - o * p.RI;
+    const long long nrest = r / p.I;
+    const int col = (int)(r - nrest * p.I);
+    const long long o_orig = o >> p.log2Kprev;
+    const long long kprev = o & ((1ll << p.log2Kprev) - 1);
+    const long long klow = (kprev >> p.kl_sa) + ((kprev & p.kl_mb) << p.kl_sb);
+    L.bin[l] = map_base(p.min, o_orig, kprev, klow, nrest, col, p.P);
+    L.bout[l] = map_base(p.mout, o_orig, kprev, klow, nrest, col, p.P);
+    L.nrest[l] = (unsigned int)nrest;
+    L.chan[l] = col / p.P;
+    L.valid[l] = ok;
+    if (l == 0) L.klow = (unsigned int)klow; else L.klow1 = (unsigned int)klow;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// global load / store of one row for the thread's lane pair
+// ------------------------------------------------------------------------------------------
+template <bool FAST>
+__device__ __forceinline__ c2 load_row(const PassArgs& p, const LaneCtx& L, long long row) {
+  c2 v;
+  if (p.load_kind == LOAD_C64) {
+    const float2* in = reinterpret_cast<const float2*>(p.in);
+    if (FAST) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(in + L.bin[0] + row * p.min.a_row));
+      v.re = make_float2(t.x, t.z);
+      v.im = make_float2(t.y, t.w);
+    } else {
+      float2 a = make_float2(0.f, 0.f), b = a;
+      if (L.valid[0]) a = __ldg(in + L.bin[0] + row * p.min.a_row);
+      if (L.valid[1]) b = __ldg(in + L.bin[1] + row * p.min.a_row);
+      v.re = make_float2(a.x, b.x);
+      v.im = make_float2(a.y, b.y);
+    }
+  } else {
+    const char2* in = reinterpret_cast<const char2*>(p.in);
+    if (FAST) {
+      const char4 t = __ldg(reinterpret_cast<const char4*>(in + L.bin[0] + row * p.min.a_row));
+      v.re = make_float2((float)t.x, (float)t.z);
+      v.im = make_float2((float)t.y, (float)t.w);
+    } else {
+      char2 a = make_char2(0, 0), b = a;
+      if (L.valid[0]) a = __ldg(in + L.bin[0] + row * p.min.a_row);
+      if (L.valid[1]) b = __ldg(in + L.bin[1] + row * p.min.a_row);
+      v.re = make_float2((float)a.x, (float)b.x);
+      v.im = make_float2((float)a.y, (float)b.y);
+    }
+  }
+  return v;
+}
+
+// plain complex64 store (intermediate data or c64 output)
+template <bool FAST>
+__device__ __forceinline__ void store_row_c64(const PassArgs& p, const LaneCtx& L, long long row,
+                                              long long shift, c2 v) {
+  float2* out = reinterpret_cast<float2*>(p.out);
+  if (FAST) {
+    *reinterpret_cast<float4*>(out + L.bout[0] + row * p.mout.a_row - shift) =
+        make_float4(v.re.x, v.im.x, v.re.y, v.im.y);
+  } else {
+    if (L.valid[0]) out[L.bout[0] + row * p.mout.a_row - shift] = make_float2(v.re.x, v.im.x);
+    if (L.valid[1]) out[L.bout[1] + row * p.mout.a_row - shift] = make_float2(v.re.y, v.im.y);
+  }
+}
+
+// final epilogue: crop on the time index, then c64 / per-pol intensity / Stokes I
+template <bool FAST>
+__device__ __forceinline__ void store_row_epi(const PassArgs& p, const LaneCtx& L, long long row,
+                                              c2 v) {
+  // time index of this row (same for both lanes when FAST; per lane otherwise)
+  const long long n0 = row * p.n_mul + L.nrest[0];
+  const long long n1 = row * p.n_mul + L.nrest[1];
+  const bool k0 = n0 >= p.crop_start && n0 < p.crop_stop;
+  const bool k1 = n1 >= p.crop_start && n1 < p.crop_stop;
+  const long long shift = p.crop_start * p.mout.a_n;  // a_n = elements per unit time index
+  if (p.epi_kind == EPI_C64) {
+    if (FAST) {
+      if (k0) store_row_c64<true>(p, L, row, shift, v);
+    } else {
+      float2* out = reinterpret_cast<float2*>(p.out);
+      if (L.valid[0] && k0) out[L.bout[0] + row * p.mout.a_row - shift] = make_float2(v.re.x, v.im.x);
+      if (L.valid[1] && k1) out[L.bout[1] + row * p.mout.a_row - shift] = make_float2(v.re.y, v.im.y);
+    }
+  } else {
+    const float2 pw = p_fma(v.re, v.re, p_mul(v.im, v.im));
+    float* out = reinterpret_cast<float*>(p.out);
+    if (p.epi_kind == EPI_INTENSITY) {
+      if (FAST) {
+        if (k0) *reinterpret_cast<float2*>(out + L.bout[0] + row * p.mout.a_row - shift) = pw;
+      } else {
+        if (L.valid[0] && k0) out[L.bout[0] + row * p.mout.a_row - shift] = pw.x;
+        if (L.valid[1] && k1) out[L.bout[1] + row * p.mout.a_row - shift] = pw.y;
+      }
+    } else {  // Stokes I: the pair is (pol0, pol1) of one channel (host enforces P == 2)
+      if (L.valid[0] && k0) out[L.bout[0] + row * p.mout.a_row - shift] = pw.x + pw.y;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// shared-memory tile: float4 {re0,re1,im0,im1} at [point ^ swz][pair]
+// ------------------------------------------------------------------------------------------
+struct Tile {
+  float4* s;
+  int log2pw;
+  int swzmask;  // (points per 128 B) - 1
+  __device__ __forceinline__ int idx(int pt, int pr) const {
+    return (((pt ^ ((pt >> 4) & swzmask)) << log2pw) + pr);
+  }
+  __device__ __forceinline__ c2 ld(int pt, int pr) const {
+    const float4 t = s[idx(pt, pr)];
+    c2 v;
+    v.re = make_float2(t.x, t.y);
+    v.im = make_float2(t.z, t.w);
+    return v;
+  }
+  __device__ __forceinline__ void st(int pt, int pr, c2 v) const {
+    s[idx(pt, pr)] = make_float4(v.re.x, v.re.y, v.im.x, v.im.y);
+  }
+};
+
+// stage twiddles from the table: tw[q*R + m] = w_M^(q*m) (forward sign); CONJ negates the sine
+template <int R, bool CONJ, bool PRE>
+__device__ __forceinline__ void apply_stage_tw(c2* v, const float2* __restrict__ tab, int q) {
+  if (R == 2) {
+    const float2 w = __ldg(tab + q * 2 + 1);
+    v[1] = cmul(v[1], p_bc(w.x), p_bc(CONJ ? -w.y : w.y));
+  } else {
+    const float4* t4 = reinterpret_cast<const float4*>(tab + (size_t)q * R);
+#pragma unroll
+    for (int j = 0; j < R / 2; ++j) {
+      const float4 w = __ldg(t4 + j);
+      if (j > 0) v[2 * j] = cmul(v[2 * j], p_bc(w.x), p_bc(CONJ ? -w.y : w.y));
+      v[2 * j + 1] = cmul(v[2 * j + 1], p_bc(w.z), p_bc(CONJ ? -w.w : w.w));
+    }
+  }
+}
+
+// inter-level twiddle for register m of a radix-R group: W_M^(nrest * (kbase + m*kstep)).
+// Built as E_a * F_c with m = 4a + c from exact roots, so every factor is one multiply deep.
+template <int R, bool CONJ, bool FAST>
+__device__ __forceinline__ void apply_level_tw(const PassArgs& p, const LaneCtx& L, c2* v,
+                                               unsigned int kbase, unsigned int kstep) {
+  if (p.log2M == 0) return;
+  constexpr int NA = (R + 3) / 4;
+  constexpr int NC = R < 4 ? R : 4;
+  float2 E0[NA], F0[NC], E1[NA], F1[NC];
+  {
+    const unsigned long long nr = L.nrest[0];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) E0[a] = unit_root(nr * (kbase + 4ull * a * kstep), p.log2M);
+#pragma unroll
+    for (int c = 1; c < NC; ++c) F0[c] = unit_root(nr * ((unsigned long long)c * kstep), p.log2M);
+  }
+  if (!FAST) {
+    const unsigned long long nr = L.nrest[1];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) E1[a] = unit_root(nr * (kbase + 4ull * a * kstep), p.log2M);
+#pragma unroll
+    for (int c = 1; c < NC; ++c) F1[c] = unit_root(nr * ((unsigned long long)c * kstep), p.log2M);
+  }
+#pragma unroll
+  for (int m = 0; m < R; ++m) {
+    const int a = m >> 2, c = m & 3;
+    float2 w0 = (c == 0) ? E0[a] : cmul1(E0[a], F0[c]);
+    float2 w1 = w0;
+    if (!FAST) w1 = (c == 0) ? E1[a] : cmul1(E1[a], F1[c]);
+    if (CONJ) { w0.y = -w0.y; w1.y = -w1.y; }
+    v[m] = cmul(v[m], make_float2(w0.x, w1.x), make_float2(w0.y, w1.y));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// chirp  H = exp(-2*pi*i*phi(k)) * scale,  phi in cycles evaluated in FP64
+// reference: transforms/dedispersion.py:19-23 (f = f_chan + fftfreq; phase = coeff*f*(1/ref-1/f)^2)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 chirp_value(const PassArgs& p, double fchan, long long kfull) {
+  const long long ks = (kfull >= (p.N >> 1)) ? kfull - p.N : kfull;
+  const double f = fma((double)ks, p.df, fchan);
+  const double a = fma(f - p.fr_sub, p.inv_fr, p.a0);   // (f - fr)/fr   (or -1 for fr = inf)
+  const double phi = (p.D * a) * a / f;                 // cycles
+  const double fr = phi - rint(phi);                    // exact reduction to [-0.5, 0.5]
+  float s, c;
+  sincospif(2.0f * (float)fr, &s, &c);
+  return make_float2(c * p.scale, -s * p.scale);
+}
+
+template <bool FAST>
+__device__ __forceinline__ void apply_chirp16(const PassArgs& p, const LaneCtx& L, c2* v,
+                                              unsigned int kbase, unsigned int kstep) {
+  if (p.chirp_kind == CHIRP_NONE) {
+    if (p.scale != 1.0f) {
+      const float2 sc = p_bc(p.scale);
+#pragma unroll
+      for (int m = 0; m < 16; ++m) { v[m].re = p_mul(v[m].re, sc); v[m].im = p_mul(v[m].im, sc); }
+    }
+    return;
+  }
+  if (p.chirp_kind == CHIRP_COMPUTED) {
+    const double f0 = p.chan_freq[L.chan[0]];
+    const double f1 = FAST ? f0 : p.chan_freq[L.chan[1]];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      const unsigned int k = kbase + m * kstep;
+      const long long kf0 = (long long)L.klow + ((long long)k << p.log2Kmul);
+      const float2 h0 = chirp_value(p, f0, kf0);
+      if (FAST) {
+        v[m] = cmul(v[m], p_bc(h0.x), p_bc(h0.y));
+      } else {
+        const long long kf1 = (long long)L.klow1 + ((long long)k << p.log2Kmul);
+        const float2 h1 = chirp_value(p, f1, kf1);
+        v[m] = cmul(v[m], make_float2(h0.x, h1.x), make_float2(h0.y, h1.y));
+      }
+    }
+  } else {  // explicit (N, C) complex64 array supplied by the caller (dedispersion.py:121-124)
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      const unsigned int k = kbase + m * kstep;
+      const long long kf0 = (long long)L.klow + ((long long)k << p.log2Kmul);
+      const long long kf1 = (long long)(FAST ? L.klow : L.klow1) + ((long long)k << p.log2Kmul);
+      const float2 h0 = __ldg(p.chirp_arr + kf0 * p.chirp_sk + (long long)L.chan[0] * p.chirp_sc);
+      const float2 h1 = __ldg(p.chirp_arr + kf1 * p.chirp_sk + (long long)L.chan[1] * p.chirp_sc);
+      v[m] = cmul(v[m], make_float2(h0.x * p.scale, h1.x * p.scale),
+                  make_float2(h0.y * p.scale, h1.y * p.scale));
+    }
+  }
+}
+
+// digit reversal of the last-stage block index b -> low part of the tile-level frequency index.
+// radices are (r1, 16, 16, ...): b = ((m1 * 16 + m2) * 16 + ...), klo = m1 + r1*(m2 + 16*(...)).
+__device__ __forceinline__ unsigned int klo_of_block(unsigned int b, int nstages, int log2r1) {
+  if (nstages <= 1) return 0;
+  unsigned int klo = 0, mul_shift = log2r1 + 4 * (nstages - 2);
+  // peel digits from the least significant (last radix-16 digit is most significant in k)
+  for (int s = nstages - 2; s >= 1; --s) {
+    mul_shift -= 4;
+    klo += (b & 15u) << (mul_shift);
+    b >>= 4;
+  }
+  klo += b;  // m1
+  return klo;
+}
+
+// ------------------------------------------------------------------------------------------
+// generic smem -> smem stage (radix 16), DIF (butterfly then twiddle) or DIT (conj twiddle first)
+// ------------------------------------------------------------------------------------------
+template <bool DIT>
+__device__ __forceinline__ void smem_stage16(const PassArgs& p, const Tile& T, int stage,
+                                             int log2S, int pr, int bfirst, int bstep, int nb) {
+  const float2* tab = p.stage_tw + p.stage_tw_off[stage];
+  const int S = 1 << log2S;
+  for (int b = bfirst; b < nb; b += bstep) {
+    const int q = b & (S - 1);
+    const int base = ((b >> log2S) << (log2S + 4)) + q;
+    c2 v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = T.ld(base + (i << log2S), pr);
+    if (DIT) {
+      apply_stage_tw<16, true, true>(v, tab, q);
+      Butterfly<16, true>::run(v);
+    } else {
+      Butterfly<16, false>::run(v);
+      apply_stage_tw<16, false, false>(v, tab, q);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) T.st(base + (i << log2S), pr, v[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// first forward stage: global -> registers -> (smem | global when the tile is one stage)
+//   FWD/MID: DIF radix R1 with stage table 0.  SIGNINV (FWD mode ifft): conjugated exponent.
+// ------------------------------------------------------------------------------------------
+template <int R, bool FAST, bool SIGNINV, int MODE>
+__device__ __forceinline__ void first_stage(const PassArgs& p, const LaneCtx& L, const Tile& T,
+                                            int pr, int bfirst, int bstep) {
+  const int log2S = p.log2L - (R == 2 ? 1 : R == 4 ? 2 : R == 8 ? 3 : 4);
+  const int S = 1 << log2S;
+  const float2* tab = p.stage_tw + p.stage_tw_off[0];
+  for (int b = bfirst; b < S; b += bstep) {
+    c2 v[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) v[i] = load_row<FAST>(p, L, (long long)((b + (i << log2S)) ^ p.fxor));
+    Butterfly<R, SIGNINV>::run(v);
+    if (p.nstages > 1) {
+      apply_stage_tw<R, SIGNINV, false>(v, tab, b);
+#pragma unroll
+      for (int i = 0; i < R; ++i) T.st(b + (i << log2S), pr, v[i]);
+    } else {
+      // single-stage tile (L == R): FWD mode only; registers hold k = m
+      apply_level_tw<R, SIGNINV, FAST>(p, L, v, 0u, 1u);
+      if (p.scale != 1.0f) {
+        const float2 sc = p_bc(p.scale);
+#pragma unroll
+        for (int i = 0; i < R; ++i) { v[i].re = p_mul(v[i].re, sc); v[i].im = p_mul(v[i].im, sc); }
+      }
+#pragma unroll
+      for (int i = 0; i < R; ++i) store_row_c64<FAST>(p, L, (long long)(i ^ p.kxor), 0, v[i]);
+    }
+  }
+}
+
+// last inverse stage (mirror of first_stage): smem -> registers -> epilogue
+template <int R, bool FAST>
+__device__ __forceinline__ void last_inv_stage(const PassArgs& p, const LaneCtx& L, const Tile& T,
+                                               int pr, int bfirst, int bstep, bool final_epi) {
+  const int log2S = p.log2L - (R == 2 ? 1 : R == 4 ? 2 : R == 8 ? 3 : 4);
+  const int S = 1 << log2S;
+  const float2* tab = p.stage_tw + p.stage_tw_off[0];
+  for (int b = bfirst; b < S; b += bstep) {
+    c2 v[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) v[i] = T.ld(b + (i << log2S), pr);
+    apply_stage_tw<R, true, true>(v, tab, b);
+    Butterfly<R, true>::run(v);
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const long long row = b + (i << log2S);
+      if (final_epi) store_row_epi<FAST>(p, L, row, v[i]);
+      else store_row_c64<FAST>(p, L, row, 0, v[i]);
+    }
+  }
+}
+
+template <bool FAST, bool SIGNINV, int MODE>
+__device__ __forceinline__ void run_first(const PassArgs& p, const LaneCtx& L, const Tile& T, int pr,
+                                          int bfirst, int bstep) {
+  switch (p.log2r1) {
+    case 1: first_stage<2, FAST, SIGNINV, MODE>(p, L, T, pr, bfirst, bstep); break;
+    case 2: first_stage<4, FAST, SIGNINV, MODE>(p, L, T, pr, bfirst, bstep); break;
+    case 3: first_stage<8, FAST, SIGNINV, MODE>(p, L, T, pr, bfirst, bstep); break;
+    default: first_stage<16, FAST, SIGNINV, MODE>(p, L, T, pr, bfirst, bstep); break;
+  }
+}
+
+template <bool FAST>
+__device__ __forceinline__ void run_last_inv(const PassArgs& p, const LaneCtx& L, const Tile& T,
+                                             int pr, int bfirst, int bstep, bool final_epi) {
+  switch (p.log2r1) {
+    case 1: last_inv_stage<2, FAST>(p, L, T, pr, bfirst, bstep, final_epi); break;
+    case 2: last_inv_stage<4, FAST>(p, L, T, pr, bfirst, bstep, final_epi); break;
+    case 3: last_inv_stage<8, FAST>(p, L, T, pr, bfirst, bstep, final_epi); break;
+    default: last_inv_stage<16, FAST>(p, L, T, pr, bfirst, bstep, final_epi); break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// the pass kernel
+// ------------------------------------------------------------------------------------------
+template <int MODE, bool FAST, bool SIGNINV>
+__global__ void __launch_bounds__(kThreads, 2) pass_kernel(const __grid_constant__ PassArgs p) {
+  extern __shared__ float4 smem_dyn[];
+  Tile T;
+  T.s = smem_dyn;
+  T.log2pw = p.log2pw;
+  {
+    const int ppb = 8 >> p.log2pw;  // points per 128 bytes
+    T.swzmask = ppb > 1 ? ppb - 1 : 0;
+  }
+  const int pw = 1 << p.log2pw;
+  const int pr = threadIdx.x & (pw - 1);
+  int bfirst = threadIdx.x >> p.log2pw;
+  const int bstep = kThreads >> p.log2pw;
+
+  LaneCtx L;
+  lane_setup<FAST>(p, L, pr);
+  // lane pairs past the end of the array do no work (they still reach every barrier)
+  if (!L.valid[0] && !L.valid[1]) bfirst = 1 << 30;
+
+  const int ns = p.nstages;
+  const int nb16 = 1 << (p.log2L - 4);            // radix-16 groups per lane pair
+  const unsigned int kstep = 1u << (p.log2L - 4);  // k spacing between registers of the last stage
+
+  if (MODE == MODE_FWD) {
+    // level transform, DIF: first stage from global, middle stages in smem, last stage to global
+    if (ns == 1) {
+      run_first<FAST, SIGNINV, MODE>(p, L, T, pr, bfirst, bstep);
+      return;
+    }
+    run_first<FAST, SIGNINV, MODE>(p, L, T, pr, bfirst, bstep);
+    __syncthreads();
+    for (int s = 1; s < ns - 1; ++s) {
+      const int log2S = 4 * (ns - 1 - s);
+      if (SIGNINV) {
+        // inverse exponent with the DIF graph: conjugated butterflies and twiddles
+        const float2* tab = p.stage_tw + p.stage_tw_off[s];
+        const int S = 1 << log2S;
+        for (int b = bfirst; b < nb16; b += bstep) {
+          const int q = b & (S - 1);
+          const int base = ((b >> log2S) << (log2S + 4)) + q;
+          c2 v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = T.ld(base + (i << log2S), pr);
+          Butterfly<16, true>::run(v);
+          apply_stage_tw<16, true, false>(v, tab, q);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) T.st(base + (i << log2S), pr, v[i]);
+        }
+      } else {
+        smem_stage16<false>(p, T, s, log2S, pr, bfirst, bstep, nb16);
+      }
+      __syncthreads();
+    }
+    for (int b = bfirst; b < nb16; b += bstep) {
+      c2 v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = T.ld((b << 4) + i, pr);
+      Butterfly<16, SIGNINV>::run(v);
+      const unsigned int klo = klo_of_block((unsigned int)b, ns, p.log2r1);
+      apply_level_tw<16, SIGNINV, FAST>(p, L, v, klo, kstep);
+      if (p.scale != 1.0f) {
+        const float2 sc = p_bc(p.scale);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { v[i].re = p_mul(v[i].re, sc); v[i].im = p_mul(v[i].im, sc); }
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        store_row_c64<FAST>(p, L, (long long)((klo + i * kstep) ^ (unsigned int)p.kxor), 0, v[i]);
+    }
+  } else if (MODE == MODE_MID) {
+    // last level: forward DIF, chirp in registers, inverse DIT
+    if (ns > 1) {
+      run_first<FAST, false, MODE>(p, L, T, pr, bfirst, bstep);
+      __syncthreads();
+      for (int s = 1; s < ns - 1; ++s) {
+        smem_stage16<false>(p, T, s, 4 * (ns - 1 - s), pr, bfirst, bstep, nb16);
+        __syncthreads();
+      }
+    }
+    for (int b = bfirst; b < nb16; b += bstep) {
+      c2 v[16];
+      if (ns > 1) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = T.ld((b << 4) + i, pr);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = load_row<FAST>(p, L, (long long)i);
+      }
+      Butterfly<16, false>::run(v);
+      const unsigned int klo = klo_of_block((unsigned int)b, ns, p.log2r1);
+      apply_chirp16<FAST>(p, L, v, klo, kstep);
+      Butterfly<16, true>::run(v);
+      if (ns > 1) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) T.st((b << 4) + i, pr, v[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) store_row_epi<FAST>(p, L, (long long)i, v[i]);
+      }
+    }
+    if (ns > 1) {
+      __syncthreads();
+      for (int s = ns - 2; s >= 1; --s) {
+        smem_stage16<true>(p, T, s, 4 * (ns - 1 - s), pr, bfirst, bstep, nb16);
+        __syncthreads();
+      }
+      run_last_inv<FAST>(p, L, T, pr, bfirst, bstep, true);
+    }
+  } else {  // MODE_INV: inverse level, DIT: conj level twiddle, radix-16 from global, ... , epilogue
+    for (int b = bfirst; b < nb16; b += bstep) {
+      const unsigned int klo = klo_of_block((unsigned int)b, ns, p.log2r1);
+      c2 v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = load_row<FAST>(p, L, (long long)(klo + i * kstep));
+      apply_level_tw<16, true, FAST>(p, L, v, klo, kstep);
+      Butterfly<16, true>::run(v);
+      if (ns > 1) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) T.st((b << 4) + i, pr, v[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) store_row_epi<FAST>(p, L, (long long)i, v[i]);
+      }
+    }
+    if (ns > 1) {
+      __syncthreads();
+      for (int s = ns - 2; s >= 1; --s) {
+        smem_stage16<true>(p, T, s, 4 * (ns - 1 - s), pr, bfirst, bstep, nb16);
+        __syncthreads();
+      }
+      run_last_inv<FAST>(p, L, T, pr, bfirst, bstep, true);
+    }
+  }
+}
+
+}  // namespace pbk

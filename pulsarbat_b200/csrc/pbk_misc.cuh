@@ -1,0 +1,175 @@
+// pbk_misc.cuh -- bandwidth-bound companions of the FFT passes: detection, time integration and
+// phase-binned folding.
+//   detect      core.py:766-774 (re^2+im^2 per pol) and core.py:948/960 (Stokes I = AA+BB)
+//   downsample  builder-defined time sum
+//   fold        builder-defined on top of the phase polynomial returned by
+//               pulsar/predictor.py:149-160 (phasepol); numpy polyval order, FP64, no FMA.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pbk {
+
+constexpr int kFoldMaxCoef = 16;
+
+// out[j, e] = sum_{m<M} in[(j*M+m), e]      float32 in/out, float32 accumulation in time order
+__global__ void __launch_bounds__(256) downsample_kernel(const float* __restrict__ in,
+                                                         float* __restrict__ out, long long rows,
+                                                         long long E, long long M) {
+  const long long total = rows * E;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long j = i / E, e = i - j * E;
+    const float* src = in + (j * M) * E + e;
+    float acc = 0.f;
+#pragma unroll 8
+    for (long long m = 0; m < M; ++m) acc += __ldg(src + m * E);
+    out[i] = acc;
+  }
+}
+
+// float4-wide variant when E % 4 == 0 and pointers are 16-byte aligned
+__global__ void __launch_bounds__(256) downsample_kernel_v4(const float4* __restrict__ in,
+                                                            float4* __restrict__ out,
+                                                            long long rows, long long E4,
+                                                            long long M) {
+  const long long total = rows * E4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long j = i / E4, e = i - j * E4;
+    const float4* src = in + (j * M) * E4 + e;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (long long m = 0; m < M; ++m) {
+      const float4 v = __ldg(src + m * E4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    out[i] = acc;
+  }
+}
+
+static inline cudaError_t launch_downsample(const float* in, float* out, long long rows,
+                                            long long E, long long M, cudaStream_t st) {
+  if (rows <= 0) return cudaSuccess;
+  const bool v4 = (E % 4 == 0) && ((((uintptr_t)in | (uintptr_t)out) & 15) == 0);
+  const long long total = v4 ? rows * (E / 4) : rows * E;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148ll * 32) blocks = 148ll * 32;
+  if (v4)
+    downsample_kernel_v4<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(in),
+                                                           reinterpret_cast<float4*>(out), rows,
+                                                           E / 4, M);
+  else
+    downsample_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, out, rows, E, M);
+  return cudaGetLastError();
+}
+
+// power detection with optional time sum.  in (rows*M, CP) complex64.
+//   stokes == 0: out (rows, CP)   = sum_m re^2+im^2
+//   stokes == 1: out (rows, CP/2) = sum_m |A|^2+|B|^2   (pol pairs are adjacent)
+__global__ void __launch_bounds__(256) detect_kernel(const float2* __restrict__ in,
+                                                     float* __restrict__ out, long long rows,
+                                                     long long CP, int stokes, long long M) {
+  const long long E = stokes ? CP / 2 : CP;
+  const long long total = rows * E;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long j = i / E, e = i - j * E;
+    float acc = 0.f;
+    if (stokes) {
+      for (long long m = 0; m < M; ++m) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(in + (j * M + m) * CP + 2 * e));
+        // (XX) + (YY), each as re*re + im*im like the reference
+        acc += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+      }
+    } else {
+      const float2* src = in + (j * M) * CP + e;
+      for (long long m = 0; m < M; ++m) {
+        const float2 v = __ldg(src + m * CP);
+        acc += v.x * v.x + v.y * v.y;
+      }
+    }
+    out[i] = acc;
+  }
+}
+
+static inline cudaError_t launch_detect(const float2* in, float* out, long long rows, long long CP,
+                                        bool stokes, long long M, cudaStream_t st) {
+  if (rows <= 0) return cudaSuccess;
+  const long long total = rows * (stokes ? CP / 2 : CP);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148ll * 32) blocks = 148ll * 32;
+  detect_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, out, rows, CP, stokes ? 1 : 0, M);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// fold
+// ------------------------------------------------------------------------------------------
+struct FoldArgs {
+  const float* in;
+  float* profile;
+  unsigned long long* counts;
+  int* bins_out;
+  double coef[kFoldMaxCoef];
+  int ncoef;
+  double sample_rate;
+  long long n0;
+  int nbin;
+  long long nsamp, row_elems;
+};
+
+// bit-exact restatement of numpy.polynomial.polynomial.polyval + floor binning (oracle fold_bins)
+__device__ __forceinline__ int fold_bin(const FoldArgs& a, long long n) {
+  const double t = __ddiv_rn((double)(a.n0 + n), a.sample_rate);
+  double c0 = a.coef[a.ncoef - 1];
+  for (int i = a.ncoef - 2; i >= 0; --i) c0 = __dadd_rn(a.coef[i], __dmul_rn(c0, t));
+  const double fr = __dsub_rn(c0, floor(c0));
+  const long long b = (long long)floor(__dmul_rn(fr, (double)a.nbin));
+  return (int)(b % a.nbin);
+}
+
+constexpr int kFoldRows = 32;  // time samples per CTA
+
+// One CTA folds kFoldRows consecutive samples: their bins are computed once into shared memory,
+// then threads sweep the row elements (coalesced) and add into profile[bin] with float atomics.
+// Consecutive samples usually fall in the same or adjacent bins, so runs are summed in registers
+// before each atomic.
+__global__ void __launch_bounds__(256) fold_kernel(const __grid_constant__ FoldArgs a) {
+  __shared__ int sbin[kFoldRows];
+  const long long nb = (long long)blockIdx.x * kFoldRows;
+  const int nrows = (int)min((long long)kFoldRows, a.nsamp - nb);
+  if (threadIdx.x < nrows) {
+    const int b = fold_bin(a, nb + threadIdx.x);
+    sbin[threadIdx.x] = b;
+    if (a.bins_out) a.bins_out[nb + threadIdx.x] = b;
+    if (blockIdx.y == 0) atomicAdd(a.counts + b, 1ull);
+  }
+  __syncthreads();
+  const long long e = (long long)blockIdx.y * blockDim.x + threadIdx.x;
+  if (e >= a.row_elems) return;
+  const float* src = a.in + nb * a.row_elems + e;
+  int cur = sbin[0];
+  float acc = 0.f;
+  for (int r = 0; r < nrows; ++r) {
+    const int b = sbin[r];
+    if (b != cur) {
+      atomicAdd(a.profile + (long long)cur * a.row_elems + e, acc);
+      acc = 0.f;
+      cur = b;
+    }
+    acc += __ldg(src + (long long)r * a.row_elems);
+  }
+  atomicAdd(a.profile + (long long)cur * a.row_elems + e, acc);
+}
+
+static inline cudaError_t launch_fold(const FoldArgs& a, cudaStream_t st) {
+  const long long gx = (a.nsamp + kFoldRows - 1) / kFoldRows;
+  const long long gy = (a.row_elems + 255) / 256;
+  if (gy > 65535) return cudaErrorInvalidValue;
+  dim3 grid((unsigned)gx, (unsigned)gy);
+  fold_kernel<<<grid, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace pbk

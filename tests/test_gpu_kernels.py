@@ -1,0 +1,278 @@
+"""GPU parity tests of the raw kernels (through the C ABI) against the CPU oracle."""
+
+import ctypes
+
+import numpy as np
+import pytest
+import scipy.fft
+import scipy.signal
+
+from oracle import pbk_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from pulsarbat_b200 import _lib as L
+    return L
+
+
+def relerr(a, b):
+    a = np.asarray(a).astype(np.complex128 if np.iscomplexobj(a) else np.float64)
+    b = np.asarray(b).astype(a.dtype)
+    nb = np.linalg.norm(b.ravel())
+    return np.linalg.norm((a - b).ravel()) / (nb if nb > 0 else 1.0)
+
+
+def crandn(rng, shape):
+    return (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(np.complex64)
+
+
+# ------------------------------------------------------------------------------ plain FFT
+@pytest.mark.parametrize("n", [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192,
+                               2 ** 14, 2 ** 16])
+@pytest.mark.parametrize("inner", [1, 2, 3, 8])
+def test_fft_axis0(n, inner):
+    L = _lib()
+    rng = np.random.default_rng(n * 31 + inner)
+    outer = 3 if n <= 256 else 1
+    x = crandn(rng, (outer, n, inner))
+    for inverse in (False, True):
+        plan = L.FFTPlan(outer, n, inner, inverse=inverse)
+        y = plan.exec_host(x, np.empty_like(x))
+        ref = (scipy.fft.ifft if inverse else scipy.fft.fft)(x.astype(np.complex128), axis=1)
+        e = relerr(y, ref)
+        assert e < 2e-6, (n, inner, inverse, e)
+        plan.destroy()
+
+
+def test_fft_large_two_level():
+    L = _lib()
+    rng = np.random.default_rng(5)
+    n, inner = 2 ** 20, 2
+    x = crandn(rng, (1, n, inner))
+    plan = L.FFTPlan(1, n, inner)
+    y = plan.exec_host(x, np.empty_like(x))
+    ref = scipy.fft.fft(x.astype(np.complex128), axis=1)
+    assert relerr(y, ref) < 2e-6
+
+
+def test_fft_rejects_non_pow2():
+    L = _lib()
+    with pytest.raises(L.PbkUnsupported):
+        L.FFTPlan(1, 33, 2)
+
+
+# ------------------------------------------------------------------------------ stft / istft
+@pytest.mark.parametrize("shape", [(4224, 4, 2), (4096, 3, 2), (8192, 1, 1), (2 ** 17, 1, 2),
+                                   (4096, 5, 1)])
+@pytest.mark.parametrize("nperseg", [32, 64, 1024, 4096])
+def test_stft_istft(shape, nperseg):
+    L = _lib()
+    rng = np.random.default_rng(shape[0] + nperseg)
+    x = np.exp(1j * rng.uniform(-np.pi, np.pi, shape)).astype(np.complex64)
+    nseg = shape[0] // nperseg
+    xt = np.ascontiguousarray(x[: nseg * nperseg])
+    plan = L.STFTPlan(nseg, nperseg, shape[1], shape[2])
+    y = plan.exec_host(xt, np.empty((nseg, shape[1] * nperseg, shape[2]), np.complex64))
+    ref = orc.stft(x.astype(np.complex128), nperseg)
+    assert relerr(y, ref) < 2e-6
+    iplan = L.STFTPlan(nseg, nperseg, shape[1], shape[2], inverse=True)
+    keep = y.copy()
+    z = iplan.exec_host(y, np.empty_like(xt))
+    assert np.array_equal(y, keep)          # input untouched (misc.py:82-83 mutates; we do not)
+    assert relerr(z, orc.istft(ref, nperseg)) < 3e-6
+    assert relerr(z, xt) < 3e-6
+
+
+def test_stft_single_tone():
+    # reference tests/test_contrib.py:43-51
+    L = _lib()
+    x = np.exp(2j * np.pi * np.arange(1024) * 0.25)[:, None, None].astype(np.complex64)
+    for n in [32, 64, 512, 1024]:
+        plan = L.STFTPlan(1024 // n, n, 1, 1)
+        y = plan.exec_host(x, np.empty((1024 // n, n, 1), np.complex64))
+        a = np.zeros_like(y)
+        a[:, 3 * n // 4] = 1.0
+        assert np.allclose(a, y, atol=2e-6)
+
+
+# ------------------------------------------------------------------------------ dedispersion
+def _dedisp(L, x, dm, sr, fcen, ref=None, freq_align="center", crop=True, out_kind=0,
+            downsample=1, chirp=None, in_dtype=0):
+    N, C = x.shape[:2]
+    if in_dtype == 1:
+        P = int(np.prod(x.shape[2:-1])) if x.ndim > 3 else 1
+    else:
+        P = int(np.prod(x.shape[2:])) if x.ndim > 2 else 1
+    ref = fcen if ref is None else ref
+    freqs = orc.channel_freqs(fcen, sr, C, freq_align)
+    start, stop = orc.crop_range(dm, N, fcen, sr, C, ref) if crop else (0, N)
+    plan = L.DedispPlan(nsamp=N, nchan=C, npol=P, dm=dm, sample_rate_hz=sr, ref_freq_hz=ref,
+                        chan_freq_hz=freqs, crop=(max(start, 0), min(stop, N)) if stop > start
+                        else (0, 0), in_dtype=in_dtype,
+                        out_kind=out_kind, downsample=downsample,
+                        explicit_chirp=chirp is not None)
+    out = plan.out_array()
+    plan.exec_host(np.ascontiguousarray(x), out,
+                   None if chirp is None else np.ascontiguousarray(chirp))
+    info = plan.info()
+    plan.destroy()
+    return out, start, stop, info
+
+
+@pytest.mark.parametrize("shape", [(8192, 4, 2), (8192, 4), (16, 2, 2), (256, 2, 2), (4096, 1),
+                                   (2 ** 15, 3, 2), (2 ** 14, 5)])
+@pytest.mark.parametrize("dm", [10.0, 50.0])
+def test_dedisp_small(shape, dm):
+    L = _lib()
+    rng = np.random.default_rng(shape[0] + int(dm))
+    x = crandn(rng, shape)
+    sr, fcen = 1e6, 1e9
+    fmin, fmax = orc.band_edges(fcen, sr, shape[1])
+    for ref in [fcen, fmin, fmax]:
+        want, s0, s1 = orc.coherent_dedispersion(x, dm, sample_rate=sr, center_freq=fcen,
+                                                 ref_freq=ref, crop=False)
+        got, start, stop, _ = _dedisp(L, x, dm, sr, fcen, ref=ref, crop=False)
+        assert (start, stop) == (0, shape[0])
+        assert relerr(got.reshape(want.shape), want) < 1e-5, (shape, dm, ref)
+        if s1 > s0:
+            got, start, stop, _ = _dedisp(L, x, dm, sr, fcen, ref=ref, crop=True)
+            assert (start, stop) == (s0, s1)
+            assert got.shape[0] == s1 - s0
+            assert relerr(got.reshape(want[s0:s1].shape), want[s0:s1]) < 1e-5
+
+
+def test_dedisp_gabor_known_answer():
+    # reference tests/test_dedispersion.py:100-139 on the GPU path (complex64)
+    L = _lib()
+    dm, ref, sr = 0.01, 600e6, 400e6
+    index, N, width = 100000, 2 ** 18, 256
+    t = np.arange(N) / sr
+    x = np.zeros(N, dtype=np.complex128)
+    for df in np.linspace(-3 * sr / 8, 3 * sr / 8, 13):
+        dt = orc.time_delay(dm, ref + df, ref)
+        a = 2j * np.pi * (t - (t[index] + dt)) * df - ((t - (t[index] + dt)) / (width / sr)) ** 2
+        x += np.exp(a)
+    y, noffset, stop, _ = _dedisp(L, x.reshape(-1, 1).astype(np.complex64), dm, sr, ref)
+    y = y.reshape(-1)
+    id1, id2 = index - noffset - 8 * width, index - noffset + 8 * width
+    p1 = (np.abs(x) ** 2).sum()
+    p2 = (np.abs(y[id1:id2].astype(np.complex128)) ** 2).sum()
+    assert np.isclose(p1, p2, rtol=1e-5)
+    assert np.abs(y[id2:]).max() < 1e-4 and np.abs(y[:id1]).max() < 1e-4
+
+
+def test_dedisp_cfg1_precrop():
+    # BASELINE config 1: (2^20, 1) c64, DM 71, 400 MHz, 16 MHz: crop is empty
+    L = _lib()
+    rng = np.random.default_rng(42)
+    N = 2 ** 20
+    x = ((rng.standard_normal((N, 1)) + 1j * rng.standard_normal((N, 1))) / np.sqrt(2)).astype(
+        np.complex64)
+    want, s0, s1 = orc.coherent_dedispersion(x, 71.0, sample_rate=16e6, center_freq=400e6,
+                                             crop=False)
+    assert s0 == 1143991 and s1 < s0
+    got, _, _, info = _dedisp(L, x, 71.0, 16e6, 400e6, crop=False)
+    assert relerr(got.reshape(want.shape), want) < 1e-5
+    assert info["levels"] == [10, 10]
+    # the literal (empty) crop returns no rows, like dedispersion.py:133
+    got, start, stop, _ = _dedisp(L, x, 71.0, 16e6, 400e6, crop=True)
+    assert (start, stop) == (s0, s1) and got.shape[0] == 0
+
+
+def test_dedisp_dualpol_outputs():
+    # cfg-2-like geometry at reduced size: 8 channels x 2 pol, DM 0.5 (sweep fits in N)
+    L = _lib()
+    rng = np.random.default_rng(8)
+    N, C = 2 ** 16, 8
+    sr, fcen, dm = 6.25e6, 425e6, 0.5
+    x = crandn(rng, (N, C, 2))
+    want, s0, s1 = orc.coherent_dedispersion(x, dm, sample_rate=sr, center_freq=fcen, crop=False)
+    assert s1 > s0
+    got, start, stop, _ = _dedisp(L, x, dm, sr, fcen)
+    assert (start, stop) == (s0, s1)
+    assert relerr(got, want[s0:s1]) < 1e-5
+    # per-pol intensity
+    inten, *_ = _dedisp(L, x, dm, sr, fcen, out_kind=1)
+    assert relerr(inten, orc.to_intensity(want[s0:s1])) < 1e-5
+    # Stokes I
+    st, *_ = _dedisp(L, x, dm, sr, fcen, out_kind=2)
+    assert relerr(st, orc.stokes_I(want[s0:s1])) < 1e-5
+    # Stokes I summed x64 in time
+    st64, *_ = _dedisp(L, x, dm, sr, fcen, out_kind=2, downsample=64)
+    assert relerr(st64, orc.downsample(orc.stokes_I(want[s0:s1]), 64)) < 1e-5
+    # explicit chirp bypass == implicit (reference tests/test_dedispersion.py:141-164)
+    chirp = orc.chirp_from_signal(dm, N, sr, orc.channel_freqs(fcen, sr, C), fcen)
+    got2, *_ = _dedisp(L, x, dm, sr, fcen, chirp=chirp)
+    assert relerr(got2, want[s0:s1]) < 1e-5
+
+
+def test_dedisp_int8_input():
+    L = _lib()
+    rng = np.random.default_rng(15)
+    N, C = 2 ** 14, 4
+    raw = np.clip(np.rint(rng.normal(0, 20, (N, C, 2, 2))), -127, 127).astype(np.int8)
+    x = orc.unpack_int8(raw)
+    sr, fcen, dm = 390625.0, 600e6, 100.0
+    want, s0, s1 = orc.coherent_dedispersion(x, dm, sample_rate=sr, center_freq=fcen, crop=False)
+    got, *_ = _dedisp(L, raw, dm, sr, fcen, crop=False, in_dtype=1)
+    assert relerr(got, want) < 1e-5
+
+
+def test_dedisp_reversibility():
+    # reference tests/test_dedispersion.py:73-98 (complex64 tolerance instead of 3e-8)
+    L = _lib()
+    ref, sr, dm = 600e6, 400e6, 0.01
+    N, M = 2 ** 18, 2 ** 12
+    R = np.random.default_rng(seed=23)
+    x = R.standard_normal(N) + 1j * R.standard_normal(N)
+    x *= np.exp(-(((np.arange(N) - N // 2) / M) ** 2))
+    sos = scipy.signal.butter(10, 0.45, "lowpass", fs=1.0, output="sos")
+    x = scipy.signal.sosfilt(sos, x).reshape(-1, 1).astype(np.complex64)
+    # the cropped output is not a power of two, so reverse the uncropped circular result
+    t_full, *_ = _dedisp(L, x, dm, sr, ref, crop=False)
+    y, *_ = _dedisp(L, t_full, -dm, sr, ref, crop=False)
+    assert relerr(y, x) < 1e-5
+
+
+# ------------------------------------------------------------------------------ detect / fold
+def test_detect_and_downsample():
+    L = _lib()
+    rng = np.random.default_rng(21)
+    x = crandn(rng, (1000, 6, 2))
+    for kind, ref in [(1, orc.to_intensity(x)), (2, orc.stokes_I(x))]:
+        for ds in (1, 8):
+            rows = 1000 // ds
+            out = np.empty((rows,) + ref.shape[1:], np.float32)
+            L.check(L.lib().pbk_detect(L.ptr(x), L.ptr(out), 1000, 6, 2, kind, ds, 0, 0, None))
+            want = orc.downsample(ref, ds) if ds > 1 else ref
+            assert relerr(out, want) < 1e-6
+    f = rng.random((1003, 12)).astype(np.float32)
+    out = np.empty((1003 // 64, 12), np.float32)
+    L.check(L.lib().pbk_downsample(L.ptr(f), L.ptr(out), 1003, 12, 64, 0, 0, None))
+    assert relerr(out, orc.downsample(f, 64)) < 1e-6
+
+
+@pytest.mark.parametrize("coef, sr, nbin", [
+    ([0.123, 29.7, 1e-6], 1e4, 64),
+    ([0.5, 641.928232294317, -3.3e-8, 1e-12], 390625.0, 1024),
+    ([1e-17 - 1e-9, 1.0], 1e3, 16),
+])
+def test_fold_bit_exact_bins(coef, sr, nbin):
+    L = _lib()
+    rng = np.random.default_rng(16)
+    N, E = 20000, 24
+    x = rng.random((N, E)).astype(np.float32)
+    prof = np.zeros((nbin, E), np.float32)
+    counts = np.zeros(nbin, np.int64)
+    bins = np.empty(N, np.int32)
+    c = np.asarray(coef, dtype=np.float64)
+    L.check(L.lib().pbk_fold(L.ptr(x), N, E, c.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                             len(c), sr, 7, nbin, L.ptr(prof), L.ptr(counts), L.ptr(bins),
+                             0, 0, None))
+    wbins = orc.fold_bins(N, c, sr, nbin, n0=7)
+    wprof, wcounts = orc.fold(x, c, sr, nbin, n0=7)
+    assert np.array_equal(bins, wbins)
+    assert np.array_equal(counts, wcounts)
+    assert relerr(prof, wprof) < 1e-5
