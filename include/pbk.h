@@ -143,6 +143,9 @@ void pbk_plan_destroy(pbk_plan* plan);
 int pbk_plan_info(const pbk_plan* plan, int32_t* launches, int64_t* workspace_bytes,
                   int32_t* levels, int32_t* level_log2 /* [3] */);
 
+/* human-readable list of the passes of a plan: "FWD:L=2^11:fast-r8:W=4:tiles=65536:threads=512;..." */
+int pbk_plan_describe(const pbk_plan* plan, char* buf, size_t n);
+
 /* raw device-memory helpers so a ctypes caller needs no other CUDA binding */
 int pbk_malloc(void** dptr, size_t bytes, int32_t device);
 int pbk_free(void* dptr, int32_t device);

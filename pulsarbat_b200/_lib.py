@@ -18,7 +18,7 @@ EXPORTS = [
     "pbk_dedisp_plan_create", "pbk_dedisp_out_shape", "pbk_dedisp_exec_host",
     "pbk_dedisp_exec_device", "pbk_fft_plan_create", "pbk_stft_plan_create",
     "pbk_fft_exec_host", "pbk_fft_exec_device", "pbk_detect", "pbk_downsample", "pbk_fold",
-    "pbk_plan_destroy", "pbk_plan_info", "pbk_malloc", "pbk_free", "pbk_memcpy_h2d",
+    "pbk_plan_destroy", "pbk_plan_info", "pbk_plan_describe", "pbk_malloc", "pbk_free", "pbk_memcpy_h2d",
     "pbk_memcpy_d2h", "pbk_device_sync",
 ]
 
@@ -86,6 +86,7 @@ def lib():
         L.pbk_plan_destroy.restype = None
         L.pbk_plan_info.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i64),
                                     ctypes.POINTER(i32), ctypes.POINTER(i32)]
+        L.pbk_plan_describe.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t]
         L.pbk_malloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t, i32]
         L.pbk_free.argtypes = [vp, i32]
         L.pbk_memcpy_h2d.argtypes = [vp, vp, ctypes.c_size_t, i32]
@@ -140,6 +141,11 @@ class Plan:
                                   ctypes.byref(levels), l2))
         return {"launches": launches.value, "workspace_bytes": ws.value,
                 "levels": [l2[i] for i in range(levels.value)]}
+
+    def describe(self):
+        buf = ctypes.create_string_buffer(1024)
+        check(lib().pbk_plan_describe(self.handle, buf, 1024))
+        return buf.value.decode()
 
     def destroy(self):
         if self._h:

@@ -14,12 +14,14 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
 #include <vector>
 
 #include "../../include/pbk.h"
+#include "pbk_fast_launch.h"
 #include "pbk_fft.cuh"
 #include "pbk_misc.cuh"
 
@@ -79,7 +81,11 @@ struct Pass {
   PassArgs a;
   unsigned grid = 0;
   size_t smem = 0;
-  int tw_table = -1;  // index into plan tables (by log2L)
+  // compile-time-shaped kernel (pbk_fast.cuh); family < 0 = generic runtime-shaped kernel
+  int family = -1;
+  FastInfo finfo{};
+  long long ntiles = 0;
+  size_t ftab_off = 0;  // float2 offset into plan->d_ftab
 };
 
 struct pbk_plan {
@@ -94,6 +100,8 @@ struct pbk_plan {
   size_t scratch_bytes = 0;
   float2* d_tw = nullptr;
   double* d_chanfreq = nullptr;
+  float2* d_ftab = nullptr;     // stage tables of the fast kernels
+  int num_sms = 148;
   void* d_tmpf = nullptr;       // pre-downsample float buffer
   size_t tmpf_bytes = 0;
   // lazily allocated staging buffers for *_host execution
@@ -196,17 +204,72 @@ static void set_klow(PassArgs& a, int level /*1-based*/, const int* l) {
   if (level == 3) { a.kl_sa = l[1]; a.kl_mb = (1 << l[1]) - 1; a.kl_sb = l[0]; }
 }
 
-static int choose_levels(int n, int* l, bool need_mid16) {
-  int m;
-  if (n <= 12) m = 1;
-  else if (n <= 24) m = 2;
-  else if (n <= 36) m = 3;
-  else return 0;
-  if (m == 1) { l[0] = n; }
-  else if (m == 2) { l[0] = n / 2; l[1] = n - l[0]; }
-  else { l[0] = n / 3; l[1] = n / 3; l[2] = n - l[0] - l[1]; }
-  if (need_mid16 && l[m - 1] < 4) return 0;
-  return m;
+// Level split N = 2^l[0] * .. * 2^l[m-1], chosen with a cost model built from measurements on
+// B200 (scripts/chunk_bw.cu, scripts/chunk_bw2.cu; logs under profiles/): what a pass can pull
+// from HBM depends almost only on the width of the contiguous chunk it touches per row,
+//   row stride >= 64 KiB :  32 B 1.55 | 64 B 3.1 | 128 B 4.6 | >=256 B 6.0  TB/s
+//   consecutive rows     :  32 B 3.8  | 64 B 5.7 | 128 B 5.7 | >=256 B 6.0  TB/s
+// and a 64 KiB tile of 2^l points leaves 65536/2^l bytes per row.  Strided levels are paid
+// twice (forward and inverse pass), the last level once (fused fft*chirp*ifft pass).
+static double bw_strided(double chunk) {
+  if (chunk >= 256) return 6.0;
+  if (chunk >= 128) return 4.6;
+  if (chunk >= 64) return 3.1;
+  if (chunk >= 32) return 1.55;
+  return 1.55 * chunk / 32.0;
+}
+static double bw_rows(double chunk) {
+  if (chunk >= 256) return 6.0;
+  if (chunk >= 64) return 5.7;
+  if (chunk >= 32) return 3.8;
+  return 3.8 * chunk / 32.0;
+}
+static double level_chunk_bytes(int l, long long lanes_avail) {
+  double w = 65536.0 / (double)(1ll << l) / 8.0;   // lanes in a 64 KiB tile
+  if (w > 128) w = 128;
+  if (w > (double)lanes_avail) w = (double)lanes_avail;
+  return w * 8.0;
+}
+
+static int choose_levels(int n, long long I, int* l, bool need_mid16) {
+  const char* e = getenv("PBK_LEVELS");   // developer override, e.g. PBK_LEVELS=11,11
+  if (e) {
+    int a = 0, b = 0, c = 0;
+    const int got = sscanf(e, "%d,%d,%d", &a, &b, &c);
+    if (got >= 1 && a + b + c == n) {
+      l[0] = a; l[1] = b; l[2] = c;
+      return got;
+    }
+  }
+  const int lo = 4, hi = 12;
+  double best = 1e30;
+  int bm = 0, bl[3] = {0, 0, 0};
+  auto consider = [&](int m, int a, int b, int c) {
+    const int ls[3] = {a, b, c};
+    if (ls[m - 1] < (need_mid16 ? 4 : 1) || ls[m - 1] > hi) return;
+    double cost = 0;
+    long long R = 1ll << n;
+    for (int i = 0; i < m; ++i) {
+      R >>= ls[i];
+      if (i + 1 < m) {
+        if (need_mid16 && ls[i] < lo) return;   // inverse passes start with a radix-16 stage
+        cost += 2.0 / bw_strided(level_chunk_bytes(ls[i], R * I));
+      } else {
+        cost += 1.0 / bw_rows(level_chunk_bytes(ls[i], I));
+      }
+      cost += 0.004 * ((ls[i] + 3) / 4);   // tie-break: fewer butterfly stages
+    }
+    if (cost < best - 1e-12) { best = cost; bm = m; bl[0] = a; bl[1] = b; bl[2] = c; }
+  };
+  if (n <= hi) consider(1, n, 0, 0);
+  for (int a = 1; a <= hi && a < n; ++a) {
+    if (n - a <= hi) consider(2, a, n - a, 0);
+    for (int b = 1; b <= hi && a + b < n; ++b)
+      if (n - a - b <= hi) consider(3, a, b, n - a - b);
+  }
+  if (bm == 0) return 0;
+  for (int i = 0; i < 3; ++i) l[i] = bl[i];
+  return bm;
 }
 
 template <int MODE, bool FAST, bool SIGNINV>
@@ -239,6 +302,73 @@ static cudaError_t launch_pass(const Pass& ps, bool fast, cudaStream_t st) {
       return fast ? launch_variant<MODE_INV, true, false>(ps, st)
                   : launch_variant<MODE_INV, false, false>(ps, st);
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// fast-kernel dispatch (instantiations in pbk_fast_r8.cu / pbk_fast_r16.cu)
+// ------------------------------------------------------------------------------------------
+namespace pbk {
+bool fast_info_r8(int log2L, FastInfo* info);
+bool fast_info_r16(int log2L, FastInfo* info);
+void fast_tables_r8(int log2L, float2* dst);
+void fast_tables_r16(int log2L, float2* dst);
+cudaError_t fast_launch_r8(int log2L, int mode, const PassArgs& a, const float2* d_tables,
+                           long long ntiles, int num_sms, cudaStream_t st);
+cudaError_t fast_launch_r16(int log2L, int mode, const PassArgs& a, const float2* d_tables,
+                            long long ntiles, int num_sms, cudaStream_t st);
+bool fast_info(int family, int log2L, FastInfo* info) {
+  return family == FAMILY_R8 ? fast_info_r8(log2L, info) : fast_info_r16(log2L, info);
+}
+void fast_tables(int family, int log2L, float2* dst) {
+  if (family == FAMILY_R8) fast_tables_r8(log2L, dst); else fast_tables_r16(log2L, dst);
+}
+cudaError_t fast_launch(int family, int log2L, int mode, const PassArgs& a, const float2* d_tables,
+                        long long ntiles, int num_sms, cudaStream_t st) {
+  return family == FAMILY_R8 ? fast_launch_r8(log2L, mode, a, d_tables, ntiles, num_sms, st)
+                             : fast_launch_r16(log2L, mode, a, d_tables, ntiles, num_sms, st);
+}
+}  // namespace pbk
+
+// developer knob: PBK_FAMILY=8|16|0 picks the fast-kernel family (0 = generic kernels only)
+static int preferred_family() {
+  const char* e = getenv("PBK_FAMILY");
+  if (!e) return FAMILY_R16;
+  if (!strcmp(e, "8")) return FAMILY_R8;
+  if (!strcmp(e, "0")) return -1;
+  return FAMILY_R16;
+}
+
+// decide which passes can run on the compile-time-shaped kernels and stage their tables
+static int setup_fast(pbk_plan* pl) {
+  const int fam = preferred_family();
+  std::vector<float2> host;
+  for (auto& ps : pl->passes) {
+    ps.family = -1;
+    if (fam < 0 || !ps.fast || ps.signinv || ps.a.fxor || ps.a.kxor) continue;
+    // the fast kernels are specialised to the dedispersion passes (see pbk_fast.cuh)
+    if (ps.a.scale != 1.0f && ps.mode != MODE_MID) continue;
+    if (ps.mode != MODE_MID && ps.a.log2M == 0) continue;
+    if (ps.mode == MODE_MID && (ps.a.chirp_kind != CHIRP_COMPUTED || ps.a.load_kind != LOAD_C64))
+      continue;
+    FastInfo fi;
+    if (!fast_info(fam, ps.a.log2L, &fi)) continue;
+    const long long W = 2ll << fi.log2pw;
+    if (ps.a.I % W || ps.a.Q % W) continue;
+    if (ps.a.min.a_row * 8 >= (1ll << 32) || ps.a.mout.a_row * 8 >= (1ll << 32)) continue;
+    ps.family = fam;
+    ps.finfo = fi;
+    ps.ntiles = ps.a.Q / W;
+    ps.ftab_off = host.size();
+    host.resize(host.size() + fi.tw_count + (fi.tw_count & 1));
+    fast_tables(fam, ps.a.log2L, host.data() + ps.ftab_off);
+  }
+  if (!host.empty()) {
+    CUDA_TRY(cudaMalloc(&pl->d_ftab, host.size() * sizeof(float2)));
+    CUDA_TRY(cudaMemcpy(pl->d_ftab, host.data(), host.size() * sizeof(float2),
+                        cudaMemcpyHostToDevice));
+  }
+  CUDA_TRY(cudaDeviceGetAttribute(&pl->num_sms, cudaDevAttrMultiProcessorCount, pl->device));
+  return PBK_OK;
 }
 
 static int upload_tables(pbk_plan* pl, TableSet& ts) {
@@ -281,9 +411,9 @@ extern "C" int pbk_dedisp_plan_create(const pbk_dedisp_desc* d, pbk_plan** out) 
                 "nsamp = %lld: this build handles power-of-two lengths >= 16 only",
                 (long long)d->nsamp);
   int l[3] = {0, 0, 0};
-  const int m = choose_levels(n, l, true);
-  if (m == 0) return fail(PBK_ERR_UNSUPPORTED, "nsamp = 2^%d is too long", n);
   const long long I = d->nchan * d->npol;
+  const int m = choose_levels(n, I, l, true);
+  if (m == 0) return fail(PBK_ERR_UNSUPPORTED, "nsamp = 2^%d is too long", n);
   if (I > INT_MAX / 2) return fail(PBK_ERR_UNSUPPORTED, "nchan*npol too large");
 
   int ndev = 0;
@@ -406,6 +536,7 @@ extern "C" int pbk_dedisp_plan_create(const pbk_dedisp_desc* d, pbk_plan** out) 
   int rc = PBK_OK;
   auto cleanup = [&](int code) { pbk_plan_destroy(pl); return code; };
   if ((rc = upload_tables(pl, ts)) != PBK_OK) return cleanup(rc);
+  if ((rc = setup_fast(pl)) != PBK_OK) return cleanup(rc);
   {
     cudaError_t e = cudaMalloc(&pl->d_chanfreq, (size_t)C * sizeof(double));
     if (e == cudaSuccess)
@@ -460,7 +591,12 @@ static int run_passes(pbk_plan* pl, const void* d_in, void* d_out, const void* d
     p.a.out = role_ptr(pl, ps.out_role, d_in, d_out);
     p.a.chirp_arr = reinterpret_cast<const float2*>(d_chirp);
     const bool aligned = (((uintptr_t)p.a.in | (uintptr_t)p.a.out) & 15) == 0;
-    cudaError_t e = launch_pass(p, ps.fast && aligned, st);
+    cudaError_t e;
+    if (ps.family >= 0 && aligned)
+      e = fast_launch(ps.family, ps.a.log2L, ps.mode, p.a, pl->d_ftab + ps.ftab_off, ps.ntiles,
+                      pl->num_sms, st);
+    else
+      e = launch_pass(p, ps.fast && aligned, st);
     if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
   }
   return PBK_OK;
@@ -532,7 +668,7 @@ static int build_fft_plan(long long O, long long n, long long C, long long P, bo
                 "transform length %lld: this build handles power-of-two lengths >= 2 only",
                 (long long)n);
   int l[3] = {0, 0, 0};
-  const int m = choose_levels(ln, l, false);
+  const int m = choose_levels(ln, C * P, l, false);
   if (m == 0) return fail(PBK_ERR_UNSUPPORTED, "transform length 2^%d is too long", ln);
   const long long I = C * P;
   if (I > INT_MAX / 2 || O <= 0 || I <= 0) return fail(PBK_ERR_INVALID, "bad batch shape");
@@ -592,6 +728,7 @@ static int build_fft_plan(long long O, long long n, long long C, long long P, bo
     pl->passes.push_back(ps);
   }
   int rc = upload_tables(pl, ts);
+  if (rc == PBK_OK) rc = setup_fast(pl);
   if (rc != PBK_OK) { pbk_plan_destroy(pl); return rc; }
   if (m > 1) {
     pl->scratch_bytes = (size_t)O * n * I * 8;
@@ -668,6 +805,7 @@ extern "C" void pbk_plan_destroy(pbk_plan* pl) {
   cudaSetDevice(pl->device);
   cudaFree(pl->scratch);
   cudaFree(pl->d_tw);
+  cudaFree(pl->d_ftab);
   cudaFree(pl->d_chanfreq);
   cudaFree(pl->d_tmpf);
   cudaFree(pl->h_din);
@@ -684,6 +822,28 @@ extern "C" int pbk_plan_info(const pbk_plan* pl, int32_t* launches, int64_t* wor
   if (levels) *levels = pl->nlevels;
   if (level_log2)
     for (int i = 0; i < 3; ++i) level_log2[i] = pl->level_log2[i];
+  return PBK_OK;
+}
+
+extern "C" int pbk_plan_describe(const pbk_plan* pl, char* buf, size_t n) {
+  if (!pl || !buf || n == 0) return fail(PBK_ERR_INVALID, "NULL argument");
+  size_t off = 0;
+  buf[0] = 0;
+  for (size_t i = 0; i < pl->passes.size() && off + 1 < n; ++i) {
+    const Pass& ps = pl->passes[i];
+    const char* mode = ps.mode == MODE_FWD ? "FWD" : ps.mode == MODE_MID ? "MID" : "INV";
+    int w;
+    if (ps.family >= 0)
+      w = snprintf(buf + off, n - off, "%s%s:L=2^%d:%s:W=%d:tiles=%lld:threads=%d", i ? ";" : "",
+                   mode, ps.a.log2L, ps.family == FAMILY_R8 ? "fast-r8" : "fast-r16",
+                   2 << ps.finfo.log2pw, ps.ntiles, ps.finfo.threads);
+    else
+      w = snprintf(buf + off, n - off, "%s%s:L=2^%d:%s:W=%d:tiles=%u:threads=%d", i ? ";" : "",
+                   mode, ps.a.log2L, ps.fast ? "generic-vec" : "generic", 2 << ps.a.log2pw,
+                   ps.grid, kThreads);
+    if (w < 0) break;
+    off += (size_t)w;
+  }
   return PBK_OK;
 }
 

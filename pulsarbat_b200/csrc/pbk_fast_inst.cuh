@@ -1,0 +1,51 @@
+// pbk_fast_inst.cuh -- shared body of the per-family instantiation units.
+#pragma once
+#include <algorithm>
+
+#include "pbk_fast.cuh"
+#include "pbk_fast_launch.h"
+
+namespace pbk {
+
+template <class C>
+static void cfg_info(FastInfo* info) {
+  info->log2pw = C::LOG2PW;
+  info->tw_count = C::TW_TOTAL;
+  info->threads = C::NT;
+  info->minb = C::MINB;
+  info->smem = C::SMEM_BYTES;
+}
+
+template <int MODE, class C, bool I8>
+static cudaError_t cfg_launch_mode(const PassArgs& a, const float2* d_tables, long long ntiles,
+                                   int num_sms, cudaStream_t st) {
+  auto kern = fast_pass_kernel<MODE, C, I8>;
+  static bool attr_done[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 16 && !attr_done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_done[dev] = true;
+  }
+  const long long resident = (long long)num_sms * C::MINB;
+  const unsigned grid = (unsigned)std::min<long long>(ntiles, resident);
+  kern<<<grid, C::NT, C::SMEM_BYTES, st>>>(a, d_tables, ntiles);
+  return cudaGetLastError();
+}
+
+template <class C>
+static cudaError_t cfg_launch(int mode, const PassArgs& a, const float2* d_tables,
+                              long long ntiles, int num_sms, cudaStream_t st) {
+  switch (mode) {
+    case MODE_FWD:
+      if (a.load_kind == LOAD_I8X2)
+        return cfg_launch_mode<MODE_FWD, C, true>(a, d_tables, ntiles, num_sms, st);
+      return cfg_launch_mode<MODE_FWD, C, false>(a, d_tables, ntiles, num_sms, st);
+    case MODE_MID: return cfg_launch_mode<MODE_MID, C, false>(a, d_tables, ntiles, num_sms, st);
+    default: return cfg_launch_mode<MODE_INV, C, false>(a, d_tables, ntiles, num_sms, st);
+  }
+}
+
+}  // namespace pbk
