@@ -126,6 +126,21 @@ int pbk_detect(const void* in, void* out, int64_t nsamp, int64_t nchan, int64_t 
 int pbk_downsample(const void* in, void* out, int64_t nsamp, int64_t row_elems,
                    int64_t factor, int32_t on_device, int32_t device, void* stream);
 
+/* ---- polarisation -------------------------------------------------------------------------
+ * pbk_stokes:    (A, B) complex64 pol pairs -> [I, Q, U, V] float32 (core.py:930-966; basis
+ *                linear when circular == 0).  npairs = nsamp * nchan.
+ * pbk_pol_basis: linear <-> circular basis change (core.py:882-928).
+ * pbk_chirp:     the chirp of dedispersion.py:19-23 / 59-75 as an explicit (nsamp, nchan)
+ *                complex64 array (DispersionMeasure.chirp_from_signal).
+ */
+int pbk_stokes(const void* in, void* out, int64_t npairs, int32_t circular, int32_t on_device,
+               int32_t device, void* stream);
+int pbk_pol_basis(const void* in, void* out, int64_t npairs, int32_t to_circular,
+                  int32_t on_device, int32_t device, void* stream);
+int pbk_chirp(int64_t nsamp, int64_t nchan, double dm, double sample_rate_hz,
+              double ref_freq_hz, const double* chan_freq_hz, void* out, int32_t on_device,
+              int32_t device, void* stream);
+
 /* ---- folding (builder-defined; phase model = pulsar/predictor.py:149-160) --
  * ph_n = polyval((n0+n)/sample_rate_hz) with numpy's Horner order in FP64 without FMA
  * contraction; bin = floor((ph - floor(ph)) * nbin) mod nbin;

@@ -18,6 +18,7 @@ EXPORTS = [
     "pbk_dedisp_plan_create", "pbk_dedisp_out_shape", "pbk_dedisp_exec_host",
     "pbk_dedisp_exec_device", "pbk_fft_plan_create", "pbk_stft_plan_create",
     "pbk_fft_exec_host", "pbk_fft_exec_device", "pbk_detect", "pbk_downsample", "pbk_fold",
+    "pbk_stokes", "pbk_pol_basis", "pbk_chirp",
     "pbk_plan_destroy", "pbk_plan_info", "pbk_plan_describe", "pbk_malloc", "pbk_free", "pbk_memcpy_h2d",
     "pbk_memcpy_d2h", "pbk_device_sync",
 ]
@@ -82,6 +83,9 @@ def lib():
         L.pbk_downsample.argtypes = [vp, vp, i64, i64, i64, i32, i32, vp]
         L.pbk_fold.argtypes = [vp, i64, i64, ctypes.POINTER(dbl), i32, dbl, i64, i32, vp, vp, vp,
                                i32, i32, vp]
+        L.pbk_stokes.argtypes = [vp, vp, i64, i32, i32, i32, vp]
+        L.pbk_pol_basis.argtypes = [vp, vp, i64, i32, i32, i32, vp]
+        L.pbk_chirp.argtypes = [i64, i64, dbl, dbl, dbl, ctypes.POINTER(dbl), vp, i32, i32, vp]
         L.pbk_plan_destroy.argtypes = [vp]
         L.pbk_plan_destroy.restype = None
         L.pbk_plan_info.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i64),

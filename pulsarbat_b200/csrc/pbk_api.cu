@@ -968,6 +968,95 @@ extern "C" int pbk_fold(const void* in, int64_t nsamp, int64_t row_elems, const 
   return PBK_OK;
 }
 
+// elementwise helper shared by the host-pointer variants below
+template <typename F>
+static int run_elementwise(const void* in, void* out, size_t in_bytes, size_t out_bytes,
+                           int on_device, int device, void* stream, F launch) {
+  if (!in || !out) return fail(PBK_ERR_INVALID, "NULL data pointer");
+  CUDA_TRY(cudaSetDevice(device));
+  if (on_device) {
+    cudaError_t e = launch(in, out, reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
+    return PBK_OK;
+  }
+  DevBuf di, dout;
+  CUDA_TRY(cudaMalloc(&di.p, in_bytes ? in_bytes : 16));
+  CUDA_TRY(cudaMalloc(&dout.p, out_bytes ? out_bytes : 16));
+  cudaStream_t st = cudaStreamPerThread;
+  CUDA_TRY(cudaMemcpyAsync(di.p, in, in_bytes, cudaMemcpyHostToDevice, st));
+  cudaError_t e = launch(di.p, dout.p, st);
+  if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
+  CUDA_TRY(cudaMemcpyAsync(out, dout.p, out_bytes, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return PBK_OK;
+}
+
+extern "C" int pbk_stokes(const void* in, void* out, int64_t npairs, int32_t circular,
+                          int32_t on_device, int32_t device, void* stream) {
+  if (npairs < 0) return fail(PBK_ERR_INVALID, "bad count");
+  return run_elementwise(in, out, (size_t)npairs * 16, (size_t)npairs * 16, on_device, device,
+                         stream, [&](const void* i, void* o, cudaStream_t st) {
+                           return launch_1d(stokes_kernel, npairs, st,
+                                            reinterpret_cast<const float4*>(i),
+                                            reinterpret_cast<float4*>(o), (long long)npairs,
+                                            (int)circular);
+                         });
+}
+
+extern "C" int pbk_pol_basis(const void* in, void* out, int64_t npairs, int32_t to_circular,
+                             int32_t on_device, int32_t device, void* stream) {
+  if (npairs < 0) return fail(PBK_ERR_INVALID, "bad count");
+  return run_elementwise(in, out, (size_t)npairs * 16, (size_t)npairs * 16, on_device, device,
+                         stream, [&](const void* i, void* o, cudaStream_t st) {
+                           return launch_1d(pol_basis_kernel, npairs, st,
+                                            reinterpret_cast<const float4*>(i),
+                                            reinterpret_cast<float4*>(o), (long long)npairs,
+                                            (int)to_circular);
+                         });
+}
+
+// chirp H[k, c] (dedispersion.py:19-23) as an explicit (nsamp, nchan) complex64 array
+__global__ void __launch_bounds__(256) chirp_kernel(PassArgs p, float2* out, long long nsamp,
+                                                    long long nchan) {
+  const long long total = nsamp * nchan;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long k = i / nchan, c = i - k * nchan;
+    out[i] = chirp_value(p, p.chan_freq[c], k);
+  }
+}
+
+extern "C" int pbk_chirp(int64_t nsamp, int64_t nchan, double dm, double sample_rate_hz,
+                         double ref_freq_hz, const double* chan_freq_hz, void* out,
+                         int32_t on_device, int32_t device, void* stream) {
+  if (nsamp <= 0 || nchan <= 0 || !chan_freq_hz || !out)
+    return fail(PBK_ERR_INVALID, "bad argument");
+  if (!(sample_rate_hz > 0)) return fail(PBK_ERR_INVALID, "sample_rate_hz must be > 0");
+  CUDA_TRY(cudaSetDevice(device));
+  DevBuf df;
+  CUDA_TRY(cudaMalloc(&df.p, (size_t)nchan * 8));
+  CUDA_TRY(cudaMemcpy(df.p, chan_freq_hz, (size_t)nchan * 8, cudaMemcpyHostToDevice));
+  PassArgs a;
+  defaults(a);
+  a.N = nsamp;
+  a.chan_freq = reinterpret_cast<const double*>(df.p);
+  a.df = 1.0 / ((double)nsamp * (1.0 / sample_rate_hz));
+  if (std::isinf(ref_freq_hz)) { a.fr_sub = 0; a.inv_fr = 0; a.a0 = -1.0; }
+  else { a.fr_sub = ref_freq_hz; a.inv_fr = 1.0 / ref_freq_hz; a.a0 = 0; }
+  a.D = (1.0 / 2.41e-4) * dm * 1e12;
+  a.scale = 1.0f;
+  const size_t ob = (size_t)nsamp * nchan * 8;
+  int rc = run_elementwise(out /*unused as input*/, out, 0, ob, on_device, device, stream,
+                           [&](const void*, void* o, cudaStream_t st) {
+                             return launch_1d(chirp_kernel, nsamp * nchan, st, a,
+                                              reinterpret_cast<float2*>(o), (long long)nsamp,
+                                              (long long)nchan);
+                           });
+  if (rc == PBK_OK && on_device)
+    CUDA_TRY(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));  // df is freed here
+  return rc;
+}
+
 // ------------------------------------------------------------------------------------------
 // raw memory helpers
 // ------------------------------------------------------------------------------------------

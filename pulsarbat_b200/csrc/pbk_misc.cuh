@@ -103,6 +103,51 @@ static inline cudaError_t launch_detect(const float2* in, float* out, long long 
   return cudaGetLastError();
 }
 
+// full Stokes [I, Q, U, V] from (A, B) pol pairs (core.py:937-966, PSR/IEEE convention)
+//   linear:   I=AA+BB  Q=AA-BB  U=2Re(A*B)  V=2Im(A*B)
+//   circular: I=AA+BB  Q=2Re(A*B)  U=2Im(A*B)  V=AA-BB          (A*B = conj(A) B)
+__global__ void __launch_bounds__(256) stokes_kernel(const float4* __restrict__ in,
+                                                     float4* __restrict__ out, long long n,
+                                                     int circular) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(in + i);  // (Are, Aim, Bre, Bim)
+    const float aa = v.x * v.x + v.y * v.y;
+    const float bb = v.z * v.z + v.w * v.w;
+    const float re = v.x * v.z + v.y * v.w;   // Re(conj(A) B)
+    const float im = v.x * v.w - v.y * v.z;   // Im(conj(A) B)
+    out[i] = circular ? make_float4(aa + bb, 2.f * re, 2.f * im, aa - bb)
+                      : make_float4(aa + bb, aa - bb, 2.f * re, 2.f * im);
+  }
+}
+
+// basis change (core.py:882-928): to_circular: [X - iY, X + iY]/sqrt2 ; to_linear: [L + R, i(L - R)]/sqrt2
+__global__ void __launch_bounds__(256) pol_basis_kernel(const float4* __restrict__ in,
+                                                        float4* __restrict__ out, long long n,
+                                                        int to_circular) {
+  const float h = 0.70710678118654752440f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(in + i);
+    float4 o;
+    if (to_circular) {   // L = X - iY = (Xre + Yim, Xim - Yre); R = X + iY = (Xre - Yim, Xim + Yre)
+      o = make_float4((v.x + v.w) * h, (v.y - v.z) * h, (v.x - v.w) * h, (v.y + v.z) * h);
+    } else {             // X = L + R ; Y = i (L - R) = (-(Lim - Rim), Lre - Rre)
+      o = make_float4((v.x + v.z) * h, (v.y + v.w) * h, -(v.y - v.w) * h, (v.x - v.z) * h);
+    }
+    out[i] = o;
+  }
+}
+
+template <typename K, typename... A>
+static inline cudaError_t launch_1d(K kern, long long n, cudaStream_t st, A... args) {
+  if (n <= 0) return cudaSuccess;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148ll * 32) blocks = 148ll * 32;
+  kern<<<(unsigned)blocks, 256, 0, st>>>(args...);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------
 // fold
 // ------------------------------------------------------------------------------------------

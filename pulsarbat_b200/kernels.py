@@ -1,0 +1,370 @@
+"""Typed wrappers over the C ABI (include/pbk.h) for numpy blocks and device arrays.
+
+One function per reference operation on the hot path.  Every function accepts either a numpy
+array (host round trip through ``*_exec_host``; safe to call from several threads, which is what
+a dask ``map_blocks`` does -- reference transforms.py:49-50) or a
+:class:`~pulsarbat_b200.device.DeviceArray` (no copies; work is queued on torch's current
+stream).  complex128 input is computed in complex64 on the GPU and returned as complex128, so the
+reference's dtype contract holds (core.py:773, fft.py:34) at complex64 precision.
+"""
+
+import collections
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+from . import _lib as L
+from .device import DeviceArray
+
+__all__ = ["default_device", "dedisperse", "chirp", "detect", "stokes", "pol_basis",
+           "downsample", "fft", "stft", "istft", "fold", "clear_plan_cache"]
+
+
+def default_device():
+    """CUDA ordinal used for host-array calls: $PBK_DEVICE, else $LOCAL_RANK, else 0."""
+    for k in ("PBK_DEVICE", "LOCAL_RANK"):
+        v = os.environ.get(k)
+        if v is not None and v.strip().lstrip("-").isdigit():
+            return int(v)
+    return 0
+
+
+# --------------------------------------------------------------------------------------------
+# plan cache: plans own their scratch (gigabytes for the large configs), so the cache is small
+# --------------------------------------------------------------------------------------------
+_MAX_PLANS = int(os.environ.get("PBK_PLAN_CACHE", "6"))
+_cache = collections.OrderedDict()
+_cache_lock = threading.Lock()
+
+
+class _Entry:
+    __slots__ = ("plan", "lock")
+
+    def __init__(self, plan):
+        self.plan = plan
+        self.lock = threading.Lock()
+
+
+def _get_plan(key, factory):
+    with _cache_lock:
+        ent = _cache.get(key)
+        if ent is not None:
+            _cache.move_to_end(key)
+            return ent
+        ent = _Entry(factory())
+        _cache[key] = ent
+        while len(_cache) > _MAX_PLANS:
+            for k, old in _cache.items():
+                if old is not ent and old.lock.acquire(blocking=False):
+                    try:
+                        old.plan.destroy()
+                    finally:
+                        old.lock.release()
+                    del _cache[k]
+                    break
+            else:
+                break
+        return ent
+
+
+def clear_plan_cache():
+    with _cache_lock:
+        for ent in _cache.values():
+            with ent.lock:
+                ent.plan.destroy()
+        _cache.clear()
+
+
+def _stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _is_dev(x):
+    return isinstance(x, DeviceArray)
+
+
+def _host_c64(x):
+    """(contiguous complex64 array, original dtype)."""
+    x = np.asarray(x)
+    if not np.iscomplexobj(x):
+        raise TypeError(f"expected complex data, got {x.dtype}")
+    return np.ascontiguousarray(x, dtype=np.complex64), x.dtype
+
+
+def _real_of(cdtype):
+    return np.float64 if np.dtype(cdtype) == np.complex128 else np.float32
+
+
+# --------------------------------------------------------------------------------------------
+# coherent dedispersion            reference: transforms/dedispersion.py:81-133
+# --------------------------------------------------------------------------------------------
+def dedisperse(data, *, dm, sample_rate_hz, chan_freq_hz, ref_freq_hz, crop=None,
+               out_kind=L.OUT_C64, downsample=1, chirp_array=None, int8=False, device=None):
+    """ifft(fft(x, axis=0) * H, axis=0)[start:stop] (+ optional fused detection / time sum).
+
+    ``data`` is (nsamp, nchan, ...) complex, or with ``int8=True`` (nsamp, nchan, ..., 2) int8
+    (re, im) pairs.  ``crop`` is the (start, stop) computed by the caller as in
+    dedispersion.py:127-131; None keeps all rows.  Returns an array shaped (rows, nchan, ...)
+    (Stokes I drops the pol axis).
+    """
+    shape = tuple(data.shape)
+    body = shape[:-1] if int8 else shape
+    nsamp, nchan = body[0], body[1]
+    trailing = body[2:]
+    npol = int(np.prod(trailing)) if trailing else 1
+    start, stop = (0, nsamp) if crop is None else (int(crop[0]), int(crop[1]))
+    if stop <= start:
+        start, stop = 0, 0
+    freqs = np.ascontiguousarray(chan_freq_hz, dtype=np.float64)
+    dev = (data.device if _is_dev(data) else (default_device() if device is None else device))
+    key = ("dedisp", nsamp, nchan, npol, bool(int8), int(out_kind), float(dm),
+           float(sample_rate_hz), float(ref_freq_hz), freqs.tobytes(), start, stop,
+           int(downsample), chirp_array is not None, dev)
+    ent = _get_plan(key, lambda: L.DedispPlan(
+        nsamp=nsamp, nchan=nchan, npol=npol, dm=dm, sample_rate_hz=sample_rate_hz,
+        ref_freq_hz=ref_freq_hz, chan_freq_hz=freqs, crop=(start, stop),
+        in_dtype=L.PBK_I8X2 if int8 else L.PBK_C64, out_kind=out_kind, downsample=downsample,
+        explicit_chirp=chirp_array is not None, device=dev))
+    plan = ent.plan
+    out_trailing = (nchan,) if out_kind == L.OUT_STOKES_I else (nchan,) + trailing
+    out_shape = (plan.out_rows,) + out_trailing
+
+    if _is_dev(data):
+        x = data.contiguous()
+        if not int8 and x.dtype != np.complex64:
+            x = x.astype(np.complex64)
+        out = DeviceArray.empty(out_shape, np.complex64 if out_kind == L.OUT_C64 else np.float32,
+                                dev)
+        ch = None
+        if chirp_array is not None:
+            ch = chirp_array if _is_dev(chirp_array) else DeviceArray.from_numpy(
+                np.ascontiguousarray(np.asarray(chirp_array).reshape(nsamp, nchan),
+                                     dtype=np.complex64), dev)
+        with ent.lock:
+            plan.exec_device(x.ptr, out.ptr, None if ch is None else ch.ptr, _stream())
+        return out
+
+    if int8:
+        x, odt = np.ascontiguousarray(data, dtype=np.int8), np.complex64
+    else:
+        x, odt = _host_c64(data)
+    out = np.empty(out_shape, np.complex64 if out_kind == L.OUT_C64 else np.float32)
+    ch = None
+    if chirp_array is not None:
+        ch = np.ascontiguousarray(np.asarray(chirp_array).reshape(nsamp, nchan),
+                                  dtype=np.complex64)
+    with ent.lock:
+        plan.exec_host(x, out, ch)
+    if out_kind == L.OUT_C64:
+        return out if odt == np.complex64 else out.astype(odt)
+    rdt = _real_of(odt)
+    return out if rdt == np.float32 else out.astype(rdt)
+
+
+def chirp(nsamp, nchan, *, dm, sample_rate_hz, ref_freq_hz, chan_freq_hz, device=None):
+    """(nsamp, nchan) complex64 chirp of dedispersion.py:19-23, generated on the GPU."""
+    freqs = np.ascontiguousarray(chan_freq_hz, dtype=np.float64)
+    out = np.empty((nsamp, nchan), np.complex64)
+    dev = default_device() if device is None else device
+    L.check(L.lib().pbk_chirp(nsamp, nchan, float(dm), float(sample_rate_hz), float(ref_freq_hz),
+                              freqs.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), L.ptr(out),
+                              0, dev, None))
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# detection / polarisation        reference: core.py:766-774, 882-966
+# --------------------------------------------------------------------------------------------
+def detect(data, stokes=False, downsample=1, device=None):
+    """re^2+im^2 per element, or |A|^2+|B|^2 over the pol axis (axis 2) when ``stokes``."""
+    shape = tuple(data.shape)
+    nsamp, nchan = shape[0], shape[1]
+    npol = int(np.prod(shape[2:])) if len(shape) > 2 else 1
+    if stokes and (len(shape) < 3 or shape[2] != 2 or npol != 2):
+        raise ValueError("Stokes I needs shape (nsamp, nchan, 2)")
+    rows = nsamp // int(downsample)
+    out_shape = (rows, nchan) if stokes else (rows,) + shape[1:]
+    kind = L.OUT_STOKES_I if stokes else L.OUT_INTENSITY
+    if _is_dev(data):
+        x = data.contiguous()
+        if x.dtype != np.complex64:
+            x = x.astype(np.complex64)
+        out = DeviceArray.empty(out_shape, np.float32, x.device)
+        L.check(L.lib().pbk_detect(L.ptr(x.ptr), L.ptr(out.ptr), nsamp, nchan, npol, kind,
+                                   int(downsample), 1, x.device, ctypes.c_void_p(_stream())))
+        return out
+    x, odt = _host_c64(data)
+    out = np.empty(out_shape, np.float32)
+    dev = default_device() if device is None else device
+    L.check(L.lib().pbk_detect(L.ptr(x), L.ptr(out), nsamp, nchan, npol, kind, int(downsample),
+                               0, dev, None))
+    rdt = _real_of(odt)
+    return out if rdt == np.float32 else out.astype(rdt)
+
+
+def _pairs_op(data, fn, flag, out_real, device):
+    shape = tuple(data.shape)
+    if len(shape) < 3 or shape[2] != 2:
+        raise ValueError("expected shape (nsamp, nchan, 2, ...)")
+    if len(shape) > 3:
+        raise L.PbkUnsupported(-2, "polarisation kernels take exactly (nsamp, nchan, 2)")
+    npairs = shape[0] * shape[1]
+    if _is_dev(data):
+        x = data.contiguous()
+        if x.dtype != np.complex64:
+            x = x.astype(np.complex64)
+        oshape = shape[:2] + ((4,) if out_real else (2,))
+        out = DeviceArray.empty(oshape, np.float32 if out_real else np.complex64, x.device)
+        L.check(fn(L.ptr(x.ptr), L.ptr(out.ptr), npairs, flag, 1, x.device,
+                   ctypes.c_void_p(_stream())))
+        return out
+    x, odt = _host_c64(data)
+    oshape = shape[:2] + ((4,) if out_real else (2,))
+    out = np.empty(oshape, np.float32 if out_real else np.complex64)
+    dev = default_device() if device is None else device
+    L.check(fn(L.ptr(x), L.ptr(out), npairs, flag, 0, dev, None))
+    if out_real:
+        rdt = _real_of(odt)
+        return out if rdt == np.float32 else out.astype(rdt)
+    return out if odt == np.complex64 else out.astype(odt)
+
+
+def stokes(data, pol_type, device=None):
+    """(nsamp, nchan, 2) complex -> (nsamp, nchan, 4) [I, Q, U, V] (core.py:930-966)."""
+    if pol_type not in ("linear", "circular"):
+        raise ValueError("pol_type must be in {'linear', 'circular'}")
+    return _pairs_op(data, L.lib().pbk_stokes, int(pol_type == "circular"), True, device)
+
+
+def pol_basis(data, to_circular, device=None):
+    """Linear <-> circular basis change (core.py:882-928)."""
+    return _pairs_op(data, L.lib().pbk_pol_basis, int(bool(to_circular)), False, device)
+
+
+def downsample(data, factor, device=None):
+    """out[j] = sum_{m<M} data[j*M+m] along time (float32; tail dropped)."""
+    shape = tuple(data.shape)
+    relems = int(np.prod(shape[1:])) if len(shape) > 1 else 1
+    rows = shape[0] // int(factor)
+    if _is_dev(data):
+        x = data.contiguous()
+        if x.dtype != np.float32:
+            x = x.astype(np.float32)
+        out = DeviceArray.empty((rows,) + shape[1:], np.float32, x.device)
+        L.check(L.lib().pbk_downsample(L.ptr(x.ptr), L.ptr(out.ptr), shape[0], relems,
+                                       int(factor), 1, x.device, ctypes.c_void_p(_stream())))
+        return out
+    x = np.asarray(data)
+    odt = x.dtype
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.empty((rows,) + shape[1:], np.float32)
+    dev = default_device() if device is None else device
+    L.check(L.lib().pbk_downsample(L.ptr(x), L.ptr(out), shape[0], relems, int(factor), 0, dev,
+                                   None))
+    return out if odt == np.float32 else out.astype(odt)
+
+
+# --------------------------------------------------------------------------------------------
+# FFT / channelize                 reference: fft.py:30-48, contrib/misc.py:17-93
+# --------------------------------------------------------------------------------------------
+def _run_fft_plan(key, factory, data, out_shape):
+    ent = _get_plan(key, factory)
+    if _is_dev(data):
+        x = data.contiguous()
+        if x.dtype != np.complex64:
+            x = x.astype(np.complex64)
+        out = DeviceArray.empty(out_shape, np.complex64, x.device)
+        with ent.lock:
+            ent.plan.exec_device(x.ptr, out.ptr, _stream())
+        return out
+    x, odt = _host_c64(data)
+    out = np.empty(out_shape, np.complex64)
+    with ent.lock:
+        ent.plan.exec_host(x, out)
+    return out if odt == np.complex64 else out.astype(odt)
+
+
+def fft(data, axis=0, inverse=False, device=None):
+    """Complex FFT along one axis with scipy's "backward" normalisation (fft.py:30-48)."""
+    shape = tuple(data.shape)
+    axis = axis % len(shape)
+    outer = int(np.prod(shape[:axis])) if axis > 0 else 1
+    n = shape[axis]
+    inner = int(np.prod(shape[axis + 1:])) if axis + 1 < len(shape) else 1
+    dev = data.device if _is_dev(data) else (default_device() if device is None else device)
+    key = ("fft", outer, n, inner, bool(inverse), dev)
+    return _run_fft_plan(key, lambda: L.FFTPlan(outer, n, inner, inverse=inverse, device=dev),
+                         data, shape)
+
+
+def stft(data, nperseg, device=None):
+    """(nseg*n, nchan, ...) -> (nseg, nchan*n, ...), fftshift-ed and scaled by 1/n
+    (misc.py:41-52).  ``data`` must already be trimmed to a multiple of nperseg."""
+    shape = tuple(data.shape)
+    n = int(nperseg)
+    nseg, nchan = shape[0] // n, shape[1]
+    npol = int(np.prod(shape[2:])) if len(shape) > 2 else 1
+    dev = data.device if _is_dev(data) else (default_device() if device is None else device)
+    key = ("stft", nseg, n, nchan, npol, False, dev)
+    return _run_fft_plan(key, lambda: L.STFTPlan(nseg, n, nchan, npol, inverse=False, device=dev),
+                         data, (nseg, nchan * n) + shape[2:])
+
+
+def istft(data, nperseg, device=None):
+    """(nseg, nchan_out*n, ...) -> (nseg*n, nchan_out, ...) (misc.py:81-91); input untouched."""
+    shape = tuple(data.shape)
+    n = int(nperseg)
+    nseg, nchan = shape[0], shape[1] // n
+    npol = int(np.prod(shape[2:])) if len(shape) > 2 else 1
+    dev = data.device if _is_dev(data) else (default_device() if device is None else device)
+    key = ("stft", nseg, n, nchan, npol, True, dev)
+    return _run_fft_plan(key, lambda: L.STFTPlan(nseg, n, nchan, npol, inverse=True, device=dev),
+                         data, (nseg * n, nchan) + shape[2:])
+
+
+# --------------------------------------------------------------------------------------------
+# fold                             builder-defined
+# --------------------------------------------------------------------------------------------
+def fold(data, coeffs, sample_rate_hz, nbin, n0=0, profile=None, counts=None, want_bins=False,
+         device=None):
+    """Accumulate ``data`` (nsamp, ...) float32 into ``nbin`` phase bins.
+
+    phase(n) = polyval((n0+n)/sample_rate_hz, coeffs) in numpy's Horner order (FP64, no FMA);
+    bin = floor(frac(phase)*nbin) mod nbin.  Returns (profile (nbin, ...) float32, counts (nbin,)
+    int64[, bins (nsamp,) int32]); ``profile``/``counts`` are accumulated into when given.
+    """
+    shape = tuple(data.shape)
+    nsamp = shape[0]
+    relems = int(np.prod(shape[1:])) if len(shape) > 1 else 1
+    c = np.ascontiguousarray(coeffs, dtype=np.float64)
+    cp = c.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    if _is_dev(data):
+        x = data.contiguous()
+        if x.dtype != np.float32:
+            x = x.astype(np.float32)
+        dev = x.device
+        import torch
+        if profile is None:
+            profile = DeviceArray(torch.zeros((nbin,) + shape[1:], dtype=torch.float32,
+                                              device=f"cuda:{dev}"))
+        if counts is None:
+            counts = DeviceArray(torch.zeros((nbin,), dtype=torch.int64, device=f"cuda:{dev}"))
+        bins = DeviceArray.empty((nsamp,), np.int32, dev) if want_bins else None
+        L.check(L.lib().pbk_fold(L.ptr(x.ptr), nsamp, relems, cp, len(c), float(sample_rate_hz),
+                                 int(n0), int(nbin), L.ptr(profile.ptr), L.ptr(counts.ptr),
+                                 L.ptr(bins.ptr) if bins is not None else None, 1, dev,
+                                 ctypes.c_void_p(_stream())))
+        return (profile, counts, bins) if want_bins else (profile, counts)
+    x = np.ascontiguousarray(data, dtype=np.float32)
+    dev = default_device() if device is None else device
+    if profile is None:
+        profile = np.zeros((nbin,) + shape[1:], np.float32)
+    if counts is None:
+        counts = np.zeros((nbin,), np.int64)
+    bins = np.empty((nsamp,), np.int32) if want_bins else None
+    L.check(L.lib().pbk_fold(L.ptr(x), nsamp, relems, cp, len(c), float(sample_rate_hz), int(n0),
+                             int(nbin), L.ptr(profile), L.ptr(counts), L.ptr(bins), 0, dev, None))
+    return (profile, counts, bins) if want_bins else (profile, counts)
