@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 coherent-dedispersion hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2]
+
+One "step" = one pass of the fused hot path over one block of synthetic baseband:
+  cfg2: DualPolarizationSignal (2^22 samples, 64 channels, 2 pol) complex64, 400-800 MHz,
+        DM = 100, coherent dedispersion + Stokes I + x64 time sum (BASELINE.json configs[1]).
+        The reference's crop is EMPTY at this DM, so the timed call keeps the
+        whole circular result (crop = (0, N)), which is what parity is asserted on.
+With N > 1 ranks (torchrun, one process per GPU) rank r processes time block r of the same band:
+overlap-save blocks are independent, there is no data-path collective, scaling is weak.
+
+Printed JSON (rank 0): `value` = Gsamples/s over all ranks with the block resident in HBM, timed
+with CUDA events, max over ranks; `e2e` = the same metric through the public API with host
+(pinned) numpy input, H2D and D2H inside the timed region; `roofline` = the dominant kernel's
+read+write bytes / its CUDA-event duration against MEASURED_PEAKS.json; `cpu_baseline` = the
+oracle (scipy.fft restatement of the reference) on this box's host cores on a bounded sample.
+`--impl reference` times that CPU restatement alone (the reference is pure Python on scipy and
+cannot be imported in this image: astropy/dask are absent).
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "dedispersed complex Gsamples/s"
+UNIT = "Gsamples/s"
+
+WORKLOADS = {
+    # name: N, C, P, dm, sample_rate (= channel bandwidth), band centre, output, time sum
+    "cfg2": dict(N=2 ** 22, C=64, P=2, dm=100.0, sr=6.25e6, fcen=600e6, stokes=True, ds=64,
+                 int8=False,
+                 text="DualPolarizationSignal 2^22 x 64 chan x 2 pol c64, 400-800 MHz, DM=100, "
+                      "coherent dedispersion + Stokes I + x64 time sum, pre-crop circular result"),
+    "cfg2_c64": dict(N=2 ** 22, C=64, P=2, dm=100.0, sr=6.25e6, fcen=600e6, stokes=None, ds=1,
+                     int8=False, text="cfg2 geometry, complex64 voltages out"),
+    "cfg3_shard": dict(N=2 ** 22, C=128, P=2, dm=100.0, sr=390625.0, fcen=600e6, stokes=None,
+                       ds=1, int8=True,
+                       text="one GPU's shard of cfg3: int8 complex 2^22 x 128 chan x 2 pol -> c64"),
+    "cfg1": dict(N=2 ** 20, C=1, P=1, dm=71.0, sr=16e6, fcen=400e6, stokes=None, ds=1, int8=False,
+                 text="BasebandSignal 2^20 x 1 chan c64, 400 MHz, 16 MHz, DM=71"),
+    "small": dict(N=2 ** 16, C=16, P=2, dm=3.0, sr=6.25e6, fcen=600e6, stokes=True, ds=64,
+                  int8=False, text="CI-sized smoke workload"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def chan_freqs(w):
+    """Channel centre frequencies, freq_align='center' (reference core.py:569-574)."""
+    return w["fcen"] + w["sr"] * (np.arange(w["C"]) + 0.5 - w["C"] / 2)
+
+
+# ------------------------------------------------------------------------------------------
+# CPU restatement of the reference (oracle) -- cpu_baseline leg and --impl reference
+# ------------------------------------------------------------------------------------------
+def cpu_step(x, w, freqs, threads):
+    """Reference arithmetic (dedispersion.py:81-133 + core.py:948 + time sum) on a host block
+    x (N, c, P); channels are spread over a thread pool ("dask threads", transforms.py:49-50)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import pbk_oracle as orc
+    N, c = x.shape[0], x.shape[1]
+    per = max(1, threads // max(1, c))
+
+    def one(i):
+        chirp = orc.chirp_from_signal(w["dm"], N, w["sr"], freqs[i:i + 1], w["fcen"])
+        y, _, _ = orc.coherent_dedispersion(x[:, i:i + 1], w["dm"], sample_rate=w["sr"],
+                                            center_freq=freqs[i], ref_freq=w["fcen"],
+                                            chirp=chirp, crop=False, workers=per)
+        if w["stokes"] is True:
+            y = orc.stokes_I(y)
+        elif w["stokes"] is False:
+            y = orc.to_intensity(y)
+        if w["ds"] > 1:
+            y = orc.downsample(y, w["ds"])
+        return y
+
+    with ThreadPoolExecutor(max_workers=min(threads, c)) as ex:
+        return list(ex.map(one, range(c)))
+
+
+def cpu_block(w, nchan, seed=8):
+    rng = np.random.default_rng(seed)
+    shape = (w["N"], nchan, w["P"])
+    x = np.empty(shape, np.complex64)
+    x.real = rng.standard_normal(shape, dtype=np.float32)
+    x.imag = rng.standard_normal(shape, dtype=np.float32)
+    return x
+
+
+def cpu_calibrate(w, freqs, threads, target_s):
+    """Pick how many channels one CPU step processes so that it takes about target_s."""
+    x1 = cpu_block(w, 1)
+    t0 = time.perf_counter()
+    cpu_step(x1, w, freqs[:1], threads)
+    t1 = time.perf_counter() - t0           # one channel using every thread on its P columns
+    x1 = cpu_block(w, min(threads, w["C"], 4))
+    t0 = time.perf_counter()
+    cpu_step(x1, w, freqs[:x1.shape[1]], threads)
+    tn = (time.perf_counter() - t0) / x1.shape[1]
+    per_chan = min(t1, tn)
+    return int(max(1, min(w["C"], round(target_s / max(per_chan, 1e-3)))))
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    freqs = chan_freqs(w)
+    nch = cpu_calibrate(w, freqs, threads, target_s=4.0)
+    x = cpu_block(w, nch)
+    for _ in range(args.warmup):
+        cpu_step(x, w, freqs[:nch], threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_step(x, w, freqs[:nch], threads)
+    dt = time.perf_counter() - t0
+    nsamp = w["N"] * nch * w["P"]
+    val = nsamp * args.steps / dt / 1e9
+    sample = (f"{nch} of {w['C']} channels x {w['P']} pol x 2^{int(np.log2(w['N']))} samples per "
+              f"step, chirp generation included, scipy.fft + thread pool")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c64",
+        "data": "synthetic",
+        "config": {"workload": w["text"], "name": args.workload, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                 "100", "-i", str(self.device)], stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.perf_counter(), ln.strip()))
+
+    def stop(self, t_begin, t_end):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [ln for (t, ln) in self.lines if t_begin <= t <= t_end + 0.1] or \
+               [ln for (_, ln) in self.lines]
+        for ln in rows:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------
+def run_b200(args, w):
+    import torch
+    import torch.distributed as dist
+
+    import pulsarbat_b200 as pb
+    from pulsarbat_b200 import _lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    os.environ["PBK_DEVICE"] = str(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    N, C, P = w["N"], w["C"], w["P"]
+    freqs = chan_freqs(w)
+    out_kind = L.OUT_C64 if w["stokes"] is None else (L.OUT_STOKES_I if w["stokes"] else
+                                                      L.OUT_INTENSITY)
+    plan = L.DedispPlan(nsamp=N, nchan=C, npol=P, dm=w["dm"], sample_rate_hz=w["sr"],
+                        ref_freq_hz=w["fcen"], chan_freq_hz=freqs, crop=(0, N),
+                        in_dtype=L.PBK_I8X2 if w["int8"] else L.PBK_C64, out_kind=out_kind,
+                        downsample=w["ds"], device=local)
+    info = plan.info()
+    desc = plan.describe().split(";") + (["downsample"] if w["ds"] > 1 else [])
+    K, W = args.steps, args.warmup
+
+    # ---- device-resident run -----------------------------------------------------------
+    g = torch.Generator(device=dev)
+    g.manual_seed(8 + rank)          # rank r holds time block r of the stream
+    if w["int8"]:
+        x = torch.randint(-127, 128, (N, C, P, 2), device=dev, dtype=torch.int8, generator=g)
+    else:
+        x = torch.randn((N, C, P, 2), device=dev, dtype=torch.float32, generator=g)
+    in_bytes = x.numel() * x.element_size()
+    out_bytes = plan.out_rows * plan.row_elems * plan.elem_bytes
+    out = torch.empty(max(out_bytes, 16), device=dev, dtype=torch.uint8)
+    stream = torch.cuda.current_stream()
+    st = stream.cuda_stream
+    for _ in range(W):
+        plan.exec_device(x.data_ptr(), out.data_ptr(), None, st)
+    plan.profile(K)
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.perf_counter()
+    e0.record(stream)
+    for _ in range(K):
+        plan.exec_device(x.data_ptr(), out.data_ptr(), None, st)
+    e1.record(stream)
+    barrier()
+    t_end = time.perf_counter()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    per_launch = np.array([plan.profile_read(i) for i in range(K)])  # (K, launches)
+    plan.profile(0)
+    nsamp = N * C * P
+    value = world * nsamp * K / (ms_total * 1e-3) / 1e9
+
+    # keep the GPU busy a little longer so the 100 ms clock sampler sees load, untimed
+    if sampler:
+        t_busy = time.perf_counter()
+        while time.perf_counter() - t_busy < 0.6:
+            plan.exec_device(x.data_ptr(), out.data_ptr(), None, st)
+            torch.cuda.synchronize()
+        clocks = sampler.stop(t_begin, time.perf_counter())
+    else:
+        clocks = None
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------
+    avg = per_launch.mean(axis=0)
+    top = int(np.argmax(avg))
+    peak, peak_src = peaks()
+    # every FFT pass reads the block once and writes it once: first pass reads the input dtype,
+    # the last pass writes the output kind, the others move complex64 (8 B) both ways
+    npass = len(desc) - (1 if w["ds"] > 1 else 0)
+    rd = [in_bytes if i == 0 else nsamp * 8 for i in range(npass)]
+    full_out = plan.row_elems * N * plan.elem_bytes
+    wr = [full_out if i == npass - 1 else nsamp * 8 for i in range(npass)]
+    if w["ds"] > 1:
+        rd.append(full_out)
+        wr.append(out_bytes)
+    kbytes = rd[top] + wr[top]
+    achieved = kbytes / (avg[top] * 1e-3) / 1e9
+    op_bytes = in_bytes + out_bytes                   # each input/output byte once
+    op_achieved = op_bytes * K / (ms_total * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "kernel": desc[top], "kernel_ms": float(avg[top]),
+        "kernel_share_of_step": float(avg[top] / avg.sum()),
+        "kernel_bytes_per_launch": int(kbytes),
+        "launch_ms": {d: float(a) for d, a in zip(desc, avg)},
+        "whole_op": {"bytes_per_step": int(op_bytes), "achieved": op_achieved,
+                     "frac": op_achieved / peak,
+                     "note": "compulsory bytes of the fused op (input once + output once) over "
+                             "the whole step time"},
+    }
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        with open(traffic_file) as f:
+            tr = json.load(f)
+        roofline["traffic"] = tr.get(args.workload, {}).get(desc[top].split(":")[0])
+
+    # ---- end to end through the public API, host buffers ---------------------------------
+    del x
+    torch.cuda.empty_cache()
+    e2e = None
+    if not args.no_e2e and not w["int8"]:
+        hx = torch.empty((N, C, P, 2), dtype=torch.float32, pin_memory=True)
+        hx.normal_(generator=torch.Generator().manual_seed(8 + rank))
+        hnp = hx.numpy().view(np.complex64).reshape(N, C, P)
+        u = pb.units
+        cls = pb.DualPolarizationSignal if P == 2 else pb.BasebandSignal
+        kw = dict(sample_rate=w["sr"] * u.Hz, center_freq=w["fcen"] * u.Hz)
+        if P == 2:
+            kw["pol_type"] = "linear"
+        z = cls(hnp if P == 2 else hnp.reshape(N, C), **kw)
+        dm = pb.DM(w["dm"])
+
+        def call():
+            if w["stokes"] is None:
+                # crop is empty at this DM: keep the circular result through the kernel wrapper
+                return pb.kernels.dedisperse(z.data, dm=w["dm"], sample_rate_hz=w["sr"],
+                                             chan_freq_hz=z.channel_freqs_hz,
+                                             ref_freq_hz=w["fcen"], crop=None)
+            return pb.dedisperse_detect(z, dm, stokes_I=bool(w["stokes"]), downsample=w["ds"],
+                                        crop=False)
+        ke = max(1, min(K, args.e2e_steps))
+        for _ in range(min(W, 2)):
+            r = call()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            r = call()
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        rbytes = int(np.asarray(r.data if hasattr(r, "data") and not isinstance(r, np.ndarray)
+                                else r).nbytes)
+        e2e = {"value": world * nsamp * ke / dt / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": int(hnp.nbytes), "d2h_bytes_per_step": rbytes,
+               "steps": ke, "ms_per_step": dt / ke * 1e3,
+               "api": "pulsarbat_b200.dedisperse_detect(DualPolarizationSignal(numpy, pinned))"}
+        del hx, hnp, z
+
+    # ---- CPU baseline (rank 0, single-GPU run only) --------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        nch = cpu_calibrate(w, freqs, threads, target_s=12.0)
+        xb = cpu_block(w, nch)
+        t0 = time.perf_counter()
+        cpu_step(xb, w, freqs[:nch], threads)
+        dt = time.perf_counter() - t0
+        cpu = {"value": w["N"] * nch * P / dt / 1e9, "unit": UNIT, "cores": threads,
+               "kind": "port",
+               "sample": f"{nch} of {C} channels x {P} pol x 2^{int(np.log2(N))} samples, one "
+                         f"pass, chirp generation included ({dt:.1f} s)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "c64", "data": "synthetic",
+            "config": {"workload": w["text"], "name": args.workload,
+                       "levels": info["levels"], "plan": desc,
+                       "parallelism": f"time-block sharding x{world}, no collective",
+                       "l2": f"input block {in_bytes / 2**20:.0f} MiB per GPU exceeds the 126 MB "
+                             "L2, no flush needed"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": int(K * info["launches"]),
+        }
+        print(json.dumps(line), flush=True)
+    plan.destroy()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_b200(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -161,6 +161,14 @@ int pbk_plan_info(const pbk_plan* plan, int32_t* launches, int64_t* workspace_by
 /* human-readable list of the passes of a plan: "FWD:L=2^11:fast-r8:W=4:tiles=65536:threads=512;..." */
 int pbk_plan_describe(const pbk_plan* plan, char* buf, size_t n);
 
+/* Per-launch device timing for benchmarks.  pbk_plan_profile(plan, nslots) makes every later
+ * execution record a CUDA event before each kernel launch and after the last one, on the
+ * execution stream, into slot (execution count mod nslots); nslots = 0 switches it off.
+ * After synchronising, pbk_plan_profile_read returns the duration in ms of each of the plan's
+ * `launches` kernels (pbk_plan_info) for one slot. */
+int pbk_plan_profile(pbk_plan* plan, int32_t nslots);
+int pbk_plan_profile_read(pbk_plan* plan, int32_t slot, float* ms, int32_t n);
+
 /* raw device-memory helpers so a ctypes caller needs no other CUDA binding */
 int pbk_malloc(void** dptr, size_t bytes, int32_t device);
 int pbk_free(void* dptr, int32_t device);

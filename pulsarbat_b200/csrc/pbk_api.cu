@@ -113,7 +113,18 @@ struct pbk_plan {
   pbk_dedisp_desc desc{};
   int64_t out_rows = 0, row_elems = 0, elem_bytes = 0, full_rows = 0;
   int launches = 0;
+  // optional per-launch device timing (pbk_plan_profile): ring of event sets, one per execution
+  std::vector<std::vector<cudaEvent_t>> prof;
+  long long prof_next = 0;
+  int prof_cur = -1;
 };
+
+static void prof_mark(pbk_plan* pl, int idx, cudaStream_t st) {
+  if (pl->prof_cur >= 0) cudaEventRecord(pl->prof[pl->prof_cur][idx], st);
+}
+static void prof_begin(pbk_plan* pl) {
+  pl->prof_cur = pl->prof.empty() ? -1 : (int)(pl->prof_next++ % (long long)pl->prof.size());
+}
 
 static int ilog2_exact(int64_t v) {
   if (v <= 0 || (v & (v - 1))) return -1;
@@ -585,7 +596,10 @@ static void* role_ptr(const pbk_plan* pl, int role, const void* uin, void* uout)
 
 static int run_passes(pbk_plan* pl, const void* d_in, void* d_out, const void* d_chirp,
                       cudaStream_t st) {
+  prof_begin(pl);
+  int pidx = 0;
   for (auto& ps : pl->passes) {
+    prof_mark(pl, pidx++, st);
     Pass p = ps;
     p.a.in = role_ptr(pl, ps.in_role, d_in, d_out);
     p.a.out = role_ptr(pl, ps.out_role, d_in, d_out);
@@ -599,6 +613,7 @@ static int run_passes(pbk_plan* pl, const void* d_in, void* d_out, const void* d
       e = launch_pass(p, ps.fast && aligned, st);
     if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
   }
+  prof_mark(pl, pidx, st);
   return PBK_OK;
 }
 
@@ -618,6 +633,7 @@ extern "C" int pbk_dedisp_exec_device(pbk_plan* pl, const void* d_in, void* d_ou
                                       reinterpret_cast<float*>(d_out), pl->out_rows,
                                       pl->row_elems, pl->desc.downsample, st);
     if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "downsample launch: %s", cudaGetErrorString(e));
+    prof_mark(pl, (int)pl->passes.size() + 1, st);
   }
   return PBK_OK;
 }
@@ -800,9 +816,45 @@ extern "C" int pbk_fft_exec_host(pbk_plan* pl, const void* in, void* out) {
   return PBK_OK;
 }
 
+static void prof_free(pbk_plan* pl) {
+  for (auto& set : pl->prof)
+    for (auto ev : set) cudaEventDestroy(ev);
+  pl->prof.clear();
+  pl->prof_next = 0;
+  pl->prof_cur = -1;
+}
+
+extern "C" int pbk_plan_profile(pbk_plan* pl, int32_t nslots) {
+  if (!pl) return fail(PBK_ERR_INVALID, "plan is NULL");
+  if (nslots < 0 || nslots > 4096) return fail(PBK_ERR_INVALID, "nslots must be in [0, 4096]");
+  std::lock_guard<std::mutex> lock(pl->mu);
+  CUDA_TRY(cudaSetDevice(pl->device));
+  prof_free(pl);
+  pl->prof.resize(nslots);
+  for (auto& set : pl->prof) {
+    set.resize(pl->launches + 1);
+    for (auto& ev : set) CUDA_TRY(cudaEventCreate(&ev));
+  }
+  return PBK_OK;
+}
+
+extern "C" int pbk_plan_profile_read(pbk_plan* pl, int32_t slot, float* ms, int32_t n) {
+  if (!pl || !ms) return fail(PBK_ERR_INVALID, "NULL argument");
+  if (slot < 0 || slot >= (int)pl->prof.size()) return fail(PBK_ERR_INVALID, "bad slot %d", slot);
+  if (n < pl->launches) return fail(PBK_ERR_INVALID, "need room for %d launches", pl->launches);
+  CUDA_TRY(cudaSetDevice(pl->device));
+  const auto& set = pl->prof[slot];
+  for (int i = 0; i < pl->launches; ++i) {
+    ms[i] = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms[i], set[i], set[i + 1]));
+  }
+  return PBK_OK;
+}
+
 extern "C" void pbk_plan_destroy(pbk_plan* pl) {
   if (!pl) return;
   cudaSetDevice(pl->device);
+  prof_free(pl);
   cudaFree(pl->scratch);
   cudaFree(pl->d_tw);
   cudaFree(pl->d_ftab);
