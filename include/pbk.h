@@ -158,14 +158,18 @@ void pbk_plan_destroy(pbk_plan* plan);
 int pbk_plan_info(const pbk_plan* plan, int32_t* launches, int64_t* workspace_bytes,
                   int32_t* levels, int32_t* level_log2 /* [3] */);
 
-/* human-readable list of the passes of a plan: "FWD:L=2^11:fast-r8:W=4:tiles=65536:threads=512;..." */
+/* human-readable list of the passes of a plan: "FWD:L=2^11:fast-r8:W=4:tiles=65536:threads=512;..."
+ * (passes joined by '+' run as one L2-blocked group, see pbk_plan_segments) */
 int pbk_plan_describe(const pbk_plan* plan, char* buf, size_t n);
 
 /* Per-launch device timing for benchmarks.  pbk_plan_profile(plan, nslots) makes every later
  * execution record a CUDA event before each kernel launch and after the last one, on the
  * execution stream, into slot (execution count mod nslots); nslots = 0 switches it off.
- * After synchronising, pbk_plan_profile_read returns the duration in ms of each of the plan's
- * `launches` kernels (pbk_plan_info) for one slot. */
+ * After synchronising, pbk_plan_profile_read returns the duration in ms of each timed segment of
+ * one slot.  A segment is one kernel launch, except that the L2-blocked middle passes of a
+ * 3-level plan (many small launches) form one segment; pbk_plan_segments gives their number and
+ * pbk_plan_describe lists them separated by ';' (a trailing time-sum kernel is not listed). */
+int pbk_plan_segments(const pbk_plan* plan, int32_t* segments);
 int pbk_plan_profile(pbk_plan* plan, int32_t nslots);
 int pbk_plan_profile_read(pbk_plan* plan, int32_t slot, float* ms, int32_t n);
 

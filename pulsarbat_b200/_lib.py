@@ -20,7 +20,7 @@ EXPORTS = [
     "pbk_fft_exec_host", "pbk_fft_exec_device", "pbk_detect", "pbk_downsample", "pbk_fold",
     "pbk_stokes", "pbk_pol_basis", "pbk_chirp",
     "pbk_plan_destroy", "pbk_plan_info", "pbk_plan_describe", "pbk_plan_profile",
-    "pbk_plan_profile_read", "pbk_malloc", "pbk_free", "pbk_memcpy_h2d",
+    "pbk_plan_profile_read", "pbk_plan_segments", "pbk_malloc", "pbk_free", "pbk_memcpy_h2d",
     "pbk_memcpy_d2h", "pbk_device_sync",
 ]
 
@@ -92,6 +92,7 @@ def lib():
         L.pbk_plan_info.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i64),
                                     ctypes.POINTER(i32), ctypes.POINTER(i32)]
         L.pbk_plan_describe.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t]
+        L.pbk_plan_segments.argtypes = [vp, ctypes.POINTER(i32)]
         L.pbk_plan_profile.argtypes = [vp, i32]
         L.pbk_plan_profile_read.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_float), i32]
         L.pbk_malloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t, i32]
@@ -154,13 +155,19 @@ class Plan:
         check(lib().pbk_plan_describe(self.handle, buf, 1024))
         return buf.value.decode()
 
+    def segments(self):
+        """Number of timed segments per execution (see pbk_plan_segments)."""
+        n = ctypes.c_int32(0)
+        check(lib().pbk_plan_segments(self.handle, ctypes.byref(n)))
+        return n.value
+
     def profile(self, nslots):
         """Record per-launch CUDA events for the next executions (0 switches it off)."""
         check(lib().pbk_plan_profile(self.handle, int(nslots)))
 
     def profile_read(self, slot):
         """Per-launch durations (ms) of one profiled execution; synchronise first."""
-        n = self.info()["launches"]
+        n = self.segments()
         ms = (ctypes.c_float * n)()
         check(lib().pbk_plan_profile_read(self.handle, int(slot), ms, n))
         return [float(v) for v in ms]

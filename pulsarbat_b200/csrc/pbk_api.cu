@@ -113,6 +113,10 @@ struct pbk_plan {
   pbk_dedisp_desc desc{};
   int64_t out_rows = 0, row_elems = 0, elem_bytes = 0, full_rows = 0;
   int launches = 0;
+  // L2-blocked schedule of the three middle passes of a 3-level plan (see run_passes)
+  int l2_chunks = 0;            // 0 = plain pass-after-pass schedule
+  long long l2_tiles[3] = {0, 0, 0};   // tiles per chunk of passes 1, 2, 3
+  int segments = 0;             // timed segments per execution (pbk_plan_profile_read)
   // optional per-launch device timing (pbk_plan_profile): ring of event sets, one per execution
   std::vector<std::vector<cudaEvent_t>> prof;
   long long prof_next = 0;
@@ -394,6 +398,8 @@ static int upload_tables(pbk_plan* pl, TableSet& ts) {
   return PBK_OK;
 }
 
+static void setup_l2_blocking(pbk_plan* pl, long long block_bytes, int nblocks);
+
 // ------------------------------------------------------------------------------------------
 // dedispersion plan
 // ------------------------------------------------------------------------------------------
@@ -571,7 +577,15 @@ extern "C" int pbk_dedisp_plan_create(const pbk_dedisp_desc* d, pbk_plan** out) 
                           cudaGetErrorString(e)));
   }
   for (auto& ps : pl->passes) ps.a.chan_freq = pl->d_chanfreq;
-  pl->launches = (int)pl->passes.size() + (d->downsample > 1 ? 1 : 0);
+  if (m == 3) setup_l2_blocking(pl, (N >> l[0]) * I * 8, 1 << l[0]);
+  const int ds = d->downsample > 1 ? 1 : 0;
+  if (pl->l2_chunks > 0) {
+    pl->launches = 2 + 3 * pl->l2_chunks + ds;
+    pl->segments = 3 + ds;
+  } else {
+    pl->launches = (int)pl->passes.size() + ds;
+    pl->segments = pl->launches;
+  }
   *out = pl;
   return PBK_OK;
 }
@@ -594,27 +608,81 @@ static void* role_ptr(const pbk_plan* pl, int role, const void* uin, void* uout)
   }
 }
 
+static int launch_one(pbk_plan* pl, const Pass& ps, const void* d_in, void* d_out,
+                      const void* d_chirp, long long tile0, long long tile_end, cudaStream_t st) {
+  Pass p = ps;
+  p.a.in = role_ptr(pl, ps.in_role, d_in, d_out);
+  p.a.out = role_ptr(pl, ps.out_role, d_in, d_out);
+  p.a.chirp_arr = reinterpret_cast<const float2*>(d_chirp);
+  p.a.tile0 = tile0;
+  const bool aligned = (((uintptr_t)p.a.in | (uintptr_t)p.a.out) & 15) == 0;
+  cudaError_t e;
+  if (ps.family >= 0 && aligned)
+    e = fast_launch(ps.family, ps.a.log2L, ps.mode, p.a, pl->d_ftab + ps.ftab_off,
+                    tile_end < 0 ? ps.ntiles : tile_end, pl->num_sms, st);
+  else
+    e = launch_pass(p, ps.fast && aligned, st);
+  if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
+  return PBK_OK;
+}
+
+// Pass schedule.  Plain: one launch per pass over the whole array.  L2-blocked (3-level plans on
+// the fast kernels): after the first forward level the array is 2^l1 independent contiguous
+// blocks (one per k1); the three middle passes (FWD level 2, MID level 3, INV level 2) work in
+// place inside a block, so they are launched block-chunk by block-chunk with chunks sized to stay
+// resident in the 126 MB L2: HBM sees one read and one write for the three passes instead of
+// three of each.
 static int run_passes(pbk_plan* pl, const void* d_in, void* d_out, const void* d_chirp,
                       cudaStream_t st) {
   prof_begin(pl);
-  int pidx = 0;
-  for (auto& ps : pl->passes) {
-    prof_mark(pl, pidx++, st);
-    Pass p = ps;
-    p.a.in = role_ptr(pl, ps.in_role, d_in, d_out);
-    p.a.out = role_ptr(pl, ps.out_role, d_in, d_out);
-    p.a.chirp_arr = reinterpret_cast<const float2*>(d_chirp);
-    const bool aligned = (((uintptr_t)p.a.in | (uintptr_t)p.a.out) & 15) == 0;
-    cudaError_t e;
-    if (ps.family >= 0 && aligned)
-      e = fast_launch(ps.family, ps.a.log2L, ps.mode, p.a, pl->d_ftab + ps.ftab_off, ps.ntiles,
-                      pl->num_sms, st);
-    else
-      e = launch_pass(p, ps.fast && aligned, st);
-    if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
+  int seg = 0, rc;
+  const size_t np = pl->passes.size();
+  const bool aligned = ((((uintptr_t)d_in | (uintptr_t)d_out | (uintptr_t)pl->scratch) & 15) == 0);
+  if (pl->l2_chunks > 0 && aligned) {
+    prof_mark(pl, seg++, st);
+    if ((rc = launch_one(pl, pl->passes[0], d_in, d_out, d_chirp, 0, -1, st)) != PBK_OK) return rc;
+    prof_mark(pl, seg++, st);
+    for (int c = 0; c < pl->l2_chunks; ++c)
+      for (int j = 0; j < 3; ++j) {
+        const long long t0 = (long long)c * pl->l2_tiles[j];
+        if ((rc = launch_one(pl, pl->passes[1 + j], d_in, d_out, d_chirp, t0,
+                             t0 + pl->l2_tiles[j], st)) != PBK_OK)
+          return rc;
+      }
+    prof_mark(pl, seg++, st);
+    if ((rc = launch_one(pl, pl->passes[4], d_in, d_out, d_chirp, 0, -1, st)) != PBK_OK) return rc;
+    prof_mark(pl, seg, st);
+    return PBK_OK;
   }
-  prof_mark(pl, pidx, st);
+  for (size_t i = 0; i < np; ++i) {
+    prof_mark(pl, seg++, st);
+    if ((rc = launch_one(pl, pl->passes[i], d_in, d_out, d_chirp, 0, -1, st)) != PBK_OK) return rc;
+  }
+  prof_mark(pl, seg, st);
   return PBK_OK;
+}
+
+// decide whether the L2-blocked schedule applies (called once the fast kernels are chosen)
+static void setup_l2_blocking(pbk_plan* pl, long long block_bytes, int nblocks) {
+  pl->l2_chunks = 0;
+  if (pl->passes.size() != 5) return;
+  for (int j = 1; j <= 3; ++j) {
+    const Pass& ps = pl->passes[j];
+    if (ps.family < 0 || ps.in_role != ROLE_SCRATCH || ps.out_role != ROLE_SCRATCH) return;
+  }
+  long long target = 0;   // off by default: on B200 the small launches cost more than the saved HBM traffic
+  if (const char* e = getenv("PBK_L2_CHUNK_MB")) target = atoll(e) << 20;
+  if (target <= 0) return;
+  long long per = std::max<long long>(1, target / block_bytes);   // blocks per chunk
+  while (nblocks % per) --per;
+  const int chunks = (int)(nblocks / per);
+  if (chunks < 2) return;
+  for (int j = 0; j < 3; ++j) {
+    const Pass& ps = pl->passes[1 + j];
+    if (ps.ntiles % chunks) return;
+    pl->l2_tiles[j] = ps.ntiles / chunks;
+  }
+  pl->l2_chunks = chunks;
 }
 
 extern "C" int pbk_dedisp_exec_device(pbk_plan* pl, const void* d_in, void* d_out,
@@ -633,7 +701,7 @@ extern "C" int pbk_dedisp_exec_device(pbk_plan* pl, const void* d_in, void* d_ou
                                       reinterpret_cast<float*>(d_out), pl->out_rows,
                                       pl->row_elems, pl->desc.downsample, st);
     if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "downsample launch: %s", cudaGetErrorString(e));
-    prof_mark(pl, (int)pl->passes.size() + 1, st);
+    prof_mark(pl, pl->segments, st);
   }
   return PBK_OK;
 }
@@ -756,6 +824,7 @@ static int build_fft_plan(long long O, long long n, long long C, long long P, bo
     }
   }
   pl->launches = (int)pl->passes.size();
+  pl->segments = pl->launches;
   *out = pl;
   return PBK_OK;
 }
@@ -832,7 +901,7 @@ extern "C" int pbk_plan_profile(pbk_plan* pl, int32_t nslots) {
   prof_free(pl);
   pl->prof.resize(nslots);
   for (auto& set : pl->prof) {
-    set.resize(pl->launches + 1);
+    set.resize(pl->segments + 1);
     for (auto& ev : set) CUDA_TRY(cudaEventCreate(&ev));
   }
   return PBK_OK;
@@ -841,10 +910,10 @@ extern "C" int pbk_plan_profile(pbk_plan* pl, int32_t nslots) {
 extern "C" int pbk_plan_profile_read(pbk_plan* pl, int32_t slot, float* ms, int32_t n) {
   if (!pl || !ms) return fail(PBK_ERR_INVALID, "NULL argument");
   if (slot < 0 || slot >= (int)pl->prof.size()) return fail(PBK_ERR_INVALID, "bad slot %d", slot);
-  if (n < pl->launches) return fail(PBK_ERR_INVALID, "need room for %d launches", pl->launches);
+  if (n < pl->segments) return fail(PBK_ERR_INVALID, "need room for %d segments", pl->segments);
   CUDA_TRY(cudaSetDevice(pl->device));
   const auto& set = pl->prof[slot];
-  for (int i = 0; i < pl->launches; ++i) {
+  for (int i = 0; i < pl->segments; ++i) {
     ms[i] = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms[i], set[i], set[i + 1]));
   }
@@ -885,17 +954,30 @@ extern "C" int pbk_plan_describe(const pbk_plan* pl, char* buf, size_t n) {
     const Pass& ps = pl->passes[i];
     const char* mode = ps.mode == MODE_FWD ? "FWD" : ps.mode == MODE_MID ? "MID" : "INV";
     int w;
+    // segments are separated by ';'; the passes of an L2-blocked group are joined by '+'
+    const bool blocked = pl->l2_chunks > 0;
+    const char* sep = i == 0 ? "" : (blocked && (i == 2 || i == 3)) ? "+" : ";";
     if (ps.family >= 0)
-      w = snprintf(buf + off, n - off, "%s%s:L=2^%d:%s:W=%d:tiles=%lld:threads=%d", i ? ";" : "",
+      w = snprintf(buf + off, n - off, "%s%s:L=2^%d:%s:W=%d:tiles=%lld:threads=%d", sep,
                    mode, ps.a.log2L, ps.family == FAMILY_R8 ? "fast-r8" : "fast-r16",
                    2 << ps.finfo.log2pw, ps.ntiles, ps.finfo.threads);
     else
-      w = snprintf(buf + off, n - off, "%s%s:L=2^%d:%s:W=%d:tiles=%u:threads=%d", i ? ";" : "",
+      w = snprintf(buf + off, n - off, "%s%s:L=2^%d:%s:W=%d:tiles=%u:threads=%d", sep,
                    mode, ps.a.log2L, ps.fast ? "generic-vec" : "generic", 2 << ps.a.log2pw,
                    ps.grid, kThreads);
     if (w < 0) break;
     off += (size_t)w;
+    if (blocked && i == 3 && off + 1 < n) {
+      w = snprintf(buf + off, n - off, ":l2chunks=%d", pl->l2_chunks);
+      if (w > 0) off += (size_t)w;
+    }
   }
+  return PBK_OK;
+}
+
+extern "C" int pbk_plan_segments(const pbk_plan* pl, int32_t* segments) {
+  if (!pl || !segments) return fail(PBK_ERR_INVALID, "NULL argument");
+  *segments = pl->segments;
   return PBK_OK;
 }
 

@@ -351,7 +351,7 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
   constexpr int LTASKS = (C::L / RL) * C::PW;
   constexpr int LITERS = (LTASKS + C::NT - 1) / C::NT;
 
-  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+  for (long long t = p.tile0 + blockIdx.x; t < ntiles; t += gridDim.x) {
     FastTile T;
     fast_tile_setup<C>(p, t, pr, T, in_eb, out_eb);
     if (MODE != MODE_MID && tid < RL)

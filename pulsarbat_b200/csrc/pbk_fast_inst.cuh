@@ -30,7 +30,7 @@ static cudaError_t cfg_launch_mode(const PassArgs& a, const float2* d_tables, lo
     attr_done[dev] = true;
   }
   const long long resident = (long long)num_sms * C::MINB;
-  const unsigned grid = (unsigned)std::min<long long>(ntiles, resident);
+  const unsigned grid = (unsigned)std::min<long long>(ntiles - a.tile0, resident);
   kern<<<grid, C::NT, C::SMEM_BYTES, st>>>(a, d_tables, ntiles);
   return cudaGetLastError();
 }

@@ -76,6 +76,7 @@ struct PassArgs {
   double df, fr_sub, inv_fr, a0, D;
   const float2* chirp_arr;
   long long chirp_sk, chirp_sc;
+  long long tile0;    // fast kernels: first tile of this launch (tiles [tile0, ntiles) are processed)
 };
 
 // ------------------------------------------------------------------------------------------

@@ -36,6 +36,7 @@ def time_plan(name, N, C, P, dm, sr, fcen, out_kind=0, downsample=1, in_dtype=0,
     for _ in range(2):
         plan.exec_device(x.data_ptr(), out.data_ptr(), None, st)
     torch.cuda.synchronize()
+    plan.profile(iters)
     ts = []
     for _ in range(iters):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -50,6 +51,10 @@ def time_plan(name, N, C, P, dm, sr, fcen, out_kind=0, downsample=1, in_dtype=0,
     print(f"{name}: N=2^{int(np.log2(N))} C={C} P={P} levels={plan.info()['levels']} "
           f"median {ms:.3f} ms best {min(ts):.3f} ms -> {nsmp / ms / 1e6:.1f} Gsamples/s, "
           f"alg {(in_b + nout) / ms / 1e6:.0f} GB/s", flush=True)
+    seg = np.array([plan.profile_read(i) for i in range(iters)]).mean(axis=0)
+    names = plan.describe().split(";") + (["downsample"] if downsample > 1 else [])
+    for nm, t in zip(names, seg):
+        print(f"      {t:7.3f} ms  {nm}", flush=True)
     plan.destroy()
     del x, out
     torch.cuda.empty_cache()
