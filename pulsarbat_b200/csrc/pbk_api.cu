@@ -363,12 +363,14 @@ static int setup_fast(pbk_plan* pl) {
     // the fast kernels are specialised to the dedispersion passes (see pbk_fast.cuh)
     if (ps.a.scale != 1.0f && ps.mode != MODE_MID) continue;
     if (ps.mode != MODE_MID && ps.a.log2M == 0) continue;
-    if (ps.mode == MODE_MID && (ps.a.chirp_kind != CHIRP_COMPUTED || ps.a.load_kind != LOAD_C64))
+    if (ps.mode == MODE_MID && (ps.a.chirp_kind != CHIRP_COMPUTED || ps.a.load_kind == LOAD_I8X2))
       continue;
+    if (ps.mode != MODE_FWD && ps.in_role == ROLE_SCRATCH && ps.a.load_kind != LOAD_PLANAR) continue;
+    if (ps.out_role == ROLE_SCRATCH && !ps.a.store_planar) continue;
     FastInfo fi;
     if (!fast_info(fam, ps.a.log2L, &fi)) continue;
     const long long W = 2ll << fi.log2pw;
-    if (ps.a.I % W || ps.a.Q % W) continue;
+    if (ps.a.I % W || ps.a.Q % W || W % ps.a.P) continue;
     if (ps.a.min.a_row * 8 >= (1ll << 32) || ps.a.mout.a_row * 8 >= (1ll << 32)) continue;
     ps.family = fam;
     ps.finfo = fi;
@@ -399,6 +401,16 @@ static int upload_tables(pbk_plan* pl, TableSet& ts) {
 }
 
 static void setup_l2_blocking(pbk_plan* pl, long long block_bytes, int nblocks);
+
+// scratch arrays are pair-planar ({re0,re1,im0,im1} per 16-byte lane pair) when the innermost
+// extent is even; every pass, generic or fast, reads and writes them through that layout
+static void mark_scratch_layout(pbk_plan* pl, long long I) {
+  const bool planar = (I % 2 == 0);
+  for (auto& ps : pl->passes) {
+    if (planar && ps.in_role == ROLE_SCRATCH) ps.a.load_kind = LOAD_PLANAR;
+    ps.a.store_planar = (planar && ps.out_role == ROLE_SCRATCH) ? 1 : 0;
+  }
+}
 
 // ------------------------------------------------------------------------------------------
 // dedispersion plan
@@ -476,6 +488,8 @@ extern "C" int pbk_dedisp_plan_create(const pbk_dedisp_desc* d, pbk_plan** out) 
     a.crop_start = d->crop_start;
     a.crop_stop = d->crop_stop;
     a.n_mul = R[level0];
+    a.log2nmul = log2ll(R[level0]);
+    a.final_epi = 1;
     if (d->out_kind == PBK_OUT_STOKES_I) {
       a.mout.a_o = 0; a.mout.a_kp = 0; a.mout.a_kl = 0;
       a.mout.a_n = C; a.mout.a_c = 1; a.mout.a_p = 0; a.mout.a_row = R[level0] * C;
@@ -552,6 +566,7 @@ extern "C" int pbk_dedisp_plan_create(const pbk_dedisp_desc* d, pbk_plan** out) 
 
   int rc = PBK_OK;
   auto cleanup = [&](int code) { pbk_plan_destroy(pl); return code; };
+  mark_scratch_layout(pl, I);
   if ((rc = upload_tables(pl, ts)) != PBK_OK) return cleanup(rc);
   if ((rc = setup_fast(pl)) != PBK_OK) return cleanup(rc);
   {
@@ -811,6 +826,7 @@ static int build_fft_plan(long long O, long long n, long long C, long long P, bo
     ts.ensure(l[i]);
     pl->passes.push_back(ps);
   }
+  mark_scratch_layout(pl, I);
   int rc = upload_tables(pl, ts);
   if (rc == PBK_OK) rc = setup_fast(pl);
   if (rc != PBK_OK) { pbk_plan_destroy(pl); return rc; }

@@ -48,8 +48,10 @@ struct FastCfg {
   }
   static constexpr int TW_TOTAL = tw_off(NS - 1) > 0 ? tw_off(NS - 1) : 1;
   static constexpr size_t TILE_BYTES = (size_t)L * PW * sizeof(float4);
-  static constexpr size_t SMEM_BYTES = TILE_BYTES + (size_t)TW_TOTAL * sizeof(float2) +
-                                       (size_t)RL * sizeof(float2) + 16;
+  // tile | stage tables (padded to 16 B) | level-twiddle table G (RL float4) | TileInfo
+  static constexpr int TW_PAD = (TW_TOTAL + 1) & ~1;
+  static constexpr size_t SMEM_BYTES = TILE_BYTES + (size_t)TW_PAD * sizeof(float2) +
+                                       (size_t)RL * sizeof(float4) + 64;
 };
 
 // host-side builder of the stage tables in the layout the kernel expects:
@@ -127,31 +129,60 @@ __device__ __forceinline__ int klo_of(int b) {
 // per-tile context (uniform across the CTA) and per-thread lane-pair pointers
 struct FastTile {
   const char* gin;    // byte pointer to this thread's lane pair at row 0 of the tile (input)
-  char* gout;         // same for the output map
+  char* gout;         // same for the output map (already shifted by the crop for final passes)
   unsigned nrest;     // inner time offset shared by the whole tile
   unsigned klow;      // low part of the full frequency index (MID chirp)
   int chan;           // channel of this thread's pair
+  unsigned row_lo, row_cnt;   // final passes: rows [row_lo, row_lo+row_cnt) survive the crop
 };
 
-template <class C>
-__device__ __forceinline__ void fast_tile_setup(const PassArgs& p, long long tile, int pr,
-                                                FastTile& T, int in_elem_bytes,
-                                                int out_elem_bytes) {
+constexpr int EPI_SCRATCH = 3;   // not a final pass: pair-planar complex64 to the scratch array
+// how a pass reads its input: user complex64 (re,im interleaved), user int8 pairs, or the scratch
+// array, where each 16-byte lane pair is stored as {re0, re1, im0, im1} ("pair-planar") so that a
+// 128-bit access is exactly the packed register layout of c2 and needs no shuffling
+enum { LK_C64 = 0, LK_I8 = 1, LK_PLANAR = 2 };
+
+// everything about a tile that is uniform across the CTA; computed by one thread (the address
+// arithmetic has 64-bit divisions) and broadcast through shared memory
+struct TileInfo {
+  long long bi, bo;     // byte offsets of lane pair 0, row 0 in the input / output array
+  unsigned nrest, klow;
+  int chan0;
+  unsigned row_lo, row_cnt;
+  int pad;
+};
+
+template <class C, int EPI>
+__device__ __forceinline__ void fast_tile_info(const PassArgs& p, long long tile, TileInfo& ti,
+                                               int in_elem_bytes, int out_elem_bytes) {
   const long long q0 = tile * C::W;              // first lane of the tile
   const long long o = q0 / p.RI;
   const long long r0 = q0 - o * p.RI;
   const long long nrest = r0 / p.I;
-  const int col = (int)(r0 - nrest * p.I) + 2 * pr;
+  const int col0 = (int)(r0 - nrest * p.I);      // multiple of W, hence of P (host checks W % P)
   const long long o_orig = o >> p.log2Kprev;
   const long long kprev = o & ((1ll << p.log2Kprev) - 1);
   const long long klow = (kprev >> p.kl_sa) + ((kprev & p.kl_mb) << p.kl_sb);
-  const long long bi = map_base(p.min, o_orig, kprev, klow, nrest, col, p.P);
-  const long long bo = map_base(p.mout, o_orig, kprev, klow, nrest, col, p.P);
-  T.gin = reinterpret_cast<const char*>(p.in) + bi * in_elem_bytes;
-  T.gout = reinterpret_cast<char*>(p.out) + bo * out_elem_bytes;
-  T.nrest = (unsigned)nrest;
-  T.klow = (unsigned)klow;
-  T.chan = col / p.P;
+  ti.bi = map_base(p.min, o_orig, kprev, klow, nrest, col0, p.P) * in_elem_bytes;
+  long long bo = map_base(p.mout, o_orig, kprev, klow, nrest, col0, p.P) * out_elem_bytes;
+  ti.nrest = (unsigned)nrest;
+  ti.klow = (unsigned)klow;
+  ti.chan0 = col0 / p.P;
+  ti.row_lo = 0;
+  ti.row_cnt = C::L;
+  if (EPI != EPI_SCRATCH) {
+    // time index of tile row r is r*n_mul + nrest (n_mul = 2^log2nmul); keep crop_start <= n <
+    // crop_stop  <=>  r in [ceil((start-nrest)/n_mul), ceil((stop-nrest)/n_mul))
+    const long long add = (1ll << p.log2nmul) - 1;
+    long long lo = (p.crop_start - nrest + add) >> p.log2nmul;
+    long long hi = (p.crop_stop - nrest + add) >> p.log2nmul;
+    lo = lo < 0 ? 0 : lo;
+    hi = hi > C::L ? C::L : hi;
+    ti.row_lo = (unsigned)lo;
+    ti.row_cnt = hi > lo ? (unsigned)(hi - lo) : 0u;
+    bo -= p.crop_start * p.mout.a_n * out_elem_bytes;
+  }
+  ti.bo = bo;
 }
 
 // streaming accesses: every element is touched once per pass, so mark it evict-first
@@ -159,11 +190,15 @@ __device__ __forceinline__ float4 ldg_stream_f4(const void* ptr) {
   return __ldcs(reinterpret_cast<const float4*>(ptr));
 }
 
-template <bool I8>
+template <int LOADK>
 __device__ __forceinline__ c2 fast_load(const FastTile& T, unsigned row, unsigned rowbytes) {
   const char* a = T.gin + (unsigned long long)row * rowbytes;
   c2 v;
-  if (!I8) {
+  if (LOADK == LK_PLANAR) {
+    const float4 t = ldg_stream_f4(a);
+    v.re = make_float2(t.x, t.y);
+    v.im = make_float2(t.z, t.w);
+  } else if (LOADK == LK_C64) {
     const float4 t = ldg_stream_f4(a);
     v.re = make_float2(t.x, t.z);
     v.im = make_float2(t.y, t.w);
@@ -175,53 +210,73 @@ __device__ __forceinline__ c2 fast_load(const FastTile& T, unsigned row, unsigne
   return v;
 }
 
+// scratch store: pair-planar {re0, re1, im0, im1}
 __device__ __forceinline__ void fast_store_c64(const FastTile& T, unsigned row, unsigned rowbytes,
                                                c2 v) {
   __stcs(reinterpret_cast<float4*>(T.gout + (unsigned long long)row * rowbytes),
-         make_float4(v.re.x, v.im.x, v.re.y, v.im.y));
+         make_float4(v.re.x, v.re.y, v.im.x, v.im.y));
 }
 
-// final epilogue (same semantics as store_row_epi in pbk_fft.cuh)
-__device__ __forceinline__ void fast_store_epi(const PassArgs& p, const FastTile& T, unsigned row,
+// store of an inverse pass: scratch (streaming complex64) or the final epilogue -- crop on the
+// time index (hoisted to a row range per tile), then c64 / per-pol intensity / Stokes I
+template <int EPI>
+__device__ __forceinline__ void fast_store_out(const FastTile& T, unsigned row,
                                                unsigned rowbytes, c2 v) {
-  const long long n = (long long)row * p.n_mul + T.nrest;
-  if (n < p.crop_start || n >= p.crop_stop) return;
   char* a = T.gout + (unsigned long long)row * rowbytes;
-  if (p.epi_kind == EPI_C64) {
-    a -= p.crop_start * p.mout.a_n * 8;
+  if (EPI == EPI_SCRATCH) {
+    __stcs(reinterpret_cast<float4*>(a), make_float4(v.re.x, v.re.y, v.im.x, v.im.y));
+    return;
+  }
+  if (row - T.row_lo >= T.row_cnt) return;
+  if (EPI == EPI_C64) {
     *reinterpret_cast<float4*>(a) = make_float4(v.re.x, v.im.x, v.re.y, v.im.y);
   } else {
-    a -= p.crop_start * p.mout.a_n * 4;
     const float2 pw = p_fma(v.re, v.re, p_mul(v.im, v.im));
-    if (p.epi_kind == EPI_INTENSITY) *reinterpret_cast<float2*>(a) = pw;
+    if (EPI == EPI_INTENSITY) *reinterpret_cast<float2*>(a) = pw;
     else *reinterpret_cast<float*>(a) = pw.x + pw.y;
   }
 }
 
 // level twiddle for the R registers of a last-stage group: W_M^(nrest*(klo + KS*m))
-//   = E * G[m],  E = W_M^(nrest*klo) (one exact root per task), G[m] = W_M^(nrest*KS*m) (per tile)
+//   = E * G[m],  E = W_M^(nrest*klo) (one exact root per task), G[m] = W_M^(nrest*KS*m) (per tile,
+//   kept in shared memory as {G.x, G.y, G.y, G.x} so that E*G[m] is two packed instructions)
 template <int R, bool CONJ>
 __device__ __forceinline__ void level_twiddle(const PassArgs& p, c2* v, unsigned nrest,
-                                              unsigned klo, const float2* G) {
+                                              unsigned klo, const float4* G4) {
   const float2 E = unit_root((unsigned long long)nrest * klo, p.log2M);
+  const float2 ex = p_bc(E.x), ey = make_float2(-E.y, E.y);
 #pragma unroll
   for (int m = 0; m < R; ++m) {
     float2 w = E;
-    if (m > 0) w = cmul1(E, G[m]);
+    if (m > 0) {
+      const float4 g = G4[m];
+      w = p_fma(make_float2(g.x, g.y), ex, p_mul(make_float2(g.z, g.w), ey));
+    }
     v[m] = cmul(v[m], p_bc(w.x), p_bc(CONJ ? -w.y : w.y));
   }
 }
 
 // chirp for the R registers of a last-stage group (uniform pair: one value serves both lanes).
 // Only the generated chirp runs here; an explicit chirp array goes through the generic kernel.
+// Register m holds full frequency index k_m = k_0 + m*N/R with k_0 < N/R, so the fftfreq wrap
+// (k >= N/2 -> k - N, dedispersion.py:20) is "m >= R/2" at compile time and the signed index is
+// k_0 + N*c_m with c_m = m/R - [m >= R/2]: one exact FP64 fma per element, no integer work.
 template <int R, class C>
 __device__ __forceinline__ void fast_chirp(const PassArgs& p, const FastTile& T, c2* v, int klo,
                                            double fchan) {
+  const double k0 = (double)((long long)T.klow + ((long long)klo << p.log2Kmul));
+  const double Nd = (double)p.N;
 #pragma unroll
   for (int m = 0; m < R; ++m) {
-    const long long kf = (long long)T.klow + ((long long)(klo + m * C::KS) << p.log2Kmul);
-    const float2 h = chirp_value(p, fchan, kf);
-    v[m] = cmul(v[m], p_bc(h.x), p_bc(h.y));
+    const double cm = (double)m / R - (m >= R / 2 ? 1.0 : 0.0);
+    const double ks = fma(cm, Nd, k0);
+    const double f = fma(ks, p.df, fchan);
+    const double a = fma(f - p.fr_sub, p.inv_fr, p.a0);   // (f - fr)/fr   (or -1 for fr = inf)
+    const double phi = (p.D * a) * a / f;                 // cycles
+    const double fr = phi - rint(phi);                    // exact reduction to [-0.5, 0.5]
+    float sn, cs;
+    sincospif(2.0f * (float)fr, &sn, &cs);
+    v[m] = cmul(v[m], p_bc(cs * p.scale), p_bc(-sn * p.scale));
   }
 }
 
@@ -229,7 +284,7 @@ __device__ __forceinline__ void fast_chirp(const PassArgs& p, const FastTile& T,
 // stages
 // ------------------------------------------------------------------------------------------
 // first forward stage: global -> registers -> smem (DIF, stage table 0)
-template <class C, bool I8>
+template <class C, int LOADK>
 __device__ __forceinline__ void fwd_first(const FastTile& T, float4* tile, const float2* tws,
                                           int tid, unsigned rowbytes_in) {
   constexpr bool SIGNINV = false;
@@ -244,7 +299,7 @@ __device__ __forceinline__ void fwd_first(const FastTile& T, float4* tile, const
     const int b = tau >> C::LOG2PW;
     c2 v[R];
 #pragma unroll
-    for (int i = 0; i < R; ++i) v[i] = fast_load<I8>(T, (unsigned)(b + i * S), rowbytes_in);
+    for (int i = 0; i < R; ++i) v[i] = fast_load<LOADK>(T, (unsigned)(b + i * S), rowbytes_in);
     Butterfly<R, SIGNINV>::run(v);
     stage_twiddle<R, S, SIGNINV>(v, tws + C::tw_off(0), b);
 #pragma unroll
@@ -301,9 +356,9 @@ __device__ __forceinline__ int last_idx(int b, int i, int pr) {
 }
 
 // last inverse stage: smem -> registers -> epilogue (mirror of fwd_first)
-template <class C>
-__device__ __forceinline__ void inv_last(const PassArgs& p, const FastTile& T, float4* tile,
-                                         const float2* tws, int tid, unsigned rowbytes_out) {
+template <class C, int EPI>
+__device__ __forceinline__ void inv_last(const FastTile& T, float4* tile, const float2* tws,
+                                         int tid, unsigned rowbytes_out) {
   constexpr int R = C::radix(0), S = C::stride(0);
   constexpr int TASKS = S * C::PW;
   constexpr int ITERS = (TASKS + C::NT - 1) / C::NT;
@@ -319,14 +374,14 @@ __device__ __forceinline__ void inv_last(const PassArgs& p, const FastTile& T, f
     stage_twiddle<R, S, true>(v, tws + C::tw_off(0), b);
     Butterfly<R, true>::run(v);
 #pragma unroll
-    for (int i = 0; i < R; ++i) fast_store_epi(p, T, (unsigned)(b + i * S), rowbytes_out, v[i]);
+    for (int i = 0; i < R; ++i) fast_store_out<EPI>(T, (unsigned)(b + i * S), rowbytes_out, v[i]);
   }
 }
 
 // ------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------
-template <int MODE, class C, bool I8>
+template <int MODE, class C, int LOADK, int EPI>
 __global__ void __launch_bounds__(C::NT, C::MINB)
 fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ tables,
                  long long ntiles) {
@@ -334,33 +389,61 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
   extern __shared__ float4 smem_dyn[];
   float4* tile = smem_dyn;
   float2* tws = reinterpret_cast<float2*>(tile + (size_t)C::L * C::PW);
-  float2* G = tws + C::TW_TOTAL;
+  float4* G4 = reinterpret_cast<float4*>(tws + C::TW_PAD);
+  TileInfo* sinfo = reinterpret_cast<TileInfo*>(G4 + C::RL);
   const int tid = threadIdx.x;
   const int pr = tid & (C::PW - 1);
 
-  for (int i = tid; i < C::TW_TOTAL; i += C::NT) tws[i] = tables[i];
-  __syncthreads();
-
   constexpr bool SIGNINV = false;
-  const int in_eb = I8 ? 2 : 8;
-  const int out_eb = (MODE != MODE_FWD && p.epi_kind != EPI_C64) ? 4 : 8;
+  constexpr int in_eb = LOADK == LK_I8 ? 2 : 8;
+  constexpr int out_eb = (EPI == EPI_INTENSITY || EPI == EPI_STOKES_I) ? 4 : 8;
   const unsigned rb_in = (unsigned)(p.min.a_row * in_eb);
   const unsigned rb_out = (unsigned)(p.mout.a_row * out_eb);
+
+  long long t = p.tile0 + blockIdx.x;
+  for (int i = tid; i < C::TW_TOTAL; i += C::NT) tws[i] = tables[i];
+  if (tid == 0 && t < ntiles) fast_tile_info<C, EPI>(p, t, *sinfo, in_eb, out_eb);
+  __syncthreads();
+
+  // per-thread part of the addresses: lane pair 2*pr inside the tile (col0 is a multiple of P)
+  const int colt = 2 * pr;
+  const long long off_in = ((long long)(colt / p.P) * p.min.a_c + (colt % p.P) * p.min.a_p) * in_eb;
+  const long long off_out =
+      ((long long)(colt / p.P) * p.mout.a_c + (colt % p.P) * p.mout.a_p) * out_eb;
+  const int chant = colt / p.P;
 
   constexpr int RL = C::RL;
   constexpr int LTASKS = (C::L / RL) * C::PW;
   constexpr int LITERS = (LTASKS + C::NT - 1) / C::NT;
 
-  for (long long t = p.tile0 + blockIdx.x; t < ntiles; t += gridDim.x) {
+  for (; t < ntiles; t += gridDim.x) {
     FastTile T;
-    fast_tile_setup<C>(p, t, pr, T, in_eb, out_eb);
-    if (MODE != MODE_MID && tid < RL)
-      G[tid] = unit_root((unsigned long long)T.nrest * (unsigned)(C::KS * tid), p.log2M);
+    {
+      const TileInfo ti = *sinfo;
+      T.gin = reinterpret_cast<const char*>(p.in) + ti.bi + off_in;
+      T.gout = reinterpret_cast<char*>(p.out) + ti.bo + off_out;
+      T.nrest = ti.nrest;
+      T.klow = ti.klow;
+      T.chan = ti.chan0 + chant;
+      T.row_lo = ti.row_lo;
+      T.row_cnt = ti.row_cnt;
+    }
+    if (MODE != MODE_MID && tid < RL) {
+      const float2 g = unit_root((unsigned long long)T.nrest * (unsigned)(C::KS * tid), p.log2M);
+      G4[tid] = make_float4(g.x, g.y, g.y, g.x);
+    }
     if (MODE == MODE_INV) __syncthreads();  // INV consumes G in its first phase
+    // every thread has copied *sinfo by the first barrier of this tile; thread 0 then prepares
+    // the next tile's record, which the end-of-tile barrier publishes
+#define PBK_NEXT_TILE_INFO()                                                        \
+  if (tid == 0 && t + gridDim.x < ntiles)                                           \
+    fast_tile_info<C, EPI>(p, t + gridDim.x, *sinfo, in_eb, out_eb)
+    if (MODE == MODE_INV) PBK_NEXT_TILE_INFO();
 
     if (MODE == MODE_FWD) {
-      fwd_first<C, I8>(T, tile, tws, tid, rb_in);
+      fwd_first<C, LOADK>(T, tile, tws, tid, rb_in);
       __syncthreads();
+      PBK_NEXT_TILE_INFO();
       mid_stages<C, false, SIGNINV>(tile, tws, tid);
 #pragma unroll
       for (int it = 0; it < LITERS; ++it) {
@@ -372,13 +455,14 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
         for (int i = 0; i < RL; ++i) v[i] = lds_c2(tile, last_idx<C>(b, i, pr));
         Butterfly<RL, SIGNINV>::run(v);
         const int klo = klo_of<C>(b);
-        level_twiddle<RL, SIGNINV>(p, v, T.nrest, (unsigned)klo, G);
+        level_twiddle<RL, SIGNINV>(p, v, T.nrest, (unsigned)klo, G4);
 #pragma unroll
         for (int i = 0; i < RL; ++i) fast_store_c64(T, (unsigned)(klo + i * C::KS), rb_out, v[i]);
       }
     } else if (MODE == MODE_MID) {
-      fwd_first<C, false>(T, tile, tws, tid, rb_in);
+      fwd_first<C, LOADK>(T, tile, tws, tid, rb_in);
       __syncthreads();
+      PBK_NEXT_TILE_INFO();
       mid_stages<C, false, false>(tile, tws, tid);
       const double fchan = p.chan_freq[T.chan];
 #pragma unroll
@@ -397,7 +481,7 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
       }
       __syncthreads();
       mid_stages<C, true, false>(tile, tws, tid);
-      inv_last<C>(p, T, tile, tws, tid, rb_out);
+      inv_last<C, EPI>(T, tile, tws, tid, rb_out);
     } else {  // MODE_INV
 #pragma unroll
       for (int it = 0; it < LITERS; ++it) {
@@ -407,18 +491,19 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
         const int klo = klo_of<C>(b);
         c2 v[RL];
 #pragma unroll
-        for (int i = 0; i < RL; ++i) v[i] = fast_load<false>(T, (unsigned)(klo + i * C::KS), rb_in);
-        level_twiddle<RL, true>(p, v, T.nrest, (unsigned)klo, G);
+        for (int i = 0; i < RL; ++i) v[i] = fast_load<LK_PLANAR>(T, (unsigned)(klo + i * C::KS), rb_in);
+        level_twiddle<RL, true>(p, v, T.nrest, (unsigned)klo, G4);
         Butterfly<RL, true>::run(v);
 #pragma unroll
         for (int i = 0; i < RL; ++i) sts_c2(tile, last_idx<C>(b, i, pr), v[i]);
       }
       __syncthreads();
       mid_stages<C, true, false>(tile, tws, tid);
-      inv_last<C>(p, T, tile, tws, tid, rb_out);
+      inv_last<C, EPI>(T, tile, tws, tid, rb_out);
     }
-    __syncthreads();  // tile buffer and G are reused by the next tile
+    __syncthreads();  // tile buffer, G and the tile record are reused by the next tile
   }
+#undef PBK_NEXT_TILE_INFO
 }
 
 }  // namespace pbk

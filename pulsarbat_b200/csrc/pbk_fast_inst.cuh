@@ -16,10 +16,10 @@ static void cfg_info(FastInfo* info) {
   info->smem = C::SMEM_BYTES;
 }
 
-template <int MODE, class C, bool I8>
+template <int MODE, class C, int LOADK, int EPI>
 static cudaError_t cfg_launch_mode(const PassArgs& a, const float2* d_tables, long long ntiles,
                                    int num_sms, cudaStream_t st) {
-  auto kern = fast_pass_kernel<MODE, C, I8>;
+  auto kern = fast_pass_kernel<MODE, C, LOADK, EPI>;
   static bool attr_done[16] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -35,16 +35,47 @@ static cudaError_t cfg_launch_mode(const PassArgs& a, const float2* d_tables, lo
   return cudaGetLastError();
 }
 
+// inverse passes always read the scratch array; a MID pass reads the user's complex64 input only
+// when it is the whole plan (then it is also final)
 template <class C>
 static cudaError_t cfg_launch(int mode, const PassArgs& a, const float2* d_tables,
                               long long ntiles, int num_sms, cudaStream_t st) {
   switch (mode) {
     case MODE_FWD:
       if (a.load_kind == LOAD_I8X2)
-        return cfg_launch_mode<MODE_FWD, C, true>(a, d_tables, ntiles, num_sms, st);
-      return cfg_launch_mode<MODE_FWD, C, false>(a, d_tables, ntiles, num_sms, st);
-    case MODE_MID: return cfg_launch_mode<MODE_MID, C, false>(a, d_tables, ntiles, num_sms, st);
-    default: return cfg_launch_mode<MODE_INV, C, false>(a, d_tables, ntiles, num_sms, st);
+        return cfg_launch_mode<MODE_FWD, C, LK_I8, EPI_SCRATCH>(a, d_tables, ntiles, num_sms, st);
+      if (a.load_kind == LOAD_PLANAR)
+        return cfg_launch_mode<MODE_FWD, C, LK_PLANAR, EPI_SCRATCH>(a, d_tables, ntiles, num_sms,
+                                                                    st);
+      return cfg_launch_mode<MODE_FWD, C, LK_C64, EPI_SCRATCH>(a, d_tables, ntiles, num_sms, st);
+    case MODE_MID:
+      if (!a.final_epi)
+        return cfg_launch_mode<MODE_MID, C, LK_PLANAR, EPI_SCRATCH>(a, d_tables, ntiles, num_sms,
+                                                                    st);
+      switch (a.epi_kind) {
+        case EPI_C64:
+          return cfg_launch_mode<MODE_MID, C, LK_C64, EPI_C64>(a, d_tables, ntiles, num_sms, st);
+        case EPI_INTENSITY:
+          return cfg_launch_mode<MODE_MID, C, LK_C64, EPI_INTENSITY>(a, d_tables, ntiles, num_sms,
+                                                                     st);
+        default:
+          return cfg_launch_mode<MODE_MID, C, LK_C64, EPI_STOKES_I>(a, d_tables, ntiles, num_sms,
+                                                                    st);
+      }
+    default:
+      if (!a.final_epi)
+        return cfg_launch_mode<MODE_INV, C, LK_PLANAR, EPI_SCRATCH>(a, d_tables, ntiles, num_sms,
+                                                                    st);
+      switch (a.epi_kind) {
+        case EPI_C64:
+          return cfg_launch_mode<MODE_INV, C, LK_PLANAR, EPI_C64>(a, d_tables, ntiles, num_sms, st);
+        case EPI_INTENSITY:
+          return cfg_launch_mode<MODE_INV, C, LK_PLANAR, EPI_INTENSITY>(a, d_tables, ntiles,
+                                                                        num_sms, st);
+        default:
+          return cfg_launch_mode<MODE_INV, C, LK_PLANAR, EPI_STOKES_I>(a, d_tables, ntiles,
+                                                                       num_sms, st);
+      }
   }
 }
 

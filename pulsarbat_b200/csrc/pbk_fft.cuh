@@ -33,7 +33,7 @@
 namespace pbk {
 
 enum { MODE_FWD = 0, MODE_MID = 1, MODE_INV = 2 };
-enum { LOAD_C64 = 0, LOAD_I8X2 = 1 };
+enum { LOAD_C64 = 0, LOAD_I8X2 = 1, LOAD_PLANAR = 2 };
 enum { EPI_C64 = 0, EPI_INTENSITY = 1, EPI_STOKES_I = 2 };
 enum { CHIRP_NONE = 0, CHIRP_COMPUTED = 1, CHIRP_ARRAY = 2 };
 
@@ -68,6 +68,9 @@ struct PassArgs {
   int load_kind, epi_kind;
   int fxor, kxor;     // ifftshift on load rows / fftshift on store rows (tile-level index xor)
   long long crop_start, crop_stop, n_mul;   // epilogue: n = row*n_mul + nrest, keep [start,stop)
+  int log2nmul;       // n_mul = 2^log2nmul (fast kernels)
+  int final_epi;      // this pass writes the user-visible output (crop + epilogue kind apply)
+  int store_planar;   // output is the scratch array in pair-planar form {re0,re1,im0,im1}
   // chirp
   int chirp_kind;
   int log2Kmul;       // kfull = klow + (k << log2Kmul)
@@ -263,10 +266,39 @@ __device__ __forceinline__ void lane_setup(const PassArgs& p, LaneCtx& L, int pr
 // ------------------------------------------------------------------------------------------
 // global load / store of one row for the thread's lane pair
 // ------------------------------------------------------------------------------------------
+// Scratch arrays between passes are "pair-planar" whenever the innermost extent is even: each
+// 16-byte pair of adjacent lanes holds {re0, re1, im0, im1}.  e is a complex-element offset.
+__device__ __forceinline__ float2 ld_lane_planar(const void* base, long long e) {
+  const float* f = reinterpret_cast<const float*>(base) + ((e & ~1ll) << 1) + (e & 1);
+  return make_float2(__ldg(f), __ldg(f + 2));
+}
+__device__ __forceinline__ void st_lane(const PassArgs& p, long long e, float re, float im) {
+  if (p.store_planar) {
+    float* f = reinterpret_cast<float*>(p.out) + ((e & ~1ll) << 1) + (e & 1);
+    f[0] = re;
+    f[2] = im;
+  } else {
+    reinterpret_cast<float2*>(p.out)[e] = make_float2(re, im);
+  }
+}
+
 template <bool FAST>
 __device__ __forceinline__ c2 load_row(const PassArgs& p, const LaneCtx& L, long long row) {
   c2 v;
-  if (p.load_kind == LOAD_C64) {
+  if (p.load_kind == LOAD_PLANAR) {
+    if (FAST) {
+      const float2* in = reinterpret_cast<const float2*>(p.in);
+      const float4 t = __ldg(reinterpret_cast<const float4*>(in + L.bin[0] + row * p.min.a_row));
+      v.re = make_float2(t.x, t.y);
+      v.im = make_float2(t.z, t.w);
+    } else {
+      float2 a = make_float2(0.f, 0.f), b = a;
+      if (L.valid[0]) a = ld_lane_planar(p.in, L.bin[0] + row * p.min.a_row);
+      if (L.valid[1]) b = ld_lane_planar(p.in, L.bin[1] + row * p.min.a_row);
+      v.re = make_float2(a.x, b.x);
+      v.im = make_float2(a.y, b.y);
+    }
+  } else if (p.load_kind == LOAD_C64) {
     const float2* in = reinterpret_cast<const float2*>(p.in);
     if (FAST) {
       const float4 t = __ldg(reinterpret_cast<const float4*>(in + L.bin[0] + row * p.min.a_row));
@@ -296,17 +328,18 @@ __device__ __forceinline__ c2 load_row(const PassArgs& p, const LaneCtx& L, long
   return v;
 }
 
-// plain complex64 store (intermediate data or c64 output)
+// complex64 store: scratch (pair-planar when store_planar) or a complex64 user array
 template <bool FAST>
 __device__ __forceinline__ void store_row_c64(const PassArgs& p, const LaneCtx& L, long long row,
                                               long long shift, c2 v) {
   float2* out = reinterpret_cast<float2*>(p.out);
   if (FAST) {
     *reinterpret_cast<float4*>(out + L.bout[0] + row * p.mout.a_row - shift) =
-        make_float4(v.re.x, v.im.x, v.re.y, v.im.y);
+        p.store_planar ? make_float4(v.re.x, v.re.y, v.im.x, v.im.y)
+                       : make_float4(v.re.x, v.im.x, v.re.y, v.im.y);
   } else {
-    if (L.valid[0]) out[L.bout[0] + row * p.mout.a_row - shift] = make_float2(v.re.x, v.im.x);
-    if (L.valid[1]) out[L.bout[1] + row * p.mout.a_row - shift] = make_float2(v.re.y, v.im.y);
+    if (L.valid[0]) st_lane(p, L.bout[0] + row * p.mout.a_row - shift, v.re.x, v.im.x);
+    if (L.valid[1]) st_lane(p, L.bout[1] + row * p.mout.a_row - shift, v.re.y, v.im.y);
   }
 }
 
@@ -324,9 +357,8 @@ __device__ __forceinline__ void store_row_epi(const PassArgs& p, const LaneCtx& 
     if (FAST) {
       if (k0) store_row_c64<true>(p, L, row, shift, v);
     } else {
-      float2* out = reinterpret_cast<float2*>(p.out);
-      if (L.valid[0] && k0) out[L.bout[0] + row * p.mout.a_row - shift] = make_float2(v.re.x, v.im.x);
-      if (L.valid[1] && k1) out[L.bout[1] + row * p.mout.a_row - shift] = make_float2(v.re.y, v.im.y);
+      if (L.valid[0] && k0) st_lane(p, L.bout[0] + row * p.mout.a_row - shift, v.re.x, v.im.x);
+      if (L.valid[1] && k1) st_lane(p, L.bout[1] + row * p.mout.a_row - shift, v.re.y, v.im.y);
     }
   } else {
     const float2 pw = p_fma(v.re, v.re, p_mul(v.im, v.im));

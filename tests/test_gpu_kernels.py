@@ -20,6 +20,8 @@ def _lib():
 def relerr(a, b):
     a = np.asarray(a).astype(np.complex128 if np.iscomplexobj(a) else np.float64)
     b = np.asarray(b).astype(a.dtype)
+    assert a.size == b.size, (a.shape, b.shape)   # never broadcast (N,1,1) against (N,1)
+    b = b.reshape(a.shape)
     nb = np.linalg.norm(b.ravel())
     return np.linalg.norm((a - b).ravel()) / (nb if nb > 0 else 1.0)
 
