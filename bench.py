@@ -248,6 +248,7 @@ def run_b200(args, w):
                         downsample=w["ds"], device=local)
     info = plan.info()
     desc = plan.describe().split(";") + (["downsample"] if w["ds"] > 1 else [])
+    desc = [f"{i}:{d}" for i, d in enumerate(desc)]      # unique names (two passes can look alike)
     K, W = args.steps, args.warmup
 
     # ---- device-resident run -----------------------------------------------------------
@@ -327,7 +328,7 @@ def run_b200(args, w):
     if os.path.exists(traffic_file):
         with open(traffic_file) as f:
             tr = json.load(f)
-        roofline["traffic"] = tr.get(args.workload, {}).get(desc[top].split(":")[0])
+        roofline["traffic"] = tr.get(args.workload, {}).get(":".join(desc[top].split(":")[:2]))
 
     # ---- end to end through the public API, host buffers ---------------------------------
     del x

@@ -100,6 +100,8 @@ struct pbk_plan {
   size_t scratch_bytes = 0;
   float2* d_tw = nullptr;
   double* d_chanfreq = nullptr;
+  double* d_chanconst = nullptr;   // per-channel constants of the fast MID chirp
+  bool chirp_series_ok = true;     // |delta/fc| small enough for the division-free chirp
   float2* d_ftab = nullptr;     // stage tables of the fast kernels
   int num_sms = 148;
   void* d_tmpf = nullptr;       // pre-downsample float buffer
@@ -257,6 +259,14 @@ static int choose_levels(int n, long long I, int* l, bool need_mid16) {
     }
   }
   const int lo = 4, hi = 12;
+  // estimated seconds per execution: every pass moves the whole array once each way at the
+  // bandwidth its chunk width allows, plus a fixed launch/ramp cost that decides small problems
+  const double pass_tb = (double)(1ll << n) * (double)I * 16.0 * 1e-12;
+  const double pass_fixed = 4e-6;
+  // an array that stays in the 126 MB L2 is not limited by the HBM chunk-width effects
+  const bool l2_resident = pass_tb * 1e12 <= 2.0 * (48ll << 20);
+  auto bw_s = [&](double chunk) { return l2_resident ? 6.0 : bw_strided(chunk); };
+  auto bw_r = [&](double chunk) { return l2_resident ? 6.0 : bw_rows(chunk); };
   double best = 1e30;
   int bm = 0, bl[3] = {0, 0, 0};
   auto consider = [&](int m, int a, int b, int c) {
@@ -268,13 +278,21 @@ static int choose_levels(int n, long long I, int* l, bool need_mid16) {
       R >>= ls[i];
       if (i + 1 < m) {
         if (need_mid16 && ls[i] < lo) return;   // inverse passes start with a radix-16 stage
-        cost += 2.0 / bw_strided(level_chunk_bytes(ls[i], R * I));
+        // tiles longer than 2^8 need a third butterfly stage per pass
+        const double stages = ls[i] <= 8 ? 1.0 : 1.0 + 0.15 * (ls[i] - 8);
+        cost += 2.0 * (stages * pass_tb / bw_s(level_chunk_bytes(ls[i], R * I)) + pass_fixed);
       } else {
-        cost += 1.0 / bw_rows(level_chunk_bytes(ls[i], I));
+        // the fused fft*chirp*ifft pass does two transforms of 2^l plus the chirp per tile and is
+        // issue-bound beyond l = 6 (measured on cfg2: 1.51 / 1.86 / 2.28 ms for l = 6 / 7 / 8
+        // against 1.45 ms for a plain pass); below 2^6 only the generic kernel exists
+        static const double mid_factor[13] = {3.0,  3.0, 3.0, 3.0, 3.0, 3.0, 1.05,
+                                              1.3,  1.6, 1.9, 2.2, 2.5, 2.8};
+        const double f = need_mid16 ? mid_factor[ls[i]]
+                                    : (ls[i] <= 8 ? 1.0 : 1.0 + 0.15 * (ls[i] - 8));
+        cost += f * pass_tb / bw_r(level_chunk_bytes(ls[i], I)) + pass_fixed;
       }
-      cost += 0.004 * ((ls[i] + 3) / 4);   // tie-break: fewer butterfly stages
     }
-    if (cost < best - 1e-12) { best = cost; bm = m; bl[0] = a; bl[1] = b; bl[2] = c; }
+    if (cost < best * (1.0 - 1e-9)) { best = cost; bm = m; bl[0] = a; bl[1] = b; bl[2] = c; }
   };
   if (n <= hi) consider(1, n, 0, 0);
   for (int a = 1; a <= hi && a < n; ++a) {
@@ -363,7 +381,8 @@ static int setup_fast(pbk_plan* pl) {
     // the fast kernels are specialised to the dedispersion passes (see pbk_fast.cuh)
     if (ps.a.scale != 1.0f && ps.mode != MODE_MID) continue;
     if (ps.mode != MODE_MID && ps.a.log2M == 0) continue;
-    if (ps.mode == MODE_MID && (ps.a.chirp_kind != CHIRP_COMPUTED || ps.a.load_kind == LOAD_I8X2))
+    if (ps.mode == MODE_MID && (ps.a.chirp_kind != CHIRP_COMPUTED || ps.a.load_kind == LOAD_I8X2 ||
+                                !pl->chirp_series_ok))
       continue;
     if (ps.mode != MODE_FWD && ps.in_role == ROLE_SCRATCH && ps.a.load_kind != LOAD_PLANAR) continue;
     if (ps.out_role == ROLE_SCRATCH && !ps.a.store_planar) continue;
@@ -567,6 +586,8 @@ extern "C" int pbk_dedisp_plan_create(const pbk_dedisp_desc* d, pbk_plan** out) 
   int rc = PBK_OK;
   auto cleanup = [&](int code) { pbk_plan_destroy(pl); return code; };
   mark_scratch_layout(pl, I);
+  for (long long c = 0; c < C; ++c)   // the fast MID chirp needs |f - fc| <= |fc| / 16
+    if (!(std::fabs(d->chan_freq_hz[c]) >= 8.0 * d->sample_rate_hz)) pl->chirp_series_ok = false;
   if ((rc = upload_tables(pl, ts)) != PBK_OK) return cleanup(rc);
   if ((rc = setup_fast(pl)) != PBK_OK) return cleanup(rc);
   {
@@ -591,7 +612,30 @@ extern "C" int pbk_dedisp_plan_create(const pbk_dedisp_desc* d, pbk_plan** out) 
       return cleanup(fail(PBK_ERR_NOMEM, "downsample buffer (%zu bytes): %s", pl->tmpf_bytes,
                           cudaGetErrorString(e)));
   }
-  for (auto& ps : pl->passes) ps.a.chan_freq = pl->d_chanfreq;
+  {
+    // constants of the division-free chirp (pbk_fast.cuh: fast_chirp), in long double on the host
+    std::vector<double> cc((size_t)C * 3);
+    const long double fr = d->ref_freq_hz, df = (long double)d->sample_rate_hz / (long double)N;
+    const long double Dl = (1.0L / 2.41e-4L) * (long double)d->dm * 1e12L;
+    for (long long c = 0; c < C; ++c) {
+      const long double fc = d->chan_freq_hz[c];
+      cc[3 * c + 0] = std::isinf(d->ref_freq_hz) ? -1.0 : (double)((fc - fr) / fr);
+      cc[3 * c + 1] = (double)(df / fc);
+      cc[3 * c + 2] = (double)(Dl / fc);
+    }
+    cudaError_t e = cudaMalloc(&pl->d_chanconst, cc.size() * sizeof(double));
+    if (e == cudaSuccess)
+      e = cudaMemcpy(pl->d_chanconst, cc.data(), cc.size() * sizeof(double),
+                     cudaMemcpyHostToDevice);
+    if (e != cudaSuccess)
+      return cleanup(fail(PBK_ERR_CUDA, "chan_const upload: %s", cudaGetErrorString(e)));
+  }
+  for (auto& ps : pl->passes) {
+    ps.a.chan_freq = pl->d_chanfreq;
+    ps.a.chan_const = pl->d_chanconst;
+    ps.a.bd = std::isinf(d->ref_freq_hz) ? 0.0
+                                         : (d->sample_rate_hz / (double)N) / d->ref_freq_hz;
+  }
   if (m == 3) setup_l2_blocking(pl, (N >> l[0]) * I * 8, 1 << l[0]);
   const int ds = d->downsample > 1 ? 1 : 0;
   if (pl->l2_chunks > 0) {
@@ -944,6 +988,7 @@ extern "C" void pbk_plan_destroy(pbk_plan* pl) {
   cudaFree(pl->d_tw);
   cudaFree(pl->d_ftab);
   cudaFree(pl->d_chanfreq);
+  cudaFree(pl->d_chanconst);
   cudaFree(pl->d_tmpf);
   cudaFree(pl->h_din);
   cudaFree(pl->h_dout);

@@ -185,10 +185,20 @@ __device__ __forceinline__ void fast_tile_info(const PassArgs& p, long long tile
   ti.bo = bo;
 }
 
-// streaming accesses: every element is touched once per pass, so mark it evict-first
+// Every element is touched once per pass.  Evict-first hints (ld.global.cs / st.global.cs) were
+// measured SLOWER than plain L2-cached accesses on B200 (cfg2: 7.58 vs 7.42 ms), so the default is
+// ld.global.cg + plain stores; PBK_STREAM_HINTS restores the hints for experiments.
+#ifdef PBK_STREAM_HINTS
+#define PBK_STCS(ptr, val) __stcs((ptr), (val))
 __device__ __forceinline__ float4 ldg_stream_f4(const void* ptr) {
   return __ldcs(reinterpret_cast<const float4*>(ptr));
 }
+#else
+#define PBK_STCS(ptr, val) (*(ptr) = (val))
+__device__ __forceinline__ float4 ldg_stream_f4(const void* ptr) {
+  return __ldcg(reinterpret_cast<const float4*>(ptr));
+}
+#endif
 
 template <int LOADK>
 __device__ __forceinline__ c2 fast_load(const FastTile& T, unsigned row, unsigned rowbytes) {
@@ -213,8 +223,8 @@ __device__ __forceinline__ c2 fast_load(const FastTile& T, unsigned row, unsigne
 // scratch store: pair-planar {re0, re1, im0, im1}
 __device__ __forceinline__ void fast_store_c64(const FastTile& T, unsigned row, unsigned rowbytes,
                                                c2 v) {
-  __stcs(reinterpret_cast<float4*>(T.gout + (unsigned long long)row * rowbytes),
-         make_float4(v.re.x, v.re.y, v.im.x, v.im.y));
+  PBK_STCS(reinterpret_cast<float4*>(T.gout + (unsigned long long)row * rowbytes),
+           make_float4(v.re.x, v.re.y, v.im.x, v.im.y));
 }
 
 // store of an inverse pass: scratch (streaming complex64) or the final epilogue -- crop on the
@@ -224,7 +234,7 @@ __device__ __forceinline__ void fast_store_out(const FastTile& T, unsigned row,
                                                unsigned rowbytes, c2 v) {
   char* a = T.gout + (unsigned long long)row * rowbytes;
   if (EPI == EPI_SCRATCH) {
-    __stcs(reinterpret_cast<float4*>(a), make_float4(v.re.x, v.re.y, v.im.x, v.im.y));
+    PBK_STCS(reinterpret_cast<float4*>(a), make_float4(v.re.x, v.re.y, v.im.x, v.im.y));
     return;
   }
   if (row - T.row_lo >= T.row_cnt) return;
@@ -258,24 +268,42 @@ __device__ __forceinline__ void level_twiddle(const PassArgs& p, c2* v, unsigned
 
 // chirp for the R registers of a last-stage group (uniform pair: one value serves both lanes).
 // Only the generated chirp runs here; an explicit chirp array goes through the generic kernel.
-// Register m holds full frequency index k_m = k_0 + m*N/R with k_0 < N/R, so the fftfreq wrap
-// (k >= N/2 -> k - N, dedispersion.py:20) is "m >= R/2" at compile time and the signed index is
-// k_0 + N*c_m with c_m = m/R - [m >= R/2]: one exact FP64 fma per element, no integer work.
+// Reference: dedispersion.py:19-23, H = exp(-2 pi i phi), phi = D f (1/fr - 1/f)^2 cycles with
+// f = f_chan + fftfreq[k].
+//  * Register m holds full frequency index k_m = k_0 + m*N/R with k_0 < N/R, so the fftfreq wrap
+//    (k >= N/2 -> k - N, dedispersion.py:20) is "m >= R/2" at compile time and the signed index
+//    is ks = k_0 + N*c_m, c_m = m/R - [m >= R/2]: one exact FP64 fma, no integer work.
+//  * With delta = ks*df (offset from the channel centre fc) the cancellation-free form is
+//        phi = (D/fc) * a^2 / (1 + x),   a = (fc - fr)/fr + delta/fr,   x = delta/fc,
+//    and 1/(1+x) comes from the cubic 1 - x + x^2 - x^3 refined by two Newton steps (error x^16;
+//    the host only selects this kernel when |x| <= 1/16), so there is no FP64 division.
+//    cc = {(fc-fr)/fr, df/fc, D/fc} per channel, p.bd = df/fr.
+//  * phi is reduced exactly (phi - rint(phi), |.| <= 1/2 cycle) before the FP32 sine/cosine.
 template <int R, class C>
-__device__ __forceinline__ void fast_chirp(const PassArgs& p, const FastTile& T, c2* v, int klo,
-                                           double fchan) {
+__device__ __forceinline__ void fast_chirp(const PassArgs& p, const FastTile& T, c2* v, int klo) {
   const double k0 = (double)((long long)T.klow + ((long long)klo << p.log2Kmul));
   const double Nd = (double)p.N;
+  const double cA = p.chan_const[3 * T.chan + 0];
+  const double cX = p.chan_const[3 * T.chan + 1];
+  const double cD = p.chan_const[3 * T.chan + 2];
 #pragma unroll
   for (int m = 0; m < R; ++m) {
     const double cm = (double)m / R - (m >= R / 2 ? 1.0 : 0.0);
     const double ks = fma(cm, Nd, k0);
-    const double f = fma(ks, p.df, fchan);
-    const double a = fma(f - p.fr_sub, p.inv_fr, p.a0);   // (f - fr)/fr   (or -1 for fr = inf)
-    const double phi = (p.D * a) * a / f;                 // cycles
-    const double fr = phi - rint(phi);                    // exact reduction to [-0.5, 0.5]
+    const double a = fma(ks, p.bd, cA);
+    const double x = ks * cX;
+    const double u = 1.0 + x;
+    double r = fma(x, fma(x, 1.0 - x, -1.0), 1.0);
+    r = fma(r, fma(-u, r, 1.0), r);
+    r = fma(r, fma(-u, r, 1.0), r);
+    const double phi = (a * a) * (r * cD);              // cycles
+    const double fr = phi - rint(phi);                  // exact reduction to [-0.5, 0.5]
     float sn, cs;
+#ifdef PBK_ACCURATE_SINCOS
     sincospif(2.0f * (float)fr, &sn, &cs);
+#else
+    __sincosf(6.283185307179586f * (float)fr, &sn, &cs);   // MUFU, |error| < 5e-7 on |x| <= pi
+#endif
     v[m] = cmul(v[m], p_bc(cs * p.scale), p_bc(-sn * p.scale));
   }
 }
@@ -464,7 +492,6 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
       __syncthreads();
       PBK_NEXT_TILE_INFO();
       mid_stages<C, false, false>(tile, tws, tid);
-      const double fchan = p.chan_freq[T.chan];
 #pragma unroll
       for (int it = 0; it < LITERS; ++it) {
         const int tau = tid + it * C::NT;
@@ -474,7 +501,7 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
 #pragma unroll
         for (int i = 0; i < RL; ++i) v[i] = lds_c2(tile, last_idx<C>(b, i, pr));
         Butterfly<RL, false>::run(v);
-        fast_chirp<RL, C>(p, T, v, klo_of<C>(b), fchan);
+        fast_chirp<RL, C>(p, T, v, klo_of<C>(b));
         Butterfly<RL, true>::run(v);
 #pragma unroll
         for (int i = 0; i < RL; ++i) sts_c2(tile, last_idx<C>(b, i, pr), v[i]);

@@ -76,6 +76,8 @@ struct PassArgs {
   int log2Kmul;       // kfull = klow + (k << log2Kmul)
   long long N;        // full transform length (for fftfreq sign wrap)
   const double* chan_freq;   // Hz, per channel
+  const double* chan_const;  // fast MID kernel: {(fc-fr)/fr, df/fc, D/fc} per channel
+  double bd;                 // df / fr (0 for fr = inf)
   double df, fr_sub, inv_fr, a0, D;
   const float2* chirp_arr;
   long long chirp_sk, chirp_sc;
