@@ -123,6 +123,12 @@ int pbk_fft_exec_device(pbk_plan* plan, const void* d_in, void* d_out, void* str
 int pbk_detect(const void* in, void* out, int64_t nsamp, int64_t nchan, int64_t npol,
                int32_t out_kind, int64_t downsample, int32_t on_device, int32_t device,
                void* stream);
+/* pbk_detect with an additional sum over `freq_sum` adjacent channels (frequency scrunching
+ * after channelize; builder-defined like row R):
+ *   out[j, c', (p)] = sum_{m<time_sum} sum_{f<freq_sum} |in[j*time_sum+m, c'*freq_sum+f, p]|^2 */
+int pbk_detect_scrunch(const void* in, void* out, int64_t nsamp, int64_t nchan, int64_t npol,
+                       int32_t out_kind, int64_t time_sum, int64_t freq_sum, int32_t on_device,
+                       int32_t device, void* stream);
 int pbk_downsample(const void* in, void* out, int64_t nsamp, int64_t row_elems,
                    int64_t factor, int32_t on_device, int32_t device, void* stream);
 

@@ -1084,6 +1084,46 @@ extern "C" int pbk_detect(const void* in, void* out, int64_t nsamp, int64_t ncha
   return PBK_OK;
 }
 
+extern "C" int pbk_detect_scrunch(const void* in, void* out, int64_t nsamp, int64_t nchan,
+                                  int64_t npol, int32_t out_kind, int64_t time_sum,
+                                  int64_t freq_sum, int32_t on_device, int32_t device,
+                                  void* stream) {
+  if (!in || !out) return fail(PBK_ERR_INVALID, "NULL data pointer");
+  if (nsamp <= 0 || nchan <= 0 || npol <= 0 || time_sum < 1 || freq_sum < 1)
+    return fail(PBK_ERR_INVALID, "bad shape");
+  if (nchan % freq_sum) return fail(PBK_ERR_INVALID, "freq_sum must divide nchan");
+  if (out_kind != PBK_OUT_INTENSITY && out_kind != PBK_OUT_STOKES_I)
+    return fail(PBK_ERR_INVALID, "out_kind must be INTENSITY or STOKES_I");
+  if (out_kind == PBK_OUT_STOKES_I && npol != 2) return fail(PBK_ERR_INVALID, "Stokes I needs npol == 2");
+  if (npol > INT_MAX) return fail(PBK_ERR_INVALID, "npol too large");
+  CUDA_TRY(cudaSetDevice(device));
+  const long long rows = nsamp / time_sum, cout = nchan / freq_sum;
+  const bool stokes = out_kind == PBK_OUT_STOKES_I;
+  if (rows == 0) return PBK_OK;
+  if (on_device) {
+    cudaError_t e = launch_detect_scrunch(reinterpret_cast<const float2*>(in),
+                                          reinterpret_cast<float*>(out), rows, cout, (int)npol,
+                                          stokes, time_sum, freq_sum,
+                                          reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "detect launch: %s", cudaGetErrorString(e));
+    return PBK_OK;
+  }
+  DevBuf di, dout;
+  const size_t ib = (size_t)rows * time_sum * nchan * npol * 8;
+  const size_t ob = (size_t)rows * cout * (stokes ? 1 : npol) * 4;
+  CUDA_TRY(cudaMalloc(&di.p, ib));
+  CUDA_TRY(cudaMalloc(&dout.p, ob));
+  cudaStream_t st = cudaStreamPerThread;
+  CUDA_TRY(cudaMemcpyAsync(di.p, in, ib, cudaMemcpyHostToDevice, st));
+  cudaError_t e = launch_detect_scrunch(reinterpret_cast<const float2*>(di.p),
+                                        reinterpret_cast<float*>(dout.p), rows, cout, (int)npol,
+                                        stokes, time_sum, freq_sum, st);
+  if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "detect launch: %s", cudaGetErrorString(e));
+  CUDA_TRY(cudaMemcpyAsync(out, dout.p, ob, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return PBK_OK;
+}
+
 extern "C" int pbk_downsample(const void* in, void* out, int64_t nsamp, int64_t row_elems,
                               int64_t factor, int32_t on_device, int32_t device, void* stream) {
   if (!in || !out) return fail(PBK_ERR_INVALID, "NULL data pointer");

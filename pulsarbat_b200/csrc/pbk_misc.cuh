@@ -103,6 +103,56 @@ static inline cudaError_t launch_detect(const float2* in, float* out, long long 
   return cudaGetLastError();
 }
 
+// detection with time AND frequency summing ("scrunching"): one warp per output element.
+//   out[j, c', (p)] = sum_{m<M} sum_{f<F} |in[j*M+m, c'*F+f, p]|^2   (Stokes: also summed over p)
+// Used after channelize, where 2^16 fine channels per coarse channel are binned down (cfg 4).
+__global__ void __launch_bounds__(256) detect_scrunch_kernel(const float2* __restrict__ in,
+                                                             float* __restrict__ out,
+                                                             long long rows, long long Cout,
+                                                             int P, int stokes, long long M,
+                                                             long long F) {
+  const int lane = threadIdx.x & 31;
+  const long long Pq = stokes ? 1 : P;
+  const long long total = rows * Cout * Pq;
+  const long long CP = Cout * F * P;   // complex elements per input row
+  const long long wstep = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long o = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); o < total;
+       o += wstep) {
+    const long long j = o / (Cout * Pq), r = o - j * Cout * Pq;
+    const long long c = r / Pq, pp = r - c * Pq;
+    float acc = 0.f;
+    for (long long m = 0; m < M; ++m) {
+      const float2* row = in + (j * M + m) * CP + c * F * P;
+      if (stokes) {
+        for (long long i = lane; i < F * P; i += 32) {
+          const float2 v = __ldg(row + i);
+          acc += v.x * v.x + v.y * v.y;
+        }
+      } else {
+        for (long long f = lane; f < F; f += 32) {
+          const float2 v = __ldg(row + f * P + pp);
+          acc += v.x * v.x + v.y * v.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) out[o] = acc;
+  }
+}
+
+static inline cudaError_t launch_detect_scrunch(const float2* in, float* out, long long rows,
+                                                long long Cout, int P, bool stokes, long long M,
+                                                long long F, cudaStream_t st) {
+  const long long total = rows * Cout * (stokes ? 1 : P);
+  if (total <= 0) return cudaSuccess;
+  long long blocks = (total + 7) / 8;
+  if (blocks > 148ll * 16) blocks = 148ll * 16;
+  detect_scrunch_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, out, rows, Cout, P, stokes ? 1 : 0,
+                                                         M, F);
+  return cudaGetLastError();
+}
+
 // full Stokes [I, Q, U, V] from (A, B) pol pairs (core.py:937-966, PSR/IEEE convention)
 //   linear:   I=AA+BB  Q=AA-BB  U=2Re(A*B)  V=2Im(A*B)
 //   circular: I=AA+BB  Q=2Re(A*B)  U=2Im(A*B)  V=AA-BB          (A*B = conj(A) B)

@@ -178,29 +178,41 @@ def chirp(nsamp, nchan, *, dm, sample_rate_hz, ref_freq_hz, chan_freq_hz, device
 # --------------------------------------------------------------------------------------------
 # detection / polarisation        reference: core.py:766-774, 882-966
 # --------------------------------------------------------------------------------------------
-def detect(data, stokes=False, downsample=1, device=None):
-    """re^2+im^2 per element, or |A|^2+|B|^2 over the pol axis (axis 2) when ``stokes``."""
+def detect(data, stokes=False, downsample=1, freq_sum=1, device=None):
+    """re^2+im^2 per element, or |A|^2+|B|^2 over the pol axis (axis 2) when ``stokes``; summed
+    over ``downsample`` consecutive samples and ``freq_sum`` adjacent channels."""
     shape = tuple(data.shape)
     nsamp, nchan = shape[0], shape[1]
     npol = int(np.prod(shape[2:])) if len(shape) > 2 else 1
     if stokes and (len(shape) < 3 or shape[2] != 2 or npol != 2):
         raise ValueError("Stokes I needs shape (nsamp, nchan, 2)")
+    freq_sum = int(freq_sum)
+    if freq_sum < 1 or nchan % freq_sum:
+        raise ValueError("freq_sum must divide the number of channels")
     rows = nsamp // int(downsample)
-    out_shape = (rows, nchan) if stokes else (rows,) + shape[1:]
+    cout = nchan // freq_sum
+    out_shape = (rows, cout) if stokes else (rows, cout) + shape[2:]
     kind = L.OUT_STOKES_I if stokes else L.OUT_INTENSITY
+
+    def call(pin, pout, on_dev, dev, stream):
+        if freq_sum > 1:
+            L.check(L.lib().pbk_detect_scrunch(pin, pout, nsamp, nchan, npol, kind,
+                                               int(downsample), freq_sum, on_dev, dev, stream))
+        else:
+            L.check(L.lib().pbk_detect(pin, pout, nsamp, nchan, npol, kind, int(downsample),
+                                       on_dev, dev, stream))
+
     if _is_dev(data):
         x = data.contiguous()
         if x.dtype != np.complex64:
             x = x.astype(np.complex64)
         out = DeviceArray.empty(out_shape, np.float32, x.device)
-        L.check(L.lib().pbk_detect(L.ptr(x.ptr), L.ptr(out.ptr), nsamp, nchan, npol, kind,
-                                   int(downsample), 1, x.device, ctypes.c_void_p(_stream())))
+        call(L.ptr(x.ptr), L.ptr(out.ptr), 1, x.device, ctypes.c_void_p(_stream()))
         return out
     x, odt = _host_c64(data)
     out = np.empty(out_shape, np.float32)
     dev = default_device() if device is None else device
-    L.check(L.lib().pbk_detect(L.ptr(x), L.ptr(out), nsamp, nchan, npol, kind, int(downsample),
-                               0, dev, None))
+    call(L.ptr(x), L.ptr(out), 0, dev, None)
     rdt = _real_of(odt)
     return out if rdt == np.float32 else out.astype(rdt)
 

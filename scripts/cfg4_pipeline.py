@@ -1,0 +1,69 @@
+"""BASELINE configs[3] on N GPUs: channelize (2^16-point STFT) -> detect -> bin 64 fine channels
+-> fold into 1024 phase bins x 1024 channels; time slices sharded over ranks, ONE all-reduce of
+the folded profile and counts over NCCL.  Run with torchrun; prints one line of timings (rank 0).
+
+    python -m torch.distributed.run --nproc-per-node N scripts/cfg4_pipeline.py [log2_samples_per_rank]
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import pulsarbat_b200 as pb  # noqa: E402
+from pulsarbat_b200 import sharding  # noqa: E402
+
+world = int(os.environ.get("WORLD_SIZE", "1"))
+rank = int(os.environ.get("RANK", "0"))
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+os.environ["PBK_DEVICE"] = str(local)
+dev = torch.device(f"cuda:{local}")
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+
+lg = int(sys.argv[1]) if len(sys.argv) > 1 else 26
+n_per_rank, nper, fsum, nbin = 2 ** lg, 2 ** 16, 64, 1024
+sr = 400e6
+g = torch.Generator(device=dev)
+g.manual_seed(16 + rank)
+x = torch.randn((n_per_rank, 1, 2), device=dev, dtype=torch.float32, generator=g)
+xd = pb.DeviceArray(torch.view_as_complex(x))
+coeffs = [0.123, 29.7, 1e-6]
+seg_per_rank = n_per_rank // nper
+
+
+def step():
+    zc = pb.kernels.stft(xd, nper)                                   # (segments, 65536)
+    inten = pb.kernels.detect(zc, freq_sum=fsum)                     # (segments, 1024)
+    prof, cnt = pb.kernels.fold(inten, coeffs, sr / nper, nbin, n0=rank * seg_per_rank)
+    return sharding.allreduce_profiles(prof, cnt)
+
+
+for _ in range(3):
+    prof, cnt = step()
+torch.cuda.synchronize()
+if world > 1:
+    dist.barrier()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+K = 10
+e0.record()
+for _ in range(K):
+    prof, cnt = step()
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / K
+t = torch.tensor([ms], device=dev, dtype=torch.float64)
+if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+total = int(np.asarray(cnt).sum())
+if rank == 0:
+    assert total == world * seg_per_rank, (total, world * seg_per_rank)
+    print(f"cfg4: {world} GPU(s) x 2^{lg} samples: {float(t.item()):.3f} ms per step -> "
+          f"{world * n_per_rank / float(t.item()) / 1e6:.1f} Gsamples/s; profile "
+          f"{tuple(np.asarray(prof).shape)}, counts sum {total} (exact)", flush=True)
+if world > 1:
+    dist.destroy_process_group()

@@ -375,3 +375,48 @@ def test_cfg2_full_size_device_resident():
     ref = (y.double() ** 2).sum(dim=(2, 3)).reshape(N // 64, 64, C).sum(dim=1)
     err = (out.double() - ref).norm() / ref.norm()
     assert float(err) < 1e-5
+
+
+# ------------------------------------------------------------------------------ cfg 4 pipeline
+@pytest.mark.parametrize("stokes", [False, True])
+def test_detect_scrunch(stokes):
+    L = _lib()
+    from pulsarbat_b200 import kernels
+    rng = np.random.default_rng(3)
+    x = crandn(rng, (96, 40, 2))
+    got = kernels.detect(x, stokes=stokes, downsample=8, freq_sum=5)
+    p = np.abs(x.astype(np.complex128)) ** 2
+    if stokes:
+        p = p.sum(axis=2)
+        want = p.reshape(12, 8, 8, 5).sum(axis=(1, 3))
+    else:
+        want = p.reshape(12, 8, 8, 5, 2).sum(axis=(1, 3))
+    assert got.shape == want.shape
+    assert relerr(got, want) < 1e-6
+
+
+def test_cfg4_channelize_detect_fold_pipeline():
+    """BASELINE configs[3] at reduced size through the public API: channelize a one-channel stream
+    (stft), detect, bin fine channels, fold with a polyco-style phase polynomial; bins and counts
+    bit-exact, profile within float32 summation tolerance."""
+    import pulsarbat_b200 as pb
+    rng = np.random.default_rng(16)
+    N, nper, fsum, nbin = 2 ** 20, 2 ** 10, 16, 64
+    sr = 400e6
+    x = crandn(rng, (N, 1))
+    z = pb.BasebandSignal(x, sample_rate=sr * pb.units.Hz, center_freq=600e6 * pb.units.Hz)
+    zc = pb.contrib.stft(z, nperseg=nper)
+    assert zc.shape == (N // nper, nper)
+    want_c = orc.stft(x.astype(np.complex128), nper)
+    assert relerr(np.asarray(zc.data), want_c) < 2e-6
+    inten = pb.kernels.detect(np.asarray(zc.data), freq_sum=fsum)
+    want_i = (np.abs(want_c) ** 2).reshape(N // nper, nper // fsum, fsum).sum(axis=2)
+    assert relerr(inten, want_i) < 1e-5
+    coeffs = [0.123, 29.7e3, 1e-3]                  # fast "pulsar" so that every bin is hit
+    sr_c = sr / nper
+    prof, counts, bins = pb.kernels.fold(inten, coeffs, sr_c, nbin, want_bins=True)
+    ref_bins = orc.fold_bins(N // nper, coeffs, sr_c, nbin)
+    assert np.array_equal(bins, ref_bins)
+    want_p, want_n = orc.fold(want_i, coeffs, sr_c, nbin)
+    assert np.array_equal(counts, want_n)
+    assert relerr(prof, want_p) < 1e-5
