@@ -129,6 +129,13 @@ int pbk_detect(const void* in, void* out, int64_t nsamp, int64_t nchan, int64_t 
 int pbk_detect_scrunch(const void* in, void* out, int64_t nsamp, int64_t nchan, int64_t npol,
                        int32_t out_kind, int64_t time_sum, int64_t freq_sum, int32_t on_device,
                        int32_t device, void* stream);
+/* Incoherent dedispersion (transforms/dedispersion.py:136-177): per-channel integer roll + crop,
+ *   out[n, c, :] = in[n + delays[c], c, :],  n < nsamp_out,  0 <= delays[c] <= nsamp_in - nsamp_out
+ * for any element type; cell_bytes = bytes per (sample, channel) cell (multiple of 4).  The delays
+ * (host array) are computed by the caller exactly as dedispersion.py:164-169. */
+int pbk_shift_channels(const void* in, void* out, int64_t nsamp_in, int64_t nsamp_out,
+                       int64_t nchan, int64_t cell_bytes, const int64_t* delays,
+                       int32_t on_device, int32_t device, void* stream);
 int pbk_downsample(const void* in, void* out, int64_t nsamp, int64_t row_elems,
                    int64_t factor, int32_t on_device, int32_t device, void* stream);
 

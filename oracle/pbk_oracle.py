@@ -145,6 +145,27 @@ def coherent_dedispersion(x, dm, *, sample_rate, center_freq, freq_align="center
     return y, start, stop
 
 
+def incoherent_dedispersion(x, dm, *, sample_rate, center_freq, chan_bw, freq_align="center",
+                            ref_freq=None):
+    """dedispersion.py:158-177: returns (y, crop_before, delays).
+
+    delays = round(sample_delay(channel_freqs, ref_freq, sample_rate)), shifted by
+    crop_before = -min(0, delays[0], delays[-1]); N = len - max(delays);
+    y[:, i] = x[delays[i] : delays[i] + N, i].
+    """
+    x = np.asarray(x)
+    nsamp, nchan = x.shape[:2]
+    if ref_freq is None:
+        ref_freq = center_freq
+    freqs = channel_freqs(center_freq, chan_bw, nchan, freq_align)
+    delays = np.asarray(sample_delay(dm, freqs, ref_freq, sample_rate)).round().astype(np.int64)
+    crop_before = -min(0, int(delays[0]), int(delays[-1]))
+    delays = delays + crop_before
+    n_out = nsamp - int(max(delays))
+    y = np.stack([x[j:j + n_out, i] for i, j in enumerate(delays)], axis=1)
+    return y, crop_before, delays
+
+
 # ----------------------------------------------------------------------------------------
 # channelize / unchannelize                  reference: contrib/misc.py:17-93
 # ----------------------------------------------------------------------------------------

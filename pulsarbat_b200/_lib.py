@@ -17,7 +17,7 @@ EXPORTS = [
     "pbk_version", "pbk_last_error", "pbk_status_string", "pbk_device_count",
     "pbk_dedisp_plan_create", "pbk_dedisp_out_shape", "pbk_dedisp_exec_host",
     "pbk_dedisp_exec_device", "pbk_fft_plan_create", "pbk_stft_plan_create",
-    "pbk_fft_exec_host", "pbk_fft_exec_device", "pbk_detect", "pbk_detect_scrunch", "pbk_downsample", "pbk_fold",
+    "pbk_fft_exec_host", "pbk_fft_exec_device", "pbk_detect", "pbk_detect_scrunch", "pbk_shift_channels", "pbk_downsample", "pbk_fold",
     "pbk_stokes", "pbk_pol_basis", "pbk_chirp",
     "pbk_plan_destroy", "pbk_plan_info", "pbk_plan_describe", "pbk_plan_profile",
     "pbk_plan_profile_read", "pbk_plan_segments", "pbk_malloc", "pbk_free", "pbk_memcpy_h2d",
@@ -82,6 +82,8 @@ def lib():
         L.pbk_fft_exec_device.argtypes = [vp, vp, vp, vp]
         L.pbk_detect.argtypes = [vp, vp, i64, i64, i64, i32, i64, i32, i32, vp]
         L.pbk_detect_scrunch.argtypes = [vp, vp, i64, i64, i64, i32, i64, i64, i32, i32, vp]
+        L.pbk_shift_channels.argtypes = [vp, vp, i64, i64, i64, i64, ctypes.POINTER(i64), i32, i32,
+                                         vp]
         L.pbk_downsample.argtypes = [vp, vp, i64, i64, i64, i32, i32, vp]
         L.pbk_fold.argtypes = [vp, i64, i64, ctypes.POINTER(dbl), i32, dbl, i64, i32, vp, vp, vp,
                                i32, i32, vp]

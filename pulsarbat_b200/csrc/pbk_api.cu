@@ -1124,6 +1124,43 @@ extern "C" int pbk_detect_scrunch(const void* in, void* out, int64_t nsamp, int6
   return PBK_OK;
 }
 
+extern "C" int pbk_shift_channels(const void* in, void* out, int64_t nsamp_in, int64_t nsamp_out,
+                                  int64_t nchan, int64_t cell_bytes, const int64_t* delays,
+                                  int32_t on_device, int32_t device, void* stream) {
+  if (!in || !out || !delays) return fail(PBK_ERR_INVALID, "NULL pointer");
+  if (nsamp_in <= 0 || nsamp_out < 0 || nchan <= 0 || cell_bytes <= 0 || cell_bytes % 4)
+    return fail(PBK_ERR_INVALID, "bad shape (cell_bytes must be a positive multiple of 4)");
+  for (int64_t c = 0; c < nchan; ++c)
+    if (delays[c] < 0 || delays[c] + nsamp_out > nsamp_in)
+      return fail(PBK_ERR_INVALID, "delay[%lld] = %lld reads outside the input", (long long)c,
+                  (long long)delays[c]);
+  if (nsamp_out == 0) return PBK_OK;
+  CUDA_TRY(cudaSetDevice(device));
+  const long long words = cell_bytes / 4;
+  DevBuf dd, di, dout;
+  CUDA_TRY(cudaMalloc(&dd.p, (size_t)nchan * 8));
+  cudaStream_t st = on_device ? reinterpret_cast<cudaStream_t>(stream) : cudaStreamPerThread;
+  CUDA_TRY(cudaMemcpyAsync(dd.p, delays, (size_t)nchan * 8, cudaMemcpyHostToDevice, st));
+  const void* src = in;
+  void* dst = out;
+  const size_t ib = (size_t)nsamp_in * nchan * cell_bytes, ob = (size_t)nsamp_out * nchan * cell_bytes;
+  if (!on_device) {
+    CUDA_TRY(cudaMalloc(&di.p, ib));
+    CUDA_TRY(cudaMalloc(&dout.p, ob));
+    CUDA_TRY(cudaMemcpyAsync(di.p, in, ib, cudaMemcpyHostToDevice, st));
+    src = di.p;
+    dst = dout.p;
+  }
+  cudaError_t e = launch_1d(shift_channels_kernel, nsamp_out * nchan * words, st,
+                            reinterpret_cast<const unsigned*>(src),
+                            reinterpret_cast<unsigned*>(dst), (long long)nsamp_out,
+                            (long long)nchan, words, reinterpret_cast<const long long*>(dd.p));
+  if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "shift launch: %s", cudaGetErrorString(e));
+  if (!on_device) CUDA_TRY(cudaMemcpyAsync(out, dout.p, ob, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));   // the delay table is freed on return
+  return PBK_OK;
+}
+
 extern "C" int pbk_downsample(const void* in, void* out, int64_t nsamp, int64_t row_elems,
                               int64_t factor, int32_t on_device, int32_t device, void* stream) {
   if (!in || !out) return fail(PBK_ERR_INVALID, "NULL data pointer");

@@ -153,6 +153,24 @@ static inline cudaError_t launch_detect_scrunch(const float2* in, float* out, lo
   return cudaGetLastError();
 }
 
+// incoherent dedispersion (transforms/dedispersion.py:136-177): per-channel integer roll + crop,
+//   out[n, c, :] = in[n + delay[c], c, :]      n < rows_out
+// a pure gather on 4-byte words: `words` words per (row, channel) cell, `C` cells per row.
+__global__ void __launch_bounds__(256) shift_channels_kernel(const unsigned* __restrict__ in,
+                                                             unsigned* __restrict__ out,
+                                                             long long rows_out, long long C,
+                                                             long long words,
+                                                             const long long* __restrict__ delay) {
+  const long long rw = C * words;           // words per row
+  const long long total = rows_out * rw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / rw, r = i - n * rw;
+    const long long c = r / words;
+    out[i] = __ldg(in + (n + __ldg(delay + c)) * rw + r);
+  }
+}
+
 // full Stokes [I, Q, U, V] from (A, B) pol pairs (core.py:937-966, PSR/IEEE convention)
 //   linear:   I=AA+BB  Q=AA-BB  U=2Re(A*B)  V=2Im(A*B)
 //   circular: I=AA+BB  Q=2Re(A*B)  U=2Im(A*B)  V=AA-BB          (A*B = conj(A) B)

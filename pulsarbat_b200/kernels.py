@@ -18,7 +18,7 @@ import numpy as np
 from . import _lib as L
 from .device import DeviceArray
 
-__all__ = ["default_device", "dedisperse", "chirp", "detect", "stokes", "pol_basis",
+__all__ = ["default_device", "dedisperse", "chirp", "detect", "shift_channels", "stokes", "pol_basis",
            "downsample", "fft", "stft", "istft", "fold", "clear_plan_cache"]
 
 
@@ -215,6 +215,35 @@ def detect(data, stokes=False, downsample=1, freq_sum=1, device=None):
     call(L.ptr(x), L.ptr(out), 0, dev, None)
     rdt = _real_of(odt)
     return out if rdt == np.float32 else out.astype(rdt)
+
+
+def shift_channels(data, delays, nsamp_out, device=None):
+    """out[n, c, ...] = data[n + delays[c], c, ...] for n < nsamp_out (incoherent dedispersion,
+    dedispersion.py:171): any 4- or 8-byte element type, bit-exact copy."""
+    shape = tuple(data.shape)
+    nsamp, nchan = shape[0], shape[1]
+    d = np.ascontiguousarray(delays, dtype=np.int64)
+    if d.shape != (nchan,):
+        raise ValueError(f"delays must have shape ({nchan},)")
+    itemsize = np.dtype(data.dtype).itemsize
+    cell = int(np.prod(shape[2:], dtype=np.int64)) * itemsize if len(shape) > 2 else itemsize
+    if cell % 4:
+        raise L.PbkUnsupported(-2, "element cells must be a multiple of 4 bytes")
+    out_shape = (int(nsamp_out),) + shape[1:]
+    dp = d.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))
+    if _is_dev(data):
+        x = data.contiguous()
+        out = DeviceArray.empty(out_shape, x.dtype, x.device)
+        L.check(L.lib().pbk_shift_channels(L.ptr(x.ptr), L.ptr(out.ptr), nsamp, int(nsamp_out),
+                                           nchan, cell, dp, 1, x.device,
+                                           ctypes.c_void_p(_stream())))
+        return out
+    x = np.ascontiguousarray(data)
+    out = np.empty(out_shape, x.dtype)
+    dev = default_device() if device is None else device
+    L.check(L.lib().pbk_shift_channels(L.ptr(x), L.ptr(out), nsamp, int(nsamp_out), nchan, cell,
+                                       dp, 0, dev, None))
+    return out
 
 
 def _pairs_op(data, fn, flag, out_real, device):

@@ -12,10 +12,10 @@ import numpy as np
 from .. import _lib as L
 from .. import kernels
 from .. import units as u
-from ..core import BasebandSignal, IntensitySignal, Signal
+from ..core import BasebandSignal, IntensitySignal, RadioSignal, Signal
 
-__all__ = ["DispersionMeasure", "DM", "coherent_dedispersion", "dedisperse_detect",
-           "overlap_save_dedispersion"]
+__all__ = ["DispersionMeasure", "DM", "coherent_dedispersion", "incoherent_dedispersion",
+           "dedisperse_detect", "overlap_save_dedispersion"]
 
 #: s MHz^2 cm^3 / pc -- dedispersion.py:30
 DISPERSION_CONSTANT = 1.0 / 2.41e-4
@@ -135,6 +135,35 @@ def coherent_dedispersion(z, DM, /, *, ref_freq=None, chirp=None):
         # empty crop: the reference would hand back a zero-length slice (dedispersion.py:133)
         start = min(start, len(z))
     return _cropped_like(type(z), z, x, start)
+
+
+def incoherent_delays(z, DM, ref_freq):
+    """(delays, N_out, crop_before) exactly as dedispersion.py:164-169."""
+    delays = np.asarray(DM.sample_delay(z.channel_freqs, ref_freq, z.sample_rate), dtype=float)
+    delays = np.atleast_1d(delays).round().astype(np.int64)
+    crop_before = -min(0, int(delays[0]), int(delays[-1]))
+    delays = delays + crop_before
+    return delays, len(z) - int(max(delays)), crop_before
+
+
+def incoherent_dedispersion(z, DM, /, *, ref_freq=None):
+    """Incoherently dedisperse a signal: per-channel integer roll and crop (drop-in for
+    dedispersion.py:136-177; same TypeError, crop and start_time update).  Any real or complex
+    RadioSignal; the roll is a bit-exact gather on the GPU."""
+    if not isinstance(z, RadioSignal):
+        raise TypeError("Signal must be a RadioSignal object.")
+    DM = _as_dm(DM)
+    if ref_freq is None:
+        ref_freq = z.center_freq
+    delays, n_out, crop_before = incoherent_delays(z, DM, ref_freq)
+    if n_out < 0 or int(delays.min()) < 0:
+        # numpy's negative slices would wrap here (sweep longer than the signal); refuse instead
+        raise ValueError("dispersion sweep exceeds the signal length")
+    x = kernels.shift_channels(z.data, delays, n_out)
+    kw = {}
+    if crop_before and z.start_time is not None:
+        kw["start_time"] = z.start_time + crop_before / z.sample_rate
+    return type(z).like(z, x, **kw)
 
 
 def dedisperse_detect(z, DM, /, *, ref_freq=None, stokes_I=False, downsample=1, crop=True):

@@ -237,3 +237,24 @@ def test_overlap_save_matches_blockwise_definition():
     a = y[lo - first:hi - first]
     b = full[lo - s_full:hi - s_full]
     assert np.linalg.norm(a - b) / np.linalg.norm(b) < 0.05
+
+
+@pytest.mark.parametrize("dm", [50.0, 100.0, 200.0])
+def test_incoherent_dedispersion_crop(dm):
+    """reference tests/test_dedispersion.py:167-189: the crop equals the rounded band-edge delays."""
+    sr, ref, bw = 1e3, 1e9, 8e6
+    x = np.random.default_rng(1).standard_normal((8192, 32, 4))
+    y, crop_before, delays = orc.incoherent_dedispersion(x, dm, sample_rate=sr, center_freq=ref,
+                                                         chan_bw=bw)
+    freqs = orc.channel_freqs(ref, bw, 32)
+    d_top = np.round(orc.sample_delay(dm, ref, freqs[-1], sr))
+    d_bot = np.round(orc.sample_delay(dm, freqs[0], ref, sr))
+    assert x.shape[0] - y.shape[0] == int(d_top + d_bot)
+    # an impulse at the dispersed arrival time of every channel lines up after dedispersion
+    imp = np.zeros((8192, 32))
+    n0 = 4000
+    raw = np.round(orc.sample_delay(dm, freqs, ref, sr)).astype(int)
+    imp[n0 + raw, np.arange(32)] = 1.0
+    yi, cb, _ = orc.incoherent_dedispersion(imp, dm, sample_rate=sr, center_freq=ref, chan_bw=bw)
+    rows = np.argmax(yi, axis=0)
+    assert np.all(rows == rows[0]) and rows[0] == n0 - cb
