@@ -91,6 +91,19 @@ int pbk_dedisp_exec_host(pbk_plan* plan, const void* in, void* out, const void* 
 int pbk_dedisp_exec_device(pbk_plan* plan, const void* d_in, void* d_out, const void* d_chirp,
                            void* stream);
 
+/* ---- FFT-domain phase ramp / band mask ("next" rows: time_shift, freq_shift) ------------------
+ * Replaces the core of transforms/transforms.py:268-271 (time_shift) and :348-361 (freq_shift):
+ *   out[:, col] = ifft(fft(in[:, col]) * H_col),
+ *   H_col[k] = 0 if lo_col <= fftshift_position(k) < hi_col, else exp(-2 pi i s_col fftfreq(N,1)[k])
+ * in/out are (nsamp, ncols) complex64.  Execute with pbk_dedisp_exec_host / _device (chirp NULL).
+ * zero_lo / zero_hi may be NULL (no zeroed band), shift_samples may be NULL (no ramp). */
+int pbk_ramp_plan_create(int64_t nsamp, int64_t ncols, const double* shift_samples,
+                         const int64_t* zero_lo, const int64_t* zero_hi, int32_t device,
+                         pbk_plan** plan);
+/* out[n, col] = in[n, col] * exp(+2 pi i cycles_per_sample[col] * n)   (transforms.py:346) */
+int pbk_mix(const void* in, void* out, int64_t nsamp, int64_t ncols,
+            const double* cycles_per_sample, int32_t on_device, int32_t device, void* stream);
+
 /* ---- axis-0 complex FFT --------------------------------------------------------------------
  * Replaces fft.py:30-48 `pb.fft.fft` / `pb.fft.ifft` with axis=0 for complex64 data (scipy
  * "backward" normalisation: forward unscaled, inverse 1/n), natural-order output.

@@ -167,6 +167,61 @@ def incoherent_dedispersion(x, dm, *, sample_rate, center_freq, chan_bw, freq_al
 
 
 # ----------------------------------------------------------------------------------------
+# FFT-based shifts                           reference: transforms/transforms.py:211-361
+# ----------------------------------------------------------------------------------------
+def time_shift(x, shift):
+    """transforms.py:248-286 for an array x (time axis 0) and per-sample-shape shifts (samples):
+    ifft(fft(x) * exp(-2j pi shift fftfreq(N, 1))) with the wrapped-around samples zeroed.
+    Returns (shifted, start, stop) where [start : N + stop] is the crop of ``crop=True``."""
+    x = np.asarray(x)
+    shift = np.array(shift, dtype=np.float64)
+    if shift.ndim > 0:
+        ix = (slice(None),) * shift.ndim + (None,) * (x.ndim - shift.ndim - 1)
+        shift = shift[ix]
+    f_ix = tuple(slice(None) if j == 0 else None for j in range(x.ndim))
+    f = np.fft.fftfreq(x.shape[0], 1)[f_ix]
+    ph = np.exp(-2j * np.pi * shift * f).astype(np.complex64)
+    shifted = scipy.fft.ifft(scipy.fft.fft(x, axis=0) * ph, axis=0)
+    shifted = shifted if np.iscomplexobj(x) else shifted.real
+    start, stop = 0, 0
+    it = np.nditer(np.broadcast_to(shift, x.shape[1:]) if shift.ndim else shift,
+                   flags=["multi_index"])
+    for a in it:
+        if a < 0:
+            a = int(np.floor(a))
+            shifted[(np.s_[a:],) + it.multi_index] = 0
+            stop = min(stop, a)
+        else:
+            a = int(np.ceil(a))
+            shifted[(np.s_[:a],) + it.multi_index] = 0
+            start = max(start, a)
+    return shifted, start, stop
+
+
+def freq_shift(x, ft):
+    """transforms.py:338-361 with ft = shift * dt (cycles per sample) per sample-shape element."""
+    x = np.asarray(x)
+    ft = np.array(ft, dtype=np.float64)
+    if ft.ndim == 0:
+        ft = ft[None]
+    ix = (slice(None),) * ft.ndim + (None,) * (x.ndim - ft.ndim - 1)
+    ft = ft[ix]
+    n = np.arange(x.shape[0])
+    nix = tuple(slice(None) if j == 0 else None for j in range(x.ndim))
+    ph = np.exp(2j * np.pi * ft * n[nix]).astype(x.dtype)
+    X = np.fft.fftshift(scipy.fft.fft(x * ph, axis=0), axes=(0,))
+    it = np.nditer(np.broadcast_to(ft, x.shape[1:]) * x.shape[0], flags=["multi_index"])
+    for a in it:
+        if a < 0:
+            a = int(np.floor(a))
+            X[(np.s_[a:],) + it.multi_index] = 0
+        else:
+            a = int(np.ceil(a))
+            X[(np.s_[:a],) + it.multi_index] = 0
+    return scipy.fft.ifft(np.fft.ifftshift(X, axes=(0,)), axis=0)
+
+
+# ----------------------------------------------------------------------------------------
 # channelize / unchannelize                  reference: contrib/misc.py:17-93
 # ----------------------------------------------------------------------------------------
 def stft(x, nperseg):

@@ -18,7 +18,7 @@ EXPORTS = [
     "pbk_dedisp_plan_create", "pbk_dedisp_out_shape", "pbk_dedisp_exec_host",
     "pbk_dedisp_exec_device", "pbk_fft_plan_create", "pbk_stft_plan_create",
     "pbk_fft_exec_host", "pbk_fft_exec_device", "pbk_detect", "pbk_detect_scrunch", "pbk_shift_channels", "pbk_downsample", "pbk_fold",
-    "pbk_stokes", "pbk_pol_basis", "pbk_chirp",
+    "pbk_stokes", "pbk_pol_basis", "pbk_chirp", "pbk_ramp_plan_create", "pbk_mix",
     "pbk_plan_destroy", "pbk_plan_info", "pbk_plan_describe", "pbk_plan_profile",
     "pbk_plan_profile_read", "pbk_plan_segments", "pbk_malloc", "pbk_free", "pbk_memcpy_h2d",
     "pbk_memcpy_d2h", "pbk_device_sync",
@@ -90,6 +90,9 @@ def lib():
         L.pbk_stokes.argtypes = [vp, vp, i64, i32, i32, i32, vp]
         L.pbk_pol_basis.argtypes = [vp, vp, i64, i32, i32, i32, vp]
         L.pbk_chirp.argtypes = [i64, i64, dbl, dbl, dbl, ctypes.POINTER(dbl), vp, i32, i32, vp]
+        L.pbk_ramp_plan_create.argtypes = [i64, i64, ctypes.POINTER(dbl), ctypes.POINTER(i64),
+                                           ctypes.POINTER(i64), i32, ctypes.POINTER(vp)]
+        L.pbk_mix.argtypes = [vp, vp, i64, i64, ctypes.POINTER(dbl), i32, i32, vp]
         L.pbk_plan_destroy.argtypes = [vp]
         L.pbk_plan_destroy.restype = None
         L.pbk_plan_info.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i64),
@@ -224,6 +227,35 @@ class DedispPlan(Plan):
 
     def exec_device(self, d_in, d_out, d_chirp=None, stream=0):
         check(lib().pbk_dedisp_exec_device(self.handle, ptr(d_in), ptr(d_out), ptr(d_chirp),
+                                           ctypes.c_void_p(stream)))
+
+
+class RampPlan(Plan):
+    """ifft(fft(x) * H) with a per-column linear phase ramp and/or zeroed band (pbk_ramp_plan_create)."""
+
+    def __init__(self, nsamp, ncols, shift_samples=None, zero_lo=None, zero_hi=None, device=0):
+        def arr(a, dt):
+            if a is None:
+                return None, None
+            a = np.ascontiguousarray(a, dtype=dt)
+            if a.shape != (ncols,):
+                raise ValueError(f"per-column arrays must have shape ({ncols},)")
+            ct = ctypes.c_double if dt == np.float64 else ctypes.c_int64
+            return a, a.ctypes.data_as(ctypes.POINTER(ct))
+        self._keep = [arr(shift_samples, np.float64), arr(zero_lo, np.int64),
+                      arr(zero_hi, np.int64)]
+        h = ctypes.c_void_p(0)
+        check(lib().pbk_ramp_plan_create(nsamp, ncols, self._keep[0][1], self._keep[1][1],
+                                         self._keep[2][1], device, ctypes.byref(h)))
+        super().__init__(h)
+        self.nsamp, self.ncols = nsamp, ncols
+
+    def exec_host(self, x, out):
+        check(lib().pbk_dedisp_exec_host(self.handle, ptr(x), ptr(out), None))
+        return out
+
+    def exec_device(self, d_in, d_out, stream=0):
+        check(lib().pbk_dedisp_exec_device(self.handle, ptr(d_in), ptr(d_out), None,
                                            ctypes.c_void_p(stream)))
 
 

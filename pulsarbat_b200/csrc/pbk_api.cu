@@ -101,6 +101,8 @@ struct pbk_plan {
   float2* d_tw = nullptr;
   double* d_chanfreq = nullptr;
   double* d_chanconst = nullptr;   // per-channel constants of the fast MID chirp
+  double* d_ramp_shift = nullptr;  // CHIRP_RAMP plans: s/N per column
+  long long* d_ramp_zero = nullptr;   // and the zeroed band [lo, hi) per column
   bool chirp_series_ok = true;     // |delta/fc| small enough for the division-free chirp
   float2* d_ftab = nullptr;     // stage tables of the fast kernels
   int num_sms = 148;
@@ -434,7 +436,44 @@ static void mark_scratch_layout(pbk_plan* pl, long long I) {
 // ------------------------------------------------------------------------------------------
 // dedispersion plan
 // ------------------------------------------------------------------------------------------
+struct RampSpec {   // linear-phase / band-zeroing transfer function per column (CHIRP_RAMP)
+  const double* shift_samples;
+  const int64_t* zero_lo;
+  const int64_t* zero_hi;
+};
+
+static int dedisp_plan_create_impl(const pbk_dedisp_desc* d, const RampSpec* ramp, pbk_plan** out);
+
 extern "C" int pbk_dedisp_plan_create(const pbk_dedisp_desc* d, pbk_plan** out) {
+  return dedisp_plan_create_impl(d, nullptr, out);
+}
+
+extern "C" int pbk_ramp_plan_create(int64_t nsamp, int64_t ncols, const double* shift_samples,
+                                    const int64_t* zero_lo, const int64_t* zero_hi,
+                                    int32_t device, pbk_plan** plan) {
+  if (!plan) return fail(PBK_ERR_INVALID, "plan is NULL");
+  if (nsamp <= 0 || ncols <= 0) return fail(PBK_ERR_INVALID, "shape must be positive");
+  std::vector<double> freqs((size_t)ncols, 1.0);
+  pbk_dedisp_desc d;
+  memset(&d, 0, sizeof(d));
+  d.nsamp = nsamp;
+  d.nchan = ncols;
+  d.npol = 1;
+  d.in_dtype = PBK_C64;
+  d.out_kind = PBK_OUT_C64;
+  d.dm = 0.0;
+  d.sample_rate_hz = 1.0;
+  d.ref_freq_hz = 1.0;
+  d.chan_freq_hz = freqs.data();
+  d.crop_start = 0;
+  d.crop_stop = nsamp;
+  d.downsample = 1;
+  d.device = device;
+  RampSpec r{shift_samples, zero_lo, zero_hi};
+  return dedisp_plan_create_impl(&d, &r, plan);
+}
+
+static int dedisp_plan_create_impl(const pbk_dedisp_desc* d, const RampSpec* ramp, pbk_plan** out) {
   if (!d || !out) return fail(PBK_ERR_INVALID, "NULL argument");
   *out = nullptr;
   if (d->nsamp <= 0 || d->nchan <= 0 || d->npol <= 0)
@@ -544,7 +583,7 @@ extern "C" int pbk_dedisp_plan_create(const pbk_dedisp_desc* d, pbk_plan** out) 
     ps.a.mout = ps.a.min;
     set_klow(ps.a, i + 1, l);
     ps.a.log2Kmul = log2ll(Kprev[i]);
-    ps.a.chirp_kind = d->explicit_chirp ? CHIRP_ARRAY : CHIRP_COMPUTED;
+    ps.a.chirp_kind = ramp ? CHIRP_RAMP : d->explicit_chirp ? CHIRP_ARRAY : CHIRP_COMPUTED;
     ps.a.N = N;
     {
       const double dt = 1.0 / d->sample_rate_hz;      // Signal.dt, core.py:250-253
@@ -630,7 +669,27 @@ extern "C" int pbk_dedisp_plan_create(const pbk_dedisp_desc* d, pbk_plan** out) 
     if (e != cudaSuccess)
       return cleanup(fail(PBK_ERR_CUDA, "chan_const upload: %s", cudaGetErrorString(e)));
   }
+  if (ramp) {
+    std::vector<double> sh((size_t)C);
+    std::vector<long long> zr((size_t)C * 2);
+    for (long long c = 0; c < C; ++c) {
+      sh[c] = (ramp->shift_samples ? ramp->shift_samples[c] : 0.0) / (double)N;
+      zr[2 * c] = ramp->zero_lo ? ramp->zero_lo[c] : 0;
+      zr[2 * c + 1] = ramp->zero_hi ? ramp->zero_hi[c] : 0;
+    }
+    cudaError_t e = cudaMalloc(&pl->d_ramp_shift, sh.size() * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_ramp_zero, zr.size() * sizeof(long long));
+    if (e == cudaSuccess)
+      e = cudaMemcpy(pl->d_ramp_shift, sh.data(), sh.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+      e = cudaMemcpy(pl->d_ramp_zero, zr.data(), zr.size() * sizeof(long long),
+                     cudaMemcpyHostToDevice);
+    if (e != cudaSuccess)
+      return cleanup(fail(PBK_ERR_CUDA, "ramp upload: %s", cudaGetErrorString(e)));
+  }
   for (auto& ps : pl->passes) {
+    ps.a.ramp_shift = pl->d_ramp_shift;
+    ps.a.ramp_zero = pl->d_ramp_zero;
     ps.a.chan_freq = pl->d_chanfreq;
     ps.a.chan_const = pl->d_chanconst;
     ps.a.bd = std::isinf(d->ref_freq_hz) ? 0.0
@@ -989,6 +1048,8 @@ extern "C" void pbk_plan_destroy(pbk_plan* pl) {
   cudaFree(pl->d_ftab);
   cudaFree(pl->d_chanfreq);
   cudaFree(pl->d_chanconst);
+  cudaFree(pl->d_ramp_shift);
+  cudaFree(pl->d_ramp_zero);
   cudaFree(pl->d_tmpf);
   cudaFree(pl->h_din);
   cudaFree(pl->h_dout);
@@ -1261,6 +1322,28 @@ static int run_elementwise(const void* in, void* out, size_t in_bytes, size_t ou
   CUDA_TRY(cudaMemcpyAsync(out, dout.p, out_bytes, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   return PBK_OK;
+}
+
+extern "C" int pbk_mix(const void* in, void* out, int64_t nsamp, int64_t ncols,
+                       const double* cycles_per_sample, int32_t on_device, int32_t device,
+                       void* stream) {
+  if (nsamp < 0 || ncols <= 0 || !cycles_per_sample) return fail(PBK_ERR_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(device));
+  DevBuf df;
+  CUDA_TRY(cudaMalloc(&df.p, (size_t)ncols * 8));
+  CUDA_TRY(cudaMemcpy(df.p, cycles_per_sample, (size_t)ncols * 8, cudaMemcpyHostToDevice));
+  const size_t nb = (size_t)nsamp * ncols * 8;
+  int rc = run_elementwise(in, out, nb, nb, on_device, device, stream,
+                           [&](const void* i, void* o, cudaStream_t st) {
+                             return launch_1d(mix_kernel, nsamp * ncols, st,
+                                              reinterpret_cast<const float2*>(i),
+                                              reinterpret_cast<float2*>(o), (long long)nsamp,
+                                              (long long)ncols,
+                                              reinterpret_cast<const double*>(df.p));
+                           });
+  if (rc == PBK_OK && on_device)
+    CUDA_TRY(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));  // df is freed here
+  return rc;
 }
 
 extern "C" int pbk_stokes(const void* in, void* out, int64_t npairs, int32_t circular,

@@ -35,7 +35,7 @@ namespace pbk {
 enum { MODE_FWD = 0, MODE_MID = 1, MODE_INV = 2 };
 enum { LOAD_C64 = 0, LOAD_I8X2 = 1, LOAD_PLANAR = 2 };
 enum { EPI_C64 = 0, EPI_INTENSITY = 1, EPI_STOKES_I = 2 };
-enum { CHIRP_NONE = 0, CHIRP_COMPUTED = 1, CHIRP_ARRAY = 2 };
+enum { CHIRP_NONE = 0, CHIRP_COMPUTED = 1, CHIRP_ARRAY = 2, CHIRP_RAMP = 3 };
 
 constexpr int kThreads = 256;
 constexpr int kMaxStages = 4;
@@ -81,6 +81,9 @@ struct PassArgs {
   double df, fr_sub, inv_fr, a0, D;
   const float2* chirp_arr;
   long long chirp_sk, chirp_sc;
+  // CHIRP_RAMP: per column, H_k = exp(-2 pi i s k_signed / N) outside the zeroed band
+  const double* ramp_shift;     // s / N per column (cycles per bin)
+  const long long* ramp_zero;   // [lo, hi) per column in fftshift-ed bin order; lo >= hi = none
   long long tile0;    // fast kernels: first tile of this launch (tiles [tile0, ntiles) are processed)
 };
 
@@ -230,6 +233,7 @@ struct LaneCtx {
   long long bin[2], bout[2];   // element offsets (without the row term)
   unsigned int nrest[2];
   int chan[2];
+  int col[2];
   unsigned int klow;           // same for both lanes when FAST; generic path recomputes per lane
   unsigned int klow1;
   bool valid[2];
@@ -260,6 +264,7 @@ __device__ __forceinline__ void lane_setup(const PassArgs& p, LaneCtx& L, int pr
     L.bout[l] = map_base(p.mout, o_orig, kprev, klow, nrest, col, p.P);
     L.nrest[l] = (unsigned int)nrest;
     L.chan[l] = col / p.P;
+    L.col[l] = col;
     L.valid[l] = ok;
     if (l == 0) L.klow = (unsigned int)klow; else L.klow1 = (unsigned int)klow;
   }
@@ -492,6 +497,29 @@ __device__ __forceinline__ void apply_chirp16(const PassArgs& p, const LaneCtx& 
         const float2 h1 = chirp_value(p, f1, kf1);
         v[m] = cmul(v[m], make_float2(h0.x, h1.x), make_float2(h0.y, h1.y));
       }
+    }
+  } else if (p.chirp_kind == CHIRP_RAMP) {
+    // linear phase ramp per column (transforms.py:271 time_shift) and/or a zeroed band
+    // (transforms.py:350-359 freq_shift); phase in FP64, reduced exactly before sincospif
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      const unsigned int k = kbase + m * kstep;
+      float2 h[2];
+#pragma unroll
+      for (int l = 0; l < 2; ++l) {
+        const long long kf = (long long)(l == 0 ? L.klow : (FAST ? L.klow : L.klow1)) +
+                             ((long long)k << p.log2Kmul);
+        const long long ks = (kf >= (p.N >> 1)) ? kf - p.N : kf;
+        const int col = L.col[l];
+        const double ph = (double)ks * p.ramp_shift[col];
+        const double fr = ph - rint(ph);
+        float s, c;
+        sincospif(2.0f * (float)fr, &s, &c);
+        const long long sh = (kf + (p.N >> 1)) & (p.N - 1);   // position after fftshift
+        const bool zero = sh >= p.ramp_zero[2 * col] && sh < p.ramp_zero[2 * col + 1];
+        h[l] = zero ? make_float2(0.f, 0.f) : make_float2(c * p.scale, -s * p.scale);
+      }
+      v[m] = cmul(v[m], make_float2(h[0].x, h[1].x), make_float2(h[0].y, h[1].y));
     }
   } else {  // explicit (N, C) complex64 array supplied by the caller (dedispersion.py:121-124)
 #pragma unroll

@@ -171,6 +171,25 @@ __global__ void __launch_bounds__(256) shift_channels_kernel(const unsigned* __r
   }
 }
 
+// mixing with a complex sinusoid per column (transforms.py:346 freq_shift):
+//   out[n, col] = in[n, col] * exp(+2 pi i ft[col] n),  ft in cycles per sample, phase in FP64
+__global__ void __launch_bounds__(256) mix_kernel(const float2* __restrict__ in,
+                                                  float2* __restrict__ out, long long nsamp,
+                                                  long long ncols,
+                                                  const double* __restrict__ ft) {
+  const long long total = nsamp * ncols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / ncols, col = i - n * ncols;
+    const double ph = __ldg(ft + col) * (double)n;
+    const double fr = ph - rint(ph);
+    float s, c;
+    sincospif(2.0f * (float)fr, &s, &c);
+    const float2 v = __ldg(in + i);
+    out[i] = make_float2(v.x * c - v.y * s, v.x * s + v.y * c);
+  }
+}
+
 // full Stokes [I, Q, U, V] from (A, B) pol pairs (core.py:937-966, PSR/IEEE convention)
 //   linear:   I=AA+BB  Q=AA-BB  U=2Re(A*B)  V=2Im(A*B)
 //   circular: I=AA+BB  Q=2Re(A*B)  U=2Im(A*B)  V=AA-BB          (A*B = conj(A) B)

@@ -18,7 +18,7 @@ import numpy as np
 from . import _lib as L
 from .device import DeviceArray
 
-__all__ = ["default_device", "dedisperse", "chirp", "detect", "shift_channels", "stokes", "pol_basis",
+__all__ = ["default_device", "dedisperse", "chirp", "detect", "shift_channels", "phase_ramp", "mix", "stokes", "pol_basis",
            "downsample", "fft", "stft", "istft", "fold", "clear_plan_cache"]
 
 
@@ -244,6 +244,61 @@ def shift_channels(data, delays, nsamp_out, device=None):
     L.check(L.lib().pbk_shift_channels(L.ptr(x), L.ptr(out), nsamp, int(nsamp_out), nchan, cell,
                                        dp, 0, dev, None))
     return out
+
+
+def phase_ramp(data, shift_samples=None, zero_lo=None, zero_hi=None, device=None):
+    """ifft(fft(x, axis=0) * H, axis=0) for (nsamp, ncols) complex data with, per column,
+    H[k] = exp(-2 pi i shift fftfreq(N, 1)[k]) and H = 0 where lo <= fftshift position < hi
+    (transforms.py:268-271 and :348-361)."""
+    shape = tuple(data.shape)
+    if len(shape) != 2:
+        raise ValueError("phase_ramp takes (nsamp, ncols) data")
+    nsamp, ncols = shape
+    dev = data.device if _is_dev(data) else (default_device() if device is None else device)
+
+    def key_of(a, dt):
+        return None if a is None else np.ascontiguousarray(a, dtype=dt).tobytes()
+    key = ("ramp", nsamp, ncols, key_of(shift_samples, np.float64), key_of(zero_lo, np.int64),
+           key_of(zero_hi, np.int64), dev)
+    ent = _get_plan(key, lambda: L.RampPlan(nsamp, ncols, shift_samples, zero_lo, zero_hi,
+                                            device=dev))
+    if _is_dev(data):
+        x = data.contiguous()
+        if x.dtype != np.complex64:
+            x = x.astype(np.complex64)
+        out = DeviceArray.empty(shape, np.complex64, dev)
+        with ent.lock:
+            ent.plan.exec_device(x.ptr, out.ptr, _stream())
+        return out
+    x, odt = _host_c64(data)
+    out = np.empty(shape, np.complex64)
+    with ent.lock:
+        ent.plan.exec_host(x, out)
+    return out if odt == np.complex64 else out.astype(odt)
+
+
+def mix(data, cycles_per_sample, device=None):
+    """out[n, col] = data[n, col] * exp(+2 pi i cycles_per_sample[col] * n) (transforms.py:346)."""
+    shape = tuple(data.shape)
+    if len(shape) != 2:
+        raise ValueError("mix takes (nsamp, ncols) data")
+    ft = np.ascontiguousarray(cycles_per_sample, dtype=np.float64)
+    if ft.shape != (shape[1],):
+        raise ValueError(f"cycles_per_sample must have shape ({shape[1]},)")
+    fp = ft.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    if _is_dev(data):
+        x = data.contiguous()
+        if x.dtype != np.complex64:
+            x = x.astype(np.complex64)
+        out = DeviceArray.empty(shape, np.complex64, x.device)
+        L.check(L.lib().pbk_mix(L.ptr(x.ptr), L.ptr(out.ptr), shape[0], shape[1], fp, 1, x.device,
+                                ctypes.c_void_p(_stream())))
+        return out
+    x, odt = _host_c64(data)
+    out = np.empty(shape, np.complex64)
+    dev = default_device() if device is None else device
+    L.check(L.lib().pbk_mix(L.ptr(x), L.ptr(out), shape[0], shape[1], fp, 0, dev, None))
+    return out if odt == np.complex64 else out.astype(odt)
 
 
 def _pairs_op(data, fn, flag, out_real, device):

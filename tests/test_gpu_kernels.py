@@ -447,3 +447,67 @@ def test_incoherent_dedispersion_bit_exact(dm, dtype):
     assert z2.start_time.isclose(t0 + crop_before / (sr * u.Hz))
     with pytest.raises(TypeError):
         pb.incoherent_dedispersion(pb.Signal(x, sample_rate=sr * u.Hz), pb.DM(dm))
+
+
+# ------------------------------------------------------------------------------ FFT shifts
+@pytest.mark.parametrize("shape", [(4096, 4, 2), (4096, 4), (4096,), (2 ** 16, 3)])
+@pytest.mark.parametrize("use_complex", [True, False])
+def test_time_shift_matches_oracle(shape, use_complex):
+    """reference transforms.py:211-293 / tests/test_transforms.py:312-378 through the public API."""
+    import pulsarbat_b200 as pb
+    u = pb.units
+    rng = np.random.default_rng(shape[0] + len(shape))
+    x = crandn(rng, shape)
+    if not use_complex:
+        x = np.ascontiguousarray(x.real)
+    t0 = pb.Time(58000.0)
+    z = pb.Signal(x, sample_rate=1e3 * u.Hz, start_time=t0)
+    for shift in [7, -12, 3.25, rng.uniform(-20, 20, shape[1:]) if len(shape) > 1 else -5.5]:
+        y = pb.time_shift(z, shift)
+        want, a, b = orc.time_shift(x.astype(np.complex128 if use_complex else np.float64), shift)
+        assert y.shape == z.shape and y.dtype == z.dtype
+        assert y.start_time.isclose(t0)
+        assert relerr(np.asarray(y.data), want) < 1e-5
+        assert np.array_equal(np.asarray(y.data) == 0, want == 0)       # same zeroed edges
+        yc = pb.time_shift(z, shift, crop=True)
+        assert len(yc) == shape[0] + b - a
+        assert yc.start_time.isclose(t0 + a / (1e3 * u.Hz))
+    assert pb.time_shift(z, 0) is z
+    assert relerr(np.asarray(pb.time_shift(z, 4 * 1e-3 * u.s).data),
+                  orc.time_shift(x.astype(np.complex128), 4)[0] if use_complex
+                  else orc.time_shift(x.astype(np.float64), 4)[0]) < 1e-5
+    if len(shape) == 3:
+        for bad in [(2,), (5, 2), (4, 5), (1, 4), (2, 1), (4, 2, 2)]:
+            with pytest.raises(ValueError):
+                pb.time_shift(z, rng.uniform(-20, 20, bad))
+
+
+def test_freq_shift_matches_oracle_and_reference_kats():
+    """reference transforms.py:296-361 / tests/test_transforms.py:398-509."""
+    import pulsarbat_b200 as pb
+    u = pb.units
+    N = 1024
+    n = np.arange(N) / N
+    fs = np.array([[-52, -45.4], [-25.5, 34], [14, -36.9], [45.1, 27]])
+    tones = np.exp(2j * np.pi * fs[None] * n[:, None, None]).astype(np.complex64)
+    x = pb.BasebandSignal(tones, sample_rate=N * u.Hz, center_freq=1e6 * u.Hz)
+    y = pb.freq_shift(x, -fs * u.Hz)
+    assert isinstance(y, pb.BasebandSignal) and y.shape == x.shape
+    assert np.allclose(np.asarray(y.data), 1, atol=2e-5)             # every tone lands on DC
+    rng = np.random.default_rng(4)
+    z = crandn(rng, (4096, 4, 2))
+    zs = pb.BasebandSignal(z, sample_rate=4096 * u.Hz, center_freq=1e6 * u.Hz)
+    for shift in [49.0, np.array([[4.0, 1.5]]), np.array([5.0, -6.0, 700.25, -8.0])]:
+        got = pb.freq_shift(zs, shift * u.Hz)
+        want = orc.freq_shift(z.astype(np.complex128), np.asarray(shift) / 4096)
+        assert relerr(np.asarray(got.data), want) < 1e-5
+    with pytest.raises(TypeError):
+        pb.freq_shift(pb.Signal(z, sample_rate=1 * u.Hz), 0 * u.Hz)
+    for bad in ["Boo", 50, 50 * u.s]:
+        with pytest.raises(ValueError):
+            pb.freq_shift(zs, bad)
+    for bad_shape in [(2, 2), (2,), (4, 2, 4), (4096, 4, 2), (1, 4, 2)]:
+        with pytest.raises(ValueError):
+            pb.freq_shift(zs, np.ones(bad_shape) * u.Hz)
+    for good_shape in [(), (1,), (1, 1), (4,), (4, 2), (1, 2)]:
+        pb.freq_shift(zs, np.ones(good_shape) * u.Hz)

@@ -258,3 +258,66 @@ def test_incoherent_dedispersion_crop(dm):
     yi, cb, _ = orc.incoherent_dedispersion(imp, dm, sample_rate=sr, center_freq=ref, chan_bw=bw)
     rows = np.argmax(yi, axis=0)
     assert np.all(rows == rows[0]) and rows[0] == n0 - cb
+
+
+# ---------------------------------------------------------------- time_shift / freq_shift KATs
+def _impulse(N, t0):
+    """reference tests/test_transforms.py:27-31."""
+    n = (np.arange(N) - N // 2) / N
+    x = np.exp(-2j * np.pi * np.asarray(t0) * n)
+    return np.fft.ifft(np.fft.ifftshift(x, axes=(-1,))).astype(np.complex128)
+
+
+def _sinusoid(N, f0):
+    """reference tests/test_transforms.py:34-37."""
+    n = np.arange(N) / N
+    return np.exp(2j * np.pi * np.asarray(f0) * n).astype(np.complex128)
+
+
+@pytest.mark.parametrize("shape", [(4096, 4, 2), (4096, 4), (4096,)])
+def test_time_shift_impulses(shape):
+    """reference tests/test_transforms.py:346-378: fractionally delayed impulses line up."""
+    rng = np.random.default_rng(5)
+    N = shape[0]
+    for lo, hi in [(-20, 20), (0, 20), (-20, 0)]:
+        shift = rng.uniform(lo, hi, shape[1:])
+        x = np.moveaxis(_impulse(N, 100 - shift[..., None]), -1, 0)
+        y, a, b = orc.time_shift(x, shift)
+        z = np.zeros_like(y)
+        z[100] = 1.0
+        assert np.allclose(y, z)
+        assert a == max(0, int(np.ceil(shift.max())))
+        assert N + b == N + min(0, int(np.floor(shift.min())))
+
+
+def test_time_shift_integer_rolls():
+    """reference tests/test_transforms.py:312-344."""
+    rng = np.random.default_rng(6)
+    z = rng.standard_normal((4096, 4, 2)) + 1j * rng.standard_normal((4096, 4, 2))
+    for n in [-12, -3, 4, 13]:
+        y, _, _ = orc.time_shift(z, n)
+        if n < 0:
+            assert np.allclose(y[:n], z[-n:], atol=1e-6) and np.allclose(y[n:], 0)
+        else:
+            assert np.allclose(y[n:], z[:-n], atol=1e-6) and np.allclose(y[:n], 0)
+
+
+def test_freq_shift_tones_and_zeroing():
+    """reference tests/test_transforms.py:420-475."""
+    N = 1024
+    fs = np.array([[-52, -45.4], [-25.5, 34], [14, -36.9], [45.1, 27]])
+    x = _sinusoid(N, fs[None].T).T
+    assert np.allclose(orc.freq_shift(x, -fs / N), 1)
+    x = np.zeros((N, 4, 2), np.complex128)
+    x[0] = 1
+    shift = np.array([[10, -10], [20.5, -20.5], [-600, 600], [2000, -2000]])
+    y = np.fft.fftshift(np.abs(scipy.fft.fft(orc.freq_shift(x, shift / N), axis=0)), axes=(0,))
+    for i in range(4):
+        for j in range(2):
+            s = shift[i, j]
+            if s < 0:
+                s = int(np.floor(s))
+                assert np.allclose(y[s:, i, j], 0) and np.allclose(y[:s, i, j], 1)
+            else:
+                s = int(np.ceil(s))
+                assert np.allclose(y[:s, i, j], 0) and np.allclose(y[s:, i, j], 1)
