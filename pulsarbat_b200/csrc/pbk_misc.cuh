@@ -141,11 +141,78 @@ __global__ void __launch_bounds__(256) detect_scrunch_kernel(const float2* __res
   }
 }
 
+// Fast path: P in {1, 2}, F*P a multiple of 64 complex values, Cout a multiple of CELLS.  A warp
+// owns CELLS adjacent output cells of one output row (CELLS*F*P*8 contiguous bytes per input
+// row) and keeps CELLS*SWEEPS 128-bit loads in flight per lane before the shuffle reduction.
+template <int P, int CELLS>
+__global__ void __launch_bounds__(256) detect_scrunch_wide(const float4* __restrict__ in,
+                                                           float* __restrict__ out,
+                                                           long long rows, long long Cout,
+                                                           int stokes, long long M, long long F) {
+  const int lane = threadIdx.x & 31;
+  const long long cells4 = F * P / 2;                 // float4 per cell per input row
+  const long long row4 = Cout * cells4;               // float4 per input row
+  const long long groups = rows * (Cout / CELLS);
+  const long long wstep = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long g = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); g < groups;
+       g += wstep) {
+    const long long j = g / (Cout / CELLS), c0 = (g - j * (Cout / CELLS)) * CELLS;
+    float a0[CELLS], a1[CELLS];
+#pragma unroll
+    for (int q = 0; q < CELLS; ++q) a0[q] = a1[q] = 0.f;
+    for (long long m = 0; m < M; ++m) {
+      const float4* base = in + (j * M + m) * row4 + c0 * cells4 + lane;
+      for (long long i = 0; i < cells4; i += 32) {
+        float4 v[CELLS];
+#pragma unroll
+        for (int q = 0; q < CELLS; ++q) v[q] = __ldcs(base + q * cells4 + i);
+#pragma unroll
+        for (int q = 0; q < CELLS; ++q) {
+          a0[q] += v[q].x * v[q].x + v[q].y * v[q].y;
+          a1[q] += v[q].z * v[q].z + v[q].w * v[q].w;
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < CELLS; ++q) {
+      float x = a0[q], y = a1[q];
+      if (P == 1 || stokes) { x += y; y = 0.f; }
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) {
+        x += __shfl_xor_sync(0xffffffffu, x, s);
+        if (P == 2 && !stokes) y += __shfl_xor_sync(0xffffffffu, y, s);
+      }
+      if (lane == 0) {
+        if (P == 2 && !stokes) {
+          out[(j * Cout + c0 + q) * 2] = x;
+          out[(j * Cout + c0 + q) * 2 + 1] = y;
+        } else {
+          out[j * Cout + c0 + q] = x;
+        }
+      }
+    }
+  }
+}
+
 static inline cudaError_t launch_detect_scrunch(const float2* in, float* out, long long rows,
                                                 long long Cout, int P, bool stokes, long long M,
                                                 long long F, cudaStream_t st) {
   const long long total = rows * Cout * (stokes ? 1 : P);
   if (total <= 0) return cudaSuccess;
+  constexpr int CELLS = 8;
+  if ((P == 1 || P == 2) && (F * P) % 64 == 0 && Cout % CELLS == 0 &&
+      (((uintptr_t)in) & 15) == 0) {
+    long long groups = rows * (Cout / CELLS);
+    long long blocks = (groups + 7) / 8;
+    if (blocks > 148ll * 8) blocks = 148ll * 8;
+    if (P == 1)
+      detect_scrunch_wide<1, CELLS><<<(unsigned)blocks, 256, 0, st>>>(
+          reinterpret_cast<const float4*>(in), out, rows, Cout, stokes ? 1 : 0, M, F);
+    else
+      detect_scrunch_wide<2, CELLS><<<(unsigned)blocks, 256, 0, st>>>(
+          reinterpret_cast<const float4*>(in), out, rows, Cout, stokes ? 1 : 0, M, F);
+    return cudaGetLastError();
+  }
   long long blocks = (total + 7) / 8;
   if (blocks > 148ll * 16) blocks = 148ll * 16;
   detect_scrunch_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, out, rows, Cout, P, stokes ? 1 : 0,

@@ -393,6 +393,18 @@ def test_detect_scrunch(stokes):
         want = p.reshape(12, 8, 8, 5, 2).sum(axis=(1, 3))
     assert got.shape == want.shape
     assert relerr(got, want) < 1e-6
+    # wide path: 64 fine channels per output, 16 outputs (P = 2) and a one-pol stream (P = 1)
+    x = crandn(rng, (24, 1024, 2))
+    got = kernels.detect(x, stokes=stokes, downsample=3, freq_sum=64)
+    p = np.abs(x.astype(np.complex128)) ** 2
+    want = (p.sum(axis=2).reshape(8, 3, 16, 64).sum(axis=(1, 3)) if stokes
+            else p.reshape(8, 3, 16, 64, 2).sum(axis=(1, 3)))
+    assert got.shape == want.shape and relerr(got, want) < 1e-6
+    if not stokes:
+        x1 = crandn(rng, (16, 2048))
+        got = kernels.detect(x1, freq_sum=128)
+        want = (np.abs(x1.astype(np.complex128)) ** 2).reshape(16, 16, 128).sum(axis=2)
+        assert got.shape == want.shape and relerr(got, want) < 1e-6
 
 
 def test_cfg4_channelize_detect_fold_pipeline():
