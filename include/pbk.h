@@ -40,7 +40,11 @@ enum pbk_status {
   PBK_ERR_NOMEM = -4
 };
 
-enum pbk_dtype { PBK_C64 = 0, PBK_I8X2 = 1 /* interleaved (re, im) int8 pairs */ };
+enum pbk_dtype {
+  PBK_C64 = 0,
+  PBK_I8X2 = 1, /* interleaved (re, im) int8 pairs */
+  PBK_F32 = 2   /* real float32 (imaginary part zero); ramp plans only */
+};
 
 enum pbk_out_kind {
   PBK_OUT_C64 = 0,       /* dedispersed voltages, complex64                              */
@@ -97,9 +101,18 @@ int pbk_dedisp_exec_device(pbk_plan* plan, const void* d_in, void* d_out, const 
  *   H_col[k] = 0 if lo_col <= fftshift_position(k) < hi_col, else exp(-2 pi i s_col fftfreq(N,1)[k])
  * in/out are (nsamp, ncols) complex64.  Execute with pbk_dedisp_exec_host / _device (chirp NULL).
  * zero_lo / zero_hi may be NULL (no zeroed band), shift_samples may be NULL (no ramp). */
+enum pbk_ramp_flags {
+  PBK_RAMP_HILBERT = 1,    /* multiply by the analytic-signal weights h = 1,2,..,2,1,0,..,0
+                              (utils.py:50-54 real_to_complex) */
+  PBK_RAMP_REAL_INPUT = 2  /* in is (nsamp, ncols) float32 */
+};
 int pbk_ramp_plan_create(int64_t nsamp, int64_t ncols, const double* shift_samples,
-                         const int64_t* zero_lo, const int64_t* zero_hi, int32_t device,
-                         pbk_plan** plan);
+                         const int64_t* zero_lo, const int64_t* zero_hi, int32_t flags,
+                         int32_t device, pbk_plan** plan);
+/* out[m, col] = (-1)^m in[2m, col]: the exp(-i pi n/2) mix + decimation by 2 that ends
+ * utils.py:56-61 real_to_complex; out is (ceil(nsamp/2), ncols) complex64 */
+int pbk_decimate2(const void* in, void* out, int64_t nsamp, int64_t ncols, int32_t on_device,
+                  int32_t device, void* stream);
 /* out[n, col] = in[n, col] * exp(+2 pi i cycles_per_sample[col] * n)   (transforms.py:346) */
 int pbk_mix(const void* in, void* out, int64_t nsamp, int64_t ncols,
             const double* cycles_per_sample, int32_t on_device, int32_t device, void* stream);

@@ -221,6 +221,29 @@ def freq_shift(x, ft):
     return scipy.fft.ifft(np.fft.ifftshift(X, axes=(0,)), axis=0)
 
 
+def real_to_complex(z, axis=0):
+    """utils.py:38-65: analytic signal (Hilbert mask), shift by -B/2, decimate by 2."""
+    z = np.asarray(z)
+    if np.iscomplexobj(z):
+        raise ValueError("Input must be real-valued.")
+    out_dtype = np.complex64 if z.dtype == np.float32 else np.complex128
+    N = z.shape[axis]
+    if N == 0:
+        return z.astype(out_dtype)
+    ind = [np.newaxis] * z.ndim
+    ind[axis] = slice(None)
+    h = np.zeros(N, dtype=out_dtype)
+    h[0] = 1
+    h[1:N // 2] = 2
+    if N > 1:
+        h[N // 2] = 2 if N % 2 else 1
+    z = scipy.fft.ifft(scipy.fft.fft(z, axis=axis) * h[tuple(ind)], axis=axis)
+    z = z * np.exp(-1j * np.pi / 2 * np.arange(N))[tuple(ind)]
+    dec = [slice(None)] * z.ndim
+    dec[axis] = slice(None, None, 2)
+    return z[tuple(dec)].astype(out_dtype)
+
+
 # ----------------------------------------------------------------------------------------
 # channelize / unchannelize                  reference: contrib/misc.py:17-93
 # ----------------------------------------------------------------------------------------

@@ -18,7 +18,7 @@ EXPORTS = [
     "pbk_dedisp_plan_create", "pbk_dedisp_out_shape", "pbk_dedisp_exec_host",
     "pbk_dedisp_exec_device", "pbk_fft_plan_create", "pbk_stft_plan_create",
     "pbk_fft_exec_host", "pbk_fft_exec_device", "pbk_detect", "pbk_detect_scrunch", "pbk_shift_channels", "pbk_downsample", "pbk_fold",
-    "pbk_stokes", "pbk_pol_basis", "pbk_chirp", "pbk_ramp_plan_create", "pbk_mix",
+    "pbk_stokes", "pbk_pol_basis", "pbk_chirp", "pbk_ramp_plan_create", "pbk_mix", "pbk_decimate2",
     "pbk_plan_destroy", "pbk_plan_info", "pbk_plan_describe", "pbk_plan_profile",
     "pbk_plan_profile_read", "pbk_plan_segments", "pbk_malloc", "pbk_free", "pbk_memcpy_h2d",
     "pbk_memcpy_d2h", "pbk_device_sync",
@@ -91,7 +91,8 @@ def lib():
         L.pbk_pol_basis.argtypes = [vp, vp, i64, i32, i32, i32, vp]
         L.pbk_chirp.argtypes = [i64, i64, dbl, dbl, dbl, ctypes.POINTER(dbl), vp, i32, i32, vp]
         L.pbk_ramp_plan_create.argtypes = [i64, i64, ctypes.POINTER(dbl), ctypes.POINTER(i64),
-                                           ctypes.POINTER(i64), i32, ctypes.POINTER(vp)]
+                                           ctypes.POINTER(i64), i32, i32, ctypes.POINTER(vp)]
+        L.pbk_decimate2.argtypes = [vp, vp, i64, i64, i32, i32, vp]
         L.pbk_mix.argtypes = [vp, vp, i64, i64, ctypes.POINTER(dbl), i32, i32, vp]
         L.pbk_plan_destroy.argtypes = [vp]
         L.pbk_plan_destroy.restype = None
@@ -233,7 +234,10 @@ class DedispPlan(Plan):
 class RampPlan(Plan):
     """ifft(fft(x) * H) with a per-column linear phase ramp and/or zeroed band (pbk_ramp_plan_create)."""
 
-    def __init__(self, nsamp, ncols, shift_samples=None, zero_lo=None, zero_hi=None, device=0):
+    HILBERT, REAL_INPUT = 1, 2
+
+    def __init__(self, nsamp, ncols, shift_samples=None, zero_lo=None, zero_hi=None, flags=0,
+                 device=0):
         def arr(a, dt):
             if a is None:
                 return None, None
@@ -246,7 +250,7 @@ class RampPlan(Plan):
                       arr(zero_hi, np.int64)]
         h = ctypes.c_void_p(0)
         check(lib().pbk_ramp_plan_create(nsamp, ncols, self._keep[0][1], self._keep[1][1],
-                                         self._keep[2][1], device, ctypes.byref(h)))
+                                         self._keep[2][1], int(flags), device, ctypes.byref(h)))
         super().__init__(h)
         self.nsamp, self.ncols = nsamp, ncols
 

@@ -440,6 +440,7 @@ struct RampSpec {   // linear-phase / band-zeroing transfer function per column 
   const double* shift_samples;
   const int64_t* zero_lo;
   const int64_t* zero_hi;
+  int flags;   // PBK_RAMP_HILBERT, PBK_RAMP_REAL_INPUT
 };
 
 static int dedisp_plan_create_impl(const pbk_dedisp_desc* d, const RampSpec* ramp, pbk_plan** out);
@@ -450,7 +451,7 @@ extern "C" int pbk_dedisp_plan_create(const pbk_dedisp_desc* d, pbk_plan** out) 
 
 extern "C" int pbk_ramp_plan_create(int64_t nsamp, int64_t ncols, const double* shift_samples,
                                     const int64_t* zero_lo, const int64_t* zero_hi,
-                                    int32_t device, pbk_plan** plan) {
+                                    int32_t flags, int32_t device, pbk_plan** plan) {
   if (!plan) return fail(PBK_ERR_INVALID, "plan is NULL");
   if (nsamp <= 0 || ncols <= 0) return fail(PBK_ERR_INVALID, "shape must be positive");
   std::vector<double> freqs((size_t)ncols, 1.0);
@@ -459,7 +460,7 @@ extern "C" int pbk_ramp_plan_create(int64_t nsamp, int64_t ncols, const double* 
   d.nsamp = nsamp;
   d.nchan = ncols;
   d.npol = 1;
-  d.in_dtype = PBK_C64;
+  d.in_dtype = (flags & PBK_RAMP_REAL_INPUT) ? PBK_F32 : PBK_C64;
   d.out_kind = PBK_OUT_C64;
   d.dm = 0.0;
   d.sample_rate_hz = 1.0;
@@ -469,7 +470,7 @@ extern "C" int pbk_ramp_plan_create(int64_t nsamp, int64_t ncols, const double* 
   d.crop_stop = nsamp;
   d.downsample = 1;
   d.device = device;
-  RampSpec r{shift_samples, zero_lo, zero_hi};
+  RampSpec r{shift_samples, zero_lo, zero_hi, flags};
   return dedisp_plan_create_impl(&d, &r, plan);
 }
 
@@ -480,7 +481,7 @@ static int dedisp_plan_create_impl(const pbk_dedisp_desc* d, const RampSpec* ram
     return fail(PBK_ERR_INVALID, "shape must be positive");
   if (!d->chan_freq_hz) return fail(PBK_ERR_INVALID, "chan_freq_hz is NULL");
   if (!(d->sample_rate_hz > 0)) return fail(PBK_ERR_INVALID, "sample_rate_hz must be > 0");
-  if (d->in_dtype != PBK_C64 && d->in_dtype != PBK_I8X2)
+  if (d->in_dtype != PBK_C64 && d->in_dtype != PBK_I8X2 && !(ramp && d->in_dtype == PBK_F32))
     return fail(PBK_ERR_INVALID, "unknown in_dtype %d", d->in_dtype);
   if (d->out_kind < PBK_OUT_C64 || d->out_kind > PBK_OUT_STOKES_I)
     return fail(PBK_ERR_INVALID, "unknown out_kind %d", d->out_kind);
@@ -525,7 +526,7 @@ static int dedisp_plan_create_impl(const pbk_dedisp_desc* d, const RampSpec* ram
   pl->out_rows = d->downsample > 1 ? crop_rows / d->downsample : crop_rows;
   pl->row_elems = d->out_kind == PBK_OUT_STOKES_I ? C : I;
   pl->elem_bytes = d->out_kind == PBK_OUT_C64 ? 8 : 4;
-  pl->in_bytes = (size_t)N * I * (d->in_dtype == PBK_C64 ? 8 : 2);
+  pl->in_bytes = (size_t)N * I * (d->in_dtype == PBK_C64 ? 8 : d->in_dtype == PBK_F32 ? 4 : 2);
   pl->out_bytes = (size_t)pl->out_rows * pl->row_elems * pl->elem_bytes;
   pl->chirp_bytes = d->explicit_chirp ? (size_t)N * C * 8 : 0;
 
@@ -567,7 +568,8 @@ static int dedisp_plan_create_impl(const pbk_dedisp_desc* d, const RampSpec* ram
     set_klow(ps.a, i + 1, l);
     ps.in_role = i == 0 ? ROLE_USER_IN : ROLE_SCRATCH;
     ps.out_role = ROLE_SCRATCH;
-    if (i == 0) ps.a.load_kind = d->in_dtype == PBK_I8X2 ? LOAD_I8X2 : LOAD_C64;
+    if (i == 0)
+      ps.a.load_kind = d->in_dtype == PBK_I8X2 ? LOAD_I8X2 : d->in_dtype == PBK_F32 ? LOAD_F32 : LOAD_C64;
     ps.fast = fast_ok;
     ts.ensure(l[i]);
     pl->passes.push_back(ps);
@@ -598,7 +600,7 @@ static int dedisp_plan_create_impl(const pbk_dedisp_desc* d, const RampSpec* ram
     ps.in_role = m == 1 ? ROLE_USER_IN : ROLE_SCRATCH;
     ps.out_role = ROLE_SCRATCH;
     if (m == 1) {
-      ps.a.load_kind = d->in_dtype == PBK_I8X2 ? LOAD_I8X2 : LOAD_C64;
+      ps.a.load_kind = d->in_dtype == PBK_I8X2 ? LOAD_I8X2 : d->in_dtype == PBK_F32 ? LOAD_F32 : LOAD_C64;
       final_epilogue(ps, 0);
     }
     ps.fast = fast_ok;
@@ -688,6 +690,7 @@ static int dedisp_plan_create_impl(const pbk_dedisp_desc* d, const RampSpec* ram
       return cleanup(fail(PBK_ERR_CUDA, "ramp upload: %s", cudaGetErrorString(e)));
   }
   for (auto& ps : pl->passes) {
+    ps.a.ramp_hilbert = (ramp && (ramp->flags & PBK_RAMP_HILBERT)) ? 1 : 0;
     ps.a.ramp_shift = pl->d_ramp_shift;
     ps.a.ramp_zero = pl->d_ramp_zero;
     ps.a.chan_freq = pl->d_chanfreq;
@@ -1344,6 +1347,19 @@ extern "C" int pbk_mix(const void* in, void* out, int64_t nsamp, int64_t ncols,
   if (rc == PBK_OK && on_device)
     CUDA_TRY(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));  // df is freed here
   return rc;
+}
+
+extern "C" int pbk_decimate2(const void* in, void* out, int64_t nsamp, int64_t ncols,
+                             int32_t on_device, int32_t device, void* stream) {
+  if (nsamp < 0 || ncols <= 0) return fail(PBK_ERR_INVALID, "bad shape");
+  const long long rows_out = (nsamp + 1) / 2;
+  return run_elementwise(in, out, (size_t)nsamp * ncols * 8, (size_t)rows_out * ncols * 8,
+                         on_device, device, stream, [&](const void* i, void* o, cudaStream_t st) {
+                           return launch_1d(decimate2_kernel, rows_out * ncols, st,
+                                            reinterpret_cast<const float2*>(i),
+                                            reinterpret_cast<float2*>(o), rows_out,
+                                            (long long)ncols);
+                         });
 }
 
 extern "C" int pbk_stokes(const void* in, void* out, int64_t npairs, int32_t circular,

@@ -33,7 +33,7 @@
 namespace pbk {
 
 enum { MODE_FWD = 0, MODE_MID = 1, MODE_INV = 2 };
-enum { LOAD_C64 = 0, LOAD_I8X2 = 1, LOAD_PLANAR = 2 };
+enum { LOAD_C64 = 0, LOAD_I8X2 = 1, LOAD_PLANAR = 2, LOAD_F32 = 3 /* real input, im = 0 */ };
 enum { EPI_C64 = 0, EPI_INTENSITY = 1, EPI_STOKES_I = 2 };
 enum { CHIRP_NONE = 0, CHIRP_COMPUTED = 1, CHIRP_ARRAY = 2, CHIRP_RAMP = 3 };
 
@@ -84,6 +84,7 @@ struct PassArgs {
   // CHIRP_RAMP: per column, H_k = exp(-2 pi i s k_signed / N) outside the zeroed band
   const double* ramp_shift;     // s / N per column (cycles per bin)
   const long long* ramp_zero;   // [lo, hi) per column in fftshift-ed bin order; lo >= hi = none
+  int ramp_hilbert;             // analytic-signal weights 1,2,..,2,1,0,..,0 (utils.py:50-54)
   long long tile0;    // fast kernels: first tile of this launch (tiles [tile0, ntiles) are processed)
 };
 
@@ -305,6 +306,13 @@ __device__ __forceinline__ c2 load_row(const PassArgs& p, const LaneCtx& L, long
       v.re = make_float2(a.x, b.x);
       v.im = make_float2(a.y, b.y);
     }
+  } else if (p.load_kind == LOAD_F32) {
+    const float* in = reinterpret_cast<const float*>(p.in);
+    float a = 0.f, b = 0.f;
+    if (L.valid[0]) a = __ldg(in + L.bin[0] + row * p.min.a_row);
+    if (L.valid[1]) b = __ldg(in + L.bin[1] + row * p.min.a_row);
+    v.re = make_float2(a, b);
+    v.im = make_float2(0.f, 0.f);
   } else if (p.load_kind == LOAD_C64) {
     const float2* in = reinterpret_cast<const float2*>(p.in);
     if (FAST) {
@@ -517,7 +525,10 @@ __device__ __forceinline__ void apply_chirp16(const PassArgs& p, const LaneCtx& 
         sincospif(2.0f * (float)fr, &s, &c);
         const long long sh = (kf + (p.N >> 1)) & (p.N - 1);   // position after fftshift
         const bool zero = sh >= p.ramp_zero[2 * col] && sh < p.ramp_zero[2 * col + 1];
-        h[l] = zero ? make_float2(0.f, 0.f) : make_float2(c * p.scale, -s * p.scale);
+        float wgt = p.scale;
+        if (p.ramp_hilbert)   // h[0] = 1, h[1 : N/2] = 2, h[N/2] = 1, rest 0 (N even)
+          wgt *= (kf == 0 || kf == (p.N >> 1)) ? 1.f : (kf < (p.N >> 1) ? 2.f : 0.f);
+        h[l] = zero ? make_float2(0.f, 0.f) : make_float2(c * wgt, -s * wgt);
       }
       v[m] = cmul(v[m], make_float2(h[0].x, h[1].x), make_float2(h[0].y, h[1].y));
     }

@@ -257,6 +257,20 @@ __global__ void __launch_bounds__(256) mix_kernel(const float2* __restrict__ in,
   }
 }
 
+// last step of real_to_complex (utils.py:56-61): multiply by exp(-i pi n / 2) and keep every
+// second sample; for n = 2m the factor is (-1)^m exactly.   out[m, :] = (-1)^m in[2m, :]
+__global__ void __launch_bounds__(256) decimate2_kernel(const float2* __restrict__ in,
+                                                        float2* __restrict__ out,
+                                                        long long rows_out, long long ncols) {
+  const long long total = rows_out * ncols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / ncols, col = i - m * ncols;
+    const float2 v = __ldg(in + 2 * m * ncols + col);
+    out[i] = (m & 1) ? make_float2(-v.x, -v.y) : v;
+  }
+}
+
 // full Stokes [I, Q, U, V] from (A, B) pol pairs (core.py:937-966, PSR/IEEE convention)
 //   linear:   I=AA+BB  Q=AA-BB  U=2Re(A*B)  V=2Im(A*B)
 //   circular: I=AA+BB  Q=2Re(A*B)  U=2Im(A*B)  V=AA-BB          (A*B = conj(A) B)

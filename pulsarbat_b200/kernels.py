@@ -18,7 +18,7 @@ import numpy as np
 from . import _lib as L
 from .device import DeviceArray
 
-__all__ = ["default_device", "dedisperse", "chirp", "detect", "shift_channels", "phase_ramp", "mix", "stokes", "pol_basis",
+__all__ = ["default_device", "dedisperse", "chirp", "detect", "shift_channels", "phase_ramp", "mix", "analytic_decimate", "stokes", "pol_basis",
            "downsample", "fft", "stft", "istft", "fold", "clear_plan_cache"]
 
 
@@ -275,6 +275,40 @@ def phase_ramp(data, shift_samples=None, zero_lo=None, zero_hi=None, device=None
     with ent.lock:
         ent.plan.exec_host(x, out)
     return out if odt == np.complex64 else out.astype(odt)
+
+
+def analytic_decimate(data, device=None):
+    """(nsamp, ncols) float32 -> (ceil(nsamp/2), ncols) complex64:
+    (-1)^m * ifft(fft(x) * h)[2m] with the analytic-signal mask h (utils.py:50-61)."""
+    shape = tuple(data.shape)
+    if len(shape) != 2:
+        raise ValueError("analytic_decimate takes (nsamp, ncols) data")
+    nsamp, ncols = shape
+    rows_out = (nsamp + 1) // 2
+    dev = data.device if _is_dev(data) else (default_device() if device is None else device)
+    key = ("hilbert", nsamp, ncols, dev)
+    ent = _get_plan(key, lambda: L.RampPlan(nsamp, ncols,
+                                            flags=L.RampPlan.HILBERT | L.RampPlan.REAL_INPUT,
+                                            device=dev))
+    if _is_dev(data):
+        x = data.contiguous()
+        if x.dtype != np.float32:
+            x = x.astype(np.float32)
+        tmp = DeviceArray.empty(shape, np.complex64, dev)
+        out = DeviceArray.empty((rows_out, ncols), np.complex64, dev)
+        st = _stream()
+        with ent.lock:
+            ent.plan.exec_device(x.ptr, tmp.ptr, st)
+        L.check(L.lib().pbk_decimate2(L.ptr(tmp.ptr), L.ptr(out.ptr), nsamp, ncols, 1, dev,
+                                      ctypes.c_void_p(st)))
+        return out
+    x = np.ascontiguousarray(data, dtype=np.float32)
+    tmp = np.empty(shape, np.complex64)
+    with ent.lock:
+        ent.plan.exec_host(x, tmp)
+    out = np.empty((rows_out, ncols), np.complex64)
+    L.check(L.lib().pbk_decimate2(L.ptr(tmp), L.ptr(out), nsamp, ncols, 0, dev, None))
+    return out
 
 
 def mix(data, cycles_per_sample, device=None):

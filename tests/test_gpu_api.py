@@ -165,3 +165,34 @@ def test_fold_with_polyco_predictor():
     want_p, want_c = orc.fold(x, coeffs, sr, nbin)
     assert np.array_equal(counts, want_c)
     assert relerr(prof, want_p) < 1e-5
+
+
+def test_real_to_complex_matches_reference_kats():
+    """reference utils.py:15-65 / tests/test_utils.py:20-68 on the GPU."""
+    import pulsarbat_b200 as pb
+    N = 512
+    t = np.linspace(0, 2 * np.pi, N, endpoint=False)
+    for w in [1, 2, 127, 128, 129, 254, 255]:
+        for p in [-np.pi, -np.pi / 2, 0, np.pi / 2]:
+            x = np.cos(w * t + p)
+            y = np.exp(1j * ((w - N / 4) * t[::2] + p))
+            z = pb.utils.real_to_complex(x)
+            assert z.dtype == np.complex128 and np.allclose(z, y, atol=2e-5)
+    ws = [1, 2, 3, 4]
+    t = np.linspace(0, 2 * np.pi, 128, endpoint=False)
+    x = np.stack([np.cos(w * t) for w in ws], axis=0)
+    y = np.stack([np.exp(1j * (w - 32) * t[::2]) for w in ws], axis=0)
+    assert np.allclose(pb.utils.real_to_complex(x, axis=1), y, atol=2e-5)
+    assert np.allclose(pb.utils.real_to_complex(x.T.copy(), axis=0), y.T, atol=2e-5)
+    rng = np.random.default_rng(12)
+    r = rng.standard_normal((2 ** 14, 3, 2)).astype(np.float32)
+    got = pb.utils.real_to_complex(r)
+    assert got.dtype == np.complex64 and got.shape == (2 ** 13, 3, 2)
+    assert relerr(got, orc.real_to_complex(r.astype(np.float64))) < 1e-5
+    gd = pb.utils.real_to_complex(pb.DeviceArray.from_numpy(r))
+    assert isinstance(gd, pb.DeviceArray) and np.array_equal(np.asarray(gd), got)
+    with pytest.raises(ValueError):
+        pb.utils.real_to_complex(np.ones((128, 4), dtype=complex))
+    e = np.zeros((0, 2))
+    assert np.array_equal(pb.utils.real_to_complex(e), e)
+    assert pb.utils.real_to_complex(np.ones(32, np.float32)).dtype == np.complex64

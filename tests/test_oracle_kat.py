@@ -321,3 +321,19 @@ def test_freq_shift_tones_and_zeroing():
             else:
                 s = int(np.ceil(s))
                 assert np.allclose(y[:s, i, j], 0) and np.allclose(y[s:, i, j], 1)
+
+
+def test_real_to_complex_theoretical():
+    """reference tests/test_utils.py:20-68: a real tone at w becomes a complex tone at w - N/4."""
+    for N in [511, 512]:
+        t = np.linspace(0, 2 * np.pi, N, endpoint=False)
+        for w in [1, 2, 127, 128, 129, 254, 255]:
+            for p in [-np.pi, -np.pi / 2, 0, np.pi / 2]:
+                x = np.cos(w * t + p)
+                y = np.exp(1j * ((w - (len(t) / 4)) * t[::2] + p))
+                assert np.allclose(orc.real_to_complex(x), y)
+    x = np.zeros((0, 2))
+    assert np.array_equal(orc.real_to_complex(x), x)
+    with pytest.raises(ValueError):
+        orc.real_to_complex(np.ones((8, 2), complex))
+    assert orc.real_to_complex(np.ones(32, np.float32)).dtype == np.complex64
