@@ -5,13 +5,18 @@
 // task needs one sincospif instead of seven.
 //
 // These kernels are specialised at compile time to the coherent-dedispersion passes: FWD =
-// forward level with its level twiddle (complex64 or int8 input), MID = fft * generated chirp *
-// ifft, INV = inverse level + epilogue.  Run-time switches around code that touches the 64-register
-// data array make the compiler copy the whole array at every merge point, so there are none.
+// forward level with its level twiddle (complex64, int8 or pair-planar scratch input), MID =
+// fft * generated chirp * ifft, INV = inverse level + epilogue (kind and crop handling are template
+// parameters).  Run-time switches around code that touches the 64-register data array make the
+// compiler copy the whole array at every merge point, so there are none.  The scratch array
+// between passes is pair-planar ({re0,re1,im0,im1} per lane pair = the packed register layout),
+// the per-tile address record is computed by one thread and broadcast through shared memory, and
+// the chirp is evaluated in FP64 without a division (see fast_chirp).
 // Preconditions checked by the host (pbk_api.cu: setup_fast): uniform lane pairs (I and P even,
-// pair adjacent and 16-byte aligned in both maps), a tile never straddles a row (I % W == 0),
-// no fftshift bookkeeping, forward sign, unit scale, generated chirp.  Everything else runs on
-// the generic kernel in pbk_fft.cuh, which is the same algorithm with runtime tile parameters.
+// pair adjacent and 16-byte aligned in both maps), a tile never straddles a row (I % W == 0,
+// W % P == 0), no fftshift bookkeeping, forward sign, unit scale, generated chirp with
+// |f - fc| <= fc/16.  Everything else runs on the generic kernel in pbk_fft.cuh, which is the
+// same algorithm with runtime tile parameters.
 #pragma once
 #include "pbk_fft.cuh"
 

@@ -12,7 +12,7 @@ import numpy as np
 from .. import _lib as L
 from .. import kernels
 from .. import units as u
-from ..core import BasebandSignal, IntensitySignal, RadioSignal, Signal
+from ..core import BasebandSignal, IntensitySignal, RadioSignal
 
 __all__ = ["DispersionMeasure", "DM", "coherent_dedispersion", "incoherent_dedispersion",
            "dedisperse_detect", "overlap_save_dedispersion"]
@@ -220,7 +220,3 @@ def overlap_save_dedispersion(z, DM, block_len, /, *, ref_freq=None):
         b += valid
     data = np.concatenate(pieces, axis=0)
     return _cropped_like(type(z), z, data, start)
-
-
-def _unused(_: Signal):  # keeps the import meaningful for type checkers
-    return None
