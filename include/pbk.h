@@ -35,7 +35,7 @@ typedef struct pbk_plan pbk_plan;
 enum pbk_status {
   PBK_OK = 0,
   PBK_ERR_INVALID = -1,     /* bad argument */
-  PBK_ERR_UNSUPPORTED = -2, /* valid request this build cannot run (e.g. non power-of-two nsamp) */
+  PBK_ERR_UNSUPPORTED = -2, /* valid request this build cannot run (e.g. a transform too long) */
   PBK_ERR_CUDA = -3,        /* CUDA runtime error / no device */
   PBK_ERR_NOMEM = -4
 };
@@ -70,7 +70,8 @@ int pbk_device_count(int* count);
  * consecutive samples, tail dropped; builder-defined; only for float outputs).
  */
 typedef struct pbk_dedisp_desc {
-  int64_t nsamp;              /* N: power of two, >= 16 */
+  int64_t nsamp;              /* N >= 2; powers of two >= 16 run on the tile-FFT passes, any other
+                                 length through Bluestein on top of them (pbk_blue.cuh) */
   int64_t nchan;              /* C */
   int64_t npol;               /* P */
   int32_t in_dtype;           /* pbk_dtype */
@@ -120,7 +121,8 @@ int pbk_mix(const void* in, void* out, int64_t nsamp, int64_t ncols,
 /* ---- axis-0 complex FFT --------------------------------------------------------------------
  * Replaces fft.py:30-48 `pb.fft.fft` / `pb.fft.ifft` with axis=0 for complex64 data (scipy
  * "backward" normalisation: forward unscaled, inverse 1/n), natural-order output.
- * Data is (outer, n, inner) complex64, transform along n.  n must be a power of two >= 2.
+ * Data is (outer, n, inner) complex64, transform along n; any n >= 2 (powers of two run on the
+ * tile-FFT passes directly, other lengths through Bluestein on top of them).
  */
 int pbk_fft_plan_create(int64_t outer, int64_t n, int64_t inner, int32_t inverse, int32_t device,
                         pbk_plan** plan);
@@ -130,8 +132,8 @@ int pbk_fft_plan_create(int64_t outer, int64_t n, int64_t inner, int32_t inverse
  *   forward:  in (nseg*nperseg, nchan, npol) -> out (nseg, nchan*nperseg, npol),
  *             out[s, c*n + ((k + n/2) mod n), p] = (1/n) sum_t in[s*n+t, c, p] e^{-2 pi i k t/n}
  *   inverse:  in (nseg, nchan_out*nperseg, npol) -> out (nseg*nperseg, nchan_out, npol)
- * nperseg must be a power of two >= 2 (other lengths: PBK_ERR_UNSUPPORTED).  The input is never
- * modified (the reference's istft scales its input in place, misc.py:82-83).
+ * Any nperseg >= 2 (the reference's tests use 33).  The input is never modified (the reference's
+ * istft scales its input in place, misc.py:82-83).
  */
 int pbk_stft_plan_create(int64_t nseg, int64_t nperseg, int64_t nchan, int64_t npol,
                          int32_t inverse, int32_t device, pbk_plan** plan);

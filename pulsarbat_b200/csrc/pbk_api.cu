@@ -22,6 +22,7 @@
 
 #include "../../include/pbk.h"
 #include "pbk_fast_launch.h"
+#include "pbk_blue.cuh"
 #include "pbk_fft.cuh"
 #include "pbk_misc.cuh"
 
@@ -88,8 +89,11 @@ struct Pass {
   size_t ftab_off = 0;  // float2 offset into plan->d_ftab
 };
 
+struct BlueState;   // arbitrary-length (Bluestein) plans, see below
+
 struct pbk_plan {
   int kind = PLAN_DEDISP;
+  BlueState* blue = nullptr;
   int device = 0;
   std::mutex mu;
   std::vector<Pass> passes;
@@ -422,6 +426,9 @@ static int upload_tables(pbk_plan* pl, TableSet& ts) {
 }
 
 static void setup_l2_blocking(pbk_plan* pl, long long block_bytes, int nblocks);
+static void blue_free(BlueState* b);
+static int blue_exec(pbk_plan* pl, const void* d_in, void* d_out, const void* d_chirp,
+                     cudaStream_t st);
 
 // scratch arrays are pair-planar ({re0,re1,im0,im1} per 16-byte lane pair) when the innermost
 // extent is even; every pass, generic or fast, reads and writes them through that layout
@@ -444,6 +451,25 @@ struct RampSpec {   // linear-phase / band-zeroing transfer function per column 
 };
 
 static int dedisp_plan_create_impl(const pbk_dedisp_desc* d, const RampSpec* ramp, pbk_plan** out);
+static int blue_dedisp_plan_create(const pbk_dedisp_desc* d, const RampSpec* ramp, pbk_plan** out);
+
+// per-column ramp description (shift / N, zeroed band) on the device, owned by the plan
+static int upload_ramp(pbk_plan* pl, const RampSpec* ramp, long long C, long long N) {
+  std::vector<double> sh((size_t)C);
+  std::vector<long long> zr((size_t)C * 2);
+  for (long long c = 0; c < C; ++c) {
+    sh[c] = (ramp->shift_samples ? ramp->shift_samples[c] : 0.0) / (double)N;
+    zr[2 * c] = ramp->zero_lo ? ramp->zero_lo[c] : 0;
+    zr[2 * c + 1] = ramp->zero_hi ? ramp->zero_hi[c] : 0;
+  }
+  CUDA_TRY(cudaMalloc(&pl->d_ramp_shift, sh.size() * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&pl->d_ramp_zero, zr.size() * sizeof(long long)));
+  CUDA_TRY(cudaMemcpy(pl->d_ramp_shift, sh.data(), sh.size() * sizeof(double),
+                      cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(pl->d_ramp_zero, zr.data(), zr.size() * sizeof(long long),
+                      cudaMemcpyHostToDevice));
+  return PBK_OK;
+}
 
 extern "C" int pbk_dedisp_plan_create(const pbk_dedisp_desc* d, pbk_plan** out) {
   return dedisp_plan_create_impl(d, nullptr, out);
@@ -494,10 +520,12 @@ static int dedisp_plan_create_impl(const pbk_dedisp_desc* d, const RampSpec* ram
     return fail(PBK_ERR_INVALID, "crop [%lld, %lld) outside [0, %lld]", (long long)d->crop_start,
                 (long long)d->crop_stop, (long long)d->nsamp);
   const int n = ilog2_exact(d->nsamp);
-  if (n < 4)
-    return fail(PBK_ERR_UNSUPPORTED,
-                "nsamp = %lld: this build handles power-of-two lengths >= 16 only",
-                (long long)d->nsamp);
+  if (n < 4) {
+    // not a power of two (or shorter than 16): Bluestein on top of the power-of-two passes
+    if (d->nsamp < 2)
+      return fail(PBK_ERR_UNSUPPORTED, "nsamp = %lld is too short", (long long)d->nsamp);
+    return blue_dedisp_plan_create(d, ramp, out);
+  }
   int l[3] = {0, 0, 0};
   const long long I = d->nchan * d->npol;
   const int m = choose_levels(n, I, l, true);
@@ -671,24 +699,7 @@ static int dedisp_plan_create_impl(const pbk_dedisp_desc* d, const RampSpec* ram
     if (e != cudaSuccess)
       return cleanup(fail(PBK_ERR_CUDA, "chan_const upload: %s", cudaGetErrorString(e)));
   }
-  if (ramp) {
-    std::vector<double> sh((size_t)C);
-    std::vector<long long> zr((size_t)C * 2);
-    for (long long c = 0; c < C; ++c) {
-      sh[c] = (ramp->shift_samples ? ramp->shift_samples[c] : 0.0) / (double)N;
-      zr[2 * c] = ramp->zero_lo ? ramp->zero_lo[c] : 0;
-      zr[2 * c + 1] = ramp->zero_hi ? ramp->zero_hi[c] : 0;
-    }
-    cudaError_t e = cudaMalloc(&pl->d_ramp_shift, sh.size() * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&pl->d_ramp_zero, zr.size() * sizeof(long long));
-    if (e == cudaSuccess)
-      e = cudaMemcpy(pl->d_ramp_shift, sh.data(), sh.size() * sizeof(double), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess)
-      e = cudaMemcpy(pl->d_ramp_zero, zr.data(), zr.size() * sizeof(long long),
-                     cudaMemcpyHostToDevice);
-    if (e != cudaSuccess)
-      return cleanup(fail(PBK_ERR_CUDA, "ramp upload: %s", cudaGetErrorString(e)));
-  }
+  if (ramp && (rc = upload_ramp(pl, ramp, C, N)) != PBK_OK) return cleanup(rc);
   for (auto& ps : pl->passes) {
     ps.a.ramp_hilbert = (ramp && (ramp->flags & PBK_RAMP_HILBERT)) ? 1 : 0;
     ps.a.ramp_shift = pl->d_ramp_shift;
@@ -815,6 +826,7 @@ extern "C" int pbk_dedisp_exec_device(pbk_plan* pl, const void* d_in, void* d_ou
   if (!d_out) return fail(PBK_ERR_INVALID, "output pointer is NULL");
   CUDA_TRY(cudaSetDevice(pl->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (pl->blue) return blue_exec(pl, d_in, d_out, d_chirp, st);
   int rc = run_passes(pl, d_in, d_out, d_chirp, st);
   if (rc != PBK_OK) return rc;
   if (pl->desc.downsample > 1) {
@@ -862,16 +874,21 @@ extern "C" int pbk_dedisp_exec_host(pbk_plan* pl, const void* in, void* out, con
 struct ExtMap {  // external array addressing: o*eo + idx*ei + c*ec + p*ep
   long long eo, ei, ec, ep;
 };
+static int blue_fft_plan_create(long long O, long long n, long long C, long long P, bool inverse,
+                                ExtMap in, ExtMap outm, float scale, bool shift_out, bool shift_in,
+                                int device, pbk_plan** out);
 
 static int build_fft_plan(long long O, long long n, long long C, long long P, bool inverse,
                           ExtMap in, ExtMap outm, float scale, bool shift_out, bool shift_in,
                           int device, pbk_plan** out) {
   *out = nullptr;
   const int ln = ilog2_exact(n);
-  if (ln < 1)
-    return fail(PBK_ERR_UNSUPPORTED,
-                "transform length %lld: this build handles power-of-two lengths >= 2 only",
-                (long long)n);
+  if (ln < 1) {
+    if (n < 2) return fail(PBK_ERR_UNSUPPORTED, "transform length %lld is too short", (long long)n);
+    // not a power of two: Bluestein on top of the power-of-two passes (pbk_blue.cuh)
+    return blue_fft_plan_create(O, n, C, P, inverse, in, outm, scale, shift_out, shift_in, device,
+                                out);
+  }
   int l[3] = {0, 0, 0};
   const int m = choose_levels(ln, C * P, l, false);
   if (m == 0) return fail(PBK_ERR_UNSUPPORTED, "transform length 2^%d is too long", ln);
@@ -951,6 +968,221 @@ static int build_fft_plan(long long O, long long n, long long C, long long P, bo
   return PBK_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// arbitrary transform lengths (Bluestein, kernels in pbk_blue.cuh)
+// ------------------------------------------------------------------------------------------
+struct BlueState {
+  long long O = 1, n = 0, M = 0, I = 1;
+  int P = 1;
+  pbk_plan* fwdM = nullptr;   // (O, M, I) forward FFT, out of place
+  pbk_plan* invM = nullptr;   // (O, M, I) inverse FFT with the 1/M scale
+  float2 *w = nullptr, *bhat = nullptr, *A = nullptr, *B = nullptr, *T = nullptr;
+  bool dedisp = false, inverse = false;
+  BlueIO in{}, out{};
+  PassArgs chirp{};           // dedispersion: chirp description for blue_midH_kernel
+  int out_kind = PBK_OUT_C64;
+  long long crop_rows = 0, downsample = 1;
+};
+
+static long long blue_pad_len(long long n) {
+  long long M = 16;
+  while (M < 2 * n - 1) M <<= 1;
+  return M;
+}
+
+template <typename K, typename... A>
+static cudaError_t launch_grid(K kern, long long total, cudaStream_t st, A... args) {
+  if (total <= 0) return cudaSuccess;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148ll * 16) blocks = 148ll * 16;
+  kern<<<(unsigned)blocks, 256, 0, st>>>(args...);
+  return cudaGetLastError();
+}
+
+static void blue_free(BlueState* b) {
+  if (!b) return;
+  pbk_plan_destroy(b->fwdM);
+  pbk_plan_destroy(b->invM);
+  cudaFree(b->w);
+  cudaFree(b->bhat);
+  cudaFree(b->A);
+  cudaFree(b->B);
+  cudaFree(b->T);
+  delete b;
+}
+
+// common part: chirp table, filter spectrum, the two M-point FFT plans and the work buffers
+static int blue_setup(BlueState* b, int device) {
+  b->M = blue_pad_len(b->n);
+  if (b->M > (1ll << 30)) return fail(PBK_ERR_UNSUPPORTED, "transform length %lld is too long", b->n);
+  const ExtMap em{b->M * b->I, b->I, 1, 0};
+  int rc = build_fft_plan(b->O, b->M, b->I, 1, false, em, em, 1.0f, false, false, device, &b->fwdM);
+  if (rc != PBK_OK) return rc;
+  rc = build_fft_plan(b->O, b->M, b->I, 1, true, em, em, (float)(1.0 / (double)b->M), false, false,
+                      device, &b->invM);
+  if (rc != PBK_OK) return rc;
+  const size_t work = (size_t)b->O * b->M * b->I * sizeof(float2);
+  CUDA_TRY(cudaMalloc(&b->w, (size_t)b->n * sizeof(float2)));
+  CUDA_TRY(cudaMalloc(&b->bhat, (size_t)b->M * sizeof(float2)));
+  CUDA_TRY(cudaMalloc(&b->A, work));
+  CUDA_TRY(cudaMalloc(&b->B, work));
+  cudaError_t e = launch_grid(blue_chirp_kernel, b->n, 0, b->w, b->n);
+  if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "chirp table: %s", cudaGetErrorString(e));
+  // spectrum of the filter: one M-point column FFT at plan time
+  float2* filt = nullptr;
+  CUDA_TRY(cudaMalloc(&filt, (size_t)b->M * sizeof(float2)));
+  e = launch_grid(blue_filter_kernel, b->M, 0, (const float2*)b->w, filt, b->n, b->M);
+  pbk_plan* one = nullptr;
+  const ExtMap e1{b->M, 1, 1, 0};
+  rc = e == cudaSuccess ? build_fft_plan(1, b->M, 1, 1, false, e1, e1, 1.0f, false, false, device, &one)
+                        : fail(PBK_ERR_CUDA, "filter: %s", cudaGetErrorString(e));
+  if (rc == PBK_OK) rc = run_passes(one, filt, b->bhat, nullptr, 0);
+  if (rc == PBK_OK && cudaDeviceSynchronize() != cudaSuccess)
+    rc = fail(PBK_ERR_CUDA, "filter spectrum: %s", cudaGetErrorString(cudaGetLastError()));
+  pbk_plan_destroy(one);
+  cudaFree(filt);
+  return rc;
+}
+
+// forward or inverse DFT of length n through two M-point FFTs: in -> A -> B -> A -> out
+static int blue_convolve(BlueState* b, bool conj, cudaStream_t st) {
+  int rc = run_passes(b->fwdM, b->A, b->B, nullptr, st);
+  if (rc != PBK_OK) return rc;
+  cudaError_t e = launch_grid(blue_mul_kernel, b->O * b->M * b->I, st, b->B, (const float2*)b->bhat,
+                              b->O, b->M, b->I, conj ? 1 : 0);
+  if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "bluestein multiply: %s", cudaGetErrorString(e));
+  return run_passes(b->invM, b->B, b->A, nullptr, st);
+}
+
+static int blue_exec(pbk_plan* pl, const void* d_in, void* d_out, const void* d_chirp,
+                     cudaStream_t st) {
+  BlueState* b = pl->blue;
+  const long long total = b->O * b->M * b->I;
+  cudaError_t e = launch_grid(blue_pre_kernel, total, st, d_in, b->A, (const float2*)b->w, b->in);
+  if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "bluestein pre: %s", cudaGetErrorString(e));
+  int rc = blue_convolve(b, b->in.conj_w != 0, st);
+  if (rc != PBK_OK) return rc;
+  if (b->dedisp) {
+    PassArgs ch = b->chirp;
+    ch.chirp_arr = reinterpret_cast<const float2*>(d_chirp);
+    e = launch_grid(blue_midH_kernel, b->M * b->I, st, b->A, b->n, b->M, b->I, b->P, ch);
+    if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "bluestein chirp: %s", cudaGetErrorString(e));
+    if ((rc = blue_convolve(b, true, st)) != PBK_OK) return rc;
+  }
+  float2* dst = reinterpret_cast<float2*>(b->out_kind == PBK_OUT_C64 ? d_out : (void*)b->T);
+  const long long rows = b->out.hi - b->out.lo;
+  e = launch_grid(blue_post_kernel, b->O * rows * b->I, st, (const float2*)b->A, dst,
+                  (const float2*)b->w, b->out);
+  if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "bluestein post: %s", cudaGetErrorString(e));
+  if (b->out_kind != PBK_OUT_C64) {
+    e = launch_detect(b->T, reinterpret_cast<float*>(d_out), pl->out_rows, b->I,
+                      b->out_kind == PBK_OUT_STOKES_I, b->downsample, st);
+    if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "detect launch: %s", cudaGetErrorString(e));
+  }
+  return PBK_OK;
+}
+
+// coherent dedispersion of a length that is not a power of two
+static int blue_dedisp_plan_create(const pbk_dedisp_desc* d, const RampSpec* ramp,
+                                   pbk_plan** out) {
+  const long long N = d->nsamp, C = d->nchan, I = d->nchan * d->npol;
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (d->device < 0 || d->device >= ndev)
+    return fail(PBK_ERR_CUDA, "device %d not available (%d CUDA devices)", d->device, ndev);
+  CUDA_TRY(cudaSetDevice(d->device));
+  pbk_plan* pl = new pbk_plan();
+  BlueState* b = new BlueState();
+  pl->blue = b;
+  pl->kind = PLAN_DEDISP;
+  pl->device = d->device;
+  pl->desc = *d;
+  pl->desc.chan_freq_hz = nullptr;
+  b->O = 1; b->n = N; b->I = I; b->P = (int)d->npol;
+  b->dedisp = true;
+  b->out_kind = d->out_kind;
+  b->downsample = d->downsample;
+  const long long crop_rows = std::max<long long>(0, d->crop_stop - d->crop_start);
+  b->crop_rows = crop_rows;
+  pl->full_rows = crop_rows;
+  pl->out_rows = d->downsample > 1 ? crop_rows / d->downsample : crop_rows;
+  pl->row_elems = d->out_kind == PBK_OUT_STOKES_I ? C : I;
+  pl->elem_bytes = d->out_kind == PBK_OUT_C64 ? 8 : 4;
+  pl->in_bytes = (size_t)N * I * (d->in_dtype == PBK_C64 ? 8 : d->in_dtype == PBK_F32 ? 4 : 2);
+  pl->out_bytes = (size_t)pl->out_rows * pl->row_elems * pl->elem_bytes;
+  pl->chirp_bytes = d->explicit_chirp ? (size_t)N * C * 8 : 0;
+  auto cleanup = [&](int code) { pbk_plan_destroy(pl); return code; };
+  int rc = blue_setup(b, d->device);
+  if (rc != PBK_OK) return cleanup(rc);
+  b->in = BlueIO{BlueMap{0, I, d->npol, 1}, 1, N, b->M, I, (int)d->npol,
+                 d->in_dtype == PBK_I8X2 ? LOAD_I8X2 : d->in_dtype == PBK_F32 ? LOAD_F32 : LOAD_C64,
+                 0, 0, 1.0f, 0, N};
+  b->out = BlueIO{BlueMap{0, I, d->npol, 1}, 1, N, b->M, I, (int)d->npol, EPI_C64, 1, 0,
+                  (float)(1.0 / (double)N), d->crop_start, std::max(d->crop_start, d->crop_stop)};
+  defaults(b->chirp);
+  b->chirp.chirp_kind = ramp ? CHIRP_RAMP : d->explicit_chirp ? CHIRP_ARRAY : CHIRP_COMPUTED;
+  b->chirp.N = N;
+  if (ramp) {
+    if ((rc = upload_ramp(pl, ramp, C, N)) != PBK_OK) return cleanup(rc);
+    b->chirp.ramp_shift = pl->d_ramp_shift;
+    b->chirp.ramp_zero = pl->d_ramp_zero;
+    b->chirp.ramp_hilbert = (ramp->flags & PBK_RAMP_HILBERT) ? 1 : 0;
+  }
+  b->chirp.df = 1.0 / ((double)N * (1.0 / d->sample_rate_hz));
+  if (std::isinf(d->ref_freq_hz)) { b->chirp.fr_sub = 0; b->chirp.inv_fr = 0; b->chirp.a0 = -1.0; }
+  else { b->chirp.fr_sub = d->ref_freq_hz; b->chirp.inv_fr = 1.0 / d->ref_freq_hz; b->chirp.a0 = 0; }
+  b->chirp.D = (1.0 / 2.41e-4) * d->dm * 1e12;
+  b->chirp.scale = 1.0f;
+  b->chirp.chirp_sk = C;
+  b->chirp.chirp_sc = 1;
+  {
+    cudaError_t e = cudaMalloc(&pl->d_chanfreq, (size_t)C * sizeof(double));
+    if (e == cudaSuccess)
+      e = cudaMemcpy(pl->d_chanfreq, d->chan_freq_hz, (size_t)C * sizeof(double),
+                     cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && d->out_kind != PBK_OUT_C64 && crop_rows > 0)
+      e = cudaMalloc(&b->T, (size_t)crop_rows * I * sizeof(float2));
+    if (e != cudaSuccess) return cleanup(fail(PBK_ERR_CUDA, "alloc: %s", cudaGetErrorString(e)));
+  }
+  b->chirp.chan_freq = pl->d_chanfreq;
+  pl->launches = 5 + 2 * (b->fwdM->launches + b->invM->launches) +
+                 (d->out_kind != PBK_OUT_C64 ? 1 : 0);
+  pl->segments = 0;
+  *out = pl;
+  return PBK_OK;
+}
+
+// plain / STFT transform of a length that is not a power of two
+static int blue_fft_plan_create(long long O, long long n, long long C, long long P, bool inverse,
+                                ExtMap in, ExtMap outm, float scale, bool shift_out, bool shift_in,
+                                int device, pbk_plan** out) {
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev)
+    return fail(PBK_ERR_CUDA, "device %d not available (%d CUDA devices)", device, ndev);
+  CUDA_TRY(cudaSetDevice(device));
+  pbk_plan* pl = new pbk_plan();
+  BlueState* b = new BlueState();
+  pl->blue = b;
+  pl->kind = PLAN_FFT;
+  pl->device = device;
+  b->O = O; b->n = n; b->I = C * P; b->P = (int)P;
+  b->inverse = inverse;
+  pl->in_bytes = (size_t)O * n * C * P * 8;
+  pl->out_bytes = pl->in_bytes;
+  int rc = blue_setup(b, device);
+  if (rc != PBK_OK) { pbk_plan_destroy(pl); return rc; }
+  b->in = BlueIO{BlueMap{in.eo, in.ei, in.ec, in.ep}, O, n, b->M, C * P, (int)P, LOAD_C64,
+                 inverse ? 1 : 0, shift_in ? n / 2 : 0, 1.0f, 0, n};
+  b->out = BlueIO{BlueMap{outm.eo, outm.ei, outm.ec, outm.ep}, O, n, b->M, C * P, (int)P, EPI_C64,
+                  inverse ? 1 : 0, shift_out ? n / 2 : 0, scale, 0, n};
+  pl->launches = 3 + b->fwdM->launches + b->invM->launches;
+  pl->segments = 0;
+  *out = pl;
+  return PBK_OK;
+}
+
 extern "C" int pbk_fft_plan_create(int64_t outer, int64_t n, int64_t inner, int32_t inverse,
                                    int32_t device, pbk_plan** plan) {
   if (!plan) return fail(PBK_ERR_INVALID, "plan is NULL");
@@ -984,9 +1216,10 @@ extern "C" int pbk_stft_plan_create(int64_t nseg, int64_t nperseg, int64_t nchan
 extern "C" int pbk_fft_exec_device(pbk_plan* pl, const void* d_in, void* d_out, void* stream) {
   if (!pl || pl->kind != PLAN_FFT) return fail(PBK_ERR_INVALID, "not an FFT plan");
   if (!d_in || !d_out) return fail(PBK_ERR_INVALID, "NULL data pointer");
+  CUDA_TRY(cudaSetDevice(pl->device));
+  if (pl->blue) return blue_exec(pl, d_in, d_out, nullptr, reinterpret_cast<cudaStream_t>(stream));
   if (d_in == d_out && pl->passes.size() == 1)
     return fail(PBK_ERR_INVALID, "single-pass transforms cannot run in place");
-  CUDA_TRY(cudaSetDevice(pl->device));
   return run_passes(pl, d_in, d_out, nullptr, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -1046,6 +1279,7 @@ extern "C" void pbk_plan_destroy(pbk_plan* pl) {
   if (!pl) return;
   cudaSetDevice(pl->device);
   prof_free(pl);
+  blue_free(pl->blue);
   cudaFree(pl->scratch);
   cudaFree(pl->d_tw);
   cudaFree(pl->d_ftab);
@@ -1075,6 +1309,11 @@ extern "C" int pbk_plan_describe(const pbk_plan* pl, char* buf, size_t n) {
   if (!pl || !buf || n == 0) return fail(PBK_ERR_INVALID, "NULL argument");
   size_t off = 0;
   buf[0] = 0;
+  if (pl->blue) {
+    snprintf(buf, n, "BLUESTEIN:n=%lld:M=2^%d:lanes=%lld", pl->blue->n, ilog2_exact(pl->blue->M),
+             pl->blue->I);
+    return PBK_OK;
+  }
   for (size_t i = 0; i < pl->passes.size() && off + 1 < n; ++i) {
     const Pass& ps = pl->passes[i];
     const char* mode = ps.mode == MODE_FWD ? "FWD" : ps.mode == MODE_MID ? "MID" : "INV";

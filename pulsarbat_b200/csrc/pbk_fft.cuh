@@ -469,7 +469,8 @@ __device__ __forceinline__ void apply_level_tw(const PassArgs& p, const LaneCtx&
 // reference: transforms/dedispersion.py:19-23 (f = f_chan + fftfreq; phase = coeff*f*(1/ref-1/f)^2)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float2 chirp_value(const PassArgs& p, double fchan, long long kfull) {
-  const long long ks = (kfull >= (p.N >> 1)) ? kfull - p.N : kfull;
+  // numpy fftfreq: indices >= ceil(N/2) are the negative frequencies (dedispersion.py:20)
+  const long long ks = (kfull >= ((p.N + 1) >> 1)) ? kfull - p.N : kfull;
   const double f = fma((double)ks, p.df, fchan);
   const double a = fma(f - p.fr_sub, p.inv_fr, p.a0);   // (f - fr)/fr   (or -1 for fr = inf)
   const double phi = (p.D * a) * a / f;                 // cycles
@@ -477,6 +478,29 @@ __device__ __forceinline__ float2 chirp_value(const PassArgs& p, double fchan, l
   float s, c;
   sincospif(2.0f * (float)fr, &s, &c);
   return make_float2(c * p.scale, -s * p.scale);
+}
+
+// CHIRP_RAMP transfer function for column `col` at FFT bin kf of an N-point transform (any N):
+// exp(-2 pi i s fftfreq(N,1)[kf]) (transforms.py:271), zero inside the band [lo, hi) given in
+// fftshift-ed positions (transforms.py:350-359), optional analytic-signal weights (utils.py:50-54)
+__device__ __forceinline__ float2 ramp_value(const PassArgs& p, int col, long long kf) {
+  const long long ks = (kf >= ((p.N + 1) >> 1)) ? kf - p.N : kf;
+  const double ph = (double)ks * p.ramp_shift[col];
+  const double fr = ph - rint(ph);
+  float s, c;
+  sincospif(2.0f * (float)fr, &s, &c);
+  long long sh = kf + (p.N >> 1);               // position after fftshift
+  if (sh >= p.N) sh -= p.N;
+  if (sh >= p.ramp_zero[2 * col] && sh < p.ramp_zero[2 * col + 1]) return make_float2(0.f, 0.f);
+  float wgt = p.scale;
+  if (p.ramp_hilbert) {   // h[0] = 1, h[1 : N//2] = 2, h[N//2] = 2 if N odd else 1, rest 0
+    const long long h2 = p.N >> 1;
+    if (kf == 0) wgt *= 1.f;
+    else if (kf < h2) wgt *= 2.f;
+    else if (kf == h2) wgt *= (p.N & 1) ? 2.f : 1.f;
+    else wgt = 0.f;
+  }
+  return make_float2(c * wgt, -s * wgt);
 }
 
 template <bool FAST>
@@ -517,18 +541,7 @@ __device__ __forceinline__ void apply_chirp16(const PassArgs& p, const LaneCtx& 
       for (int l = 0; l < 2; ++l) {
         const long long kf = (long long)(l == 0 ? L.klow : (FAST ? L.klow : L.klow1)) +
                              ((long long)k << p.log2Kmul);
-        const long long ks = (kf >= (p.N >> 1)) ? kf - p.N : kf;
-        const int col = L.col[l];
-        const double ph = (double)ks * p.ramp_shift[col];
-        const double fr = ph - rint(ph);
-        float s, c;
-        sincospif(2.0f * (float)fr, &s, &c);
-        const long long sh = (kf + (p.N >> 1)) & (p.N - 1);   // position after fftshift
-        const bool zero = sh >= p.ramp_zero[2 * col] && sh < p.ramp_zero[2 * col + 1];
-        float wgt = p.scale;
-        if (p.ramp_hilbert)   // h[0] = 1, h[1 : N/2] = 2, h[N/2] = 1, rest 0 (N even)
-          wgt *= (kf == 0 || kf == (p.N >> 1)) ? 1.f : (kf < (p.N >> 1) ? 2.f : 0.f);
-        h[l] = zero ? make_float2(0.f, 0.f) : make_float2(c * wgt, -s * wgt);
+        h[l] = ramp_value(p, L.col[l], kf);
       }
       v[m] = cmul(v[m], make_float2(h[0].x, h[1].x), make_float2(h[0].y, h[1].y));
     }

@@ -2,8 +2,9 @@
 
 The reference forwards every name in ``_FFT_FUNCS`` to ``scipy.fft``.  Only ``fft`` and ``ifft``
 are on the baseband hot path (dedispersion.py:125, misc.py:47,87); those two run on the GPU for
-numpy arrays and device arrays and raise ``PbkUnsupported`` for what the kernels cannot do
-(non power-of-two lengths, ``n=`` padding, ``norm`` other than "backward").  The other twelve
+numpy arrays and device arrays (any length: powers of two on the tile-FFT passes, other lengths
+through Bluestein on top of them) and raise ``PbkUnsupported`` for what the kernels do not do
+(``n=`` padding, ``norm`` other than "backward").  The other twelve
 names are outside the accelerated path and are not provided: asking for them raises
 AttributeError naming ``scipy.fft`` as the place to get them, rather than silently running on
 the CPU under this package's name.

@@ -119,8 +119,8 @@ def coherent_dedispersion(z, DM, /, *, ref_freq=None, chirp=None):
 
     Returns ``type(z)`` cropped at both ends by the dispersion sweep; raises ``TypeError`` for
     non-baseband input.  With ``chirp=`` the given array multiplies the spectrum instead of the
-    generated chirp (dedispersion.py:121-124).  Lengths other than powers of two raise
-    ``PbkUnsupported`` -- there is no CPU fallback.
+    generated chirp (dedispersion.py:121-124).  Any length works (powers of two are the fast
+    path); there is no CPU fallback.
     """
     if not isinstance(z, BasebandSignal):
         raise TypeError("Signal must be a BasebandSignal object.")

@@ -196,3 +196,34 @@ def test_real_to_complex_matches_reference_kats():
     e = np.zeros((0, 2))
     assert np.array_equal(pb.utils.real_to_complex(e), e)
     assert pb.utils.real_to_complex(np.ones(32, np.float32)).dtype == np.complex64
+
+
+def test_shifts_and_real_to_complex_any_length():
+    """The reference's own odd-length cases: freq_shift at N = 1023 (tests/test_transforms.py:398),
+    real_to_complex at N = 511 (tests/test_utils.py:29), time_shift at a non power of two."""
+    import pulsarbat_b200 as pb
+    u = pb.units
+    N = 1023
+    n = np.arange(N) / N
+    fs = np.array([[-52, -45.4], [-25.5, 34], [14, -36.9], [45.1, 27]])
+    tones = np.exp(2j * np.pi * fs[None] * n[:, None, None]).astype(np.complex64)
+    x = pb.BasebandSignal(tones, sample_rate=N * u.Hz, center_freq=1e6 * u.Hz)
+    assert np.allclose(np.asarray(pb.freq_shift(x, -fs * u.Hz).data), 1, atol=3e-5)
+    rng = np.random.default_rng(7)
+    z = crandn(rng, (N, 4, 2))
+    zs = pb.BasebandSignal(z, sample_rate=N * u.Hz, center_freq=1e6 * u.Hz)
+    for shift in [49.0, np.array([5.0, -6.0, 300.25, -8.0])]:
+        want = orc.freq_shift(z.astype(np.complex128), np.asarray(shift) / N)
+        assert relerr(np.asarray(pb.freq_shift(zs, shift * u.Hz).data), want) < 1e-5
+    zt = crandn(rng, (4095, 3))
+    st = pb.Signal(zt, sample_rate=1e3 * u.Hz)
+    for shift in [7, -3.5, np.array([1.25, -20.0, 11.0])]:
+        want, a, b = orc.time_shift(zt.astype(np.complex128), shift)
+        got = pb.time_shift(st, shift)
+        assert relerr(np.asarray(got.data), want) < 1e-5
+        assert np.array_equal(np.asarray(got.data) == 0, want == 0)
+    t = np.linspace(0, 2 * np.pi, 511, endpoint=False)
+    for w in [1, 2, 127, 128, 129, 254, 255]:
+        for p in [-np.pi, 0, np.pi / 2]:
+            y = np.exp(1j * ((w - 511 / 4) * t[::2] + p))
+            assert np.allclose(pb.utils.real_to_complex(np.cos(w * t + p)), y, atol=3e-5)

@@ -63,10 +63,71 @@ def test_fft_large_two_level():
     assert relerr(y, ref) < 2e-6
 
 
-def test_fft_rejects_non_pow2():
+# ------------------------------------------------------------------------------ any length
+@pytest.mark.parametrize("n", [3, 5, 7, 33, 100, 1000, 1023, 4233, 3 * 2 ** 14])
+@pytest.mark.parametrize("inner", [1, 2, 6])
+def test_fft_any_length(n, inner):
+    """Lengths that are not powers of two go through Bluestein on the power-of-two passes (the
+    reference accepts any length: scipy.fft, fft.py:34)."""
     L = _lib()
-    with pytest.raises(L.PbkUnsupported):
-        L.FFTPlan(1, 33, 2)
+    rng = np.random.default_rng(n + inner)
+    outer = 2 if n < 5000 else 1
+    x = crandn(rng, (outer, n, inner))
+    for inverse in (False, True):
+        plan = L.FFTPlan(outer, n, inner, inverse=inverse)
+        assert "BLUESTEIN" in plan.describe()
+        y = plan.exec_host(x, np.empty_like(x))
+        ref = (scipy.fft.ifft if inverse else scipy.fft.fft)(x.astype(np.complex128), axis=1)
+        assert relerr(y, ref) < 3e-6, (n, inner, inverse)
+        plan.destroy()
+
+
+@pytest.mark.parametrize("shape, nperseg", [((4224, 4, 2), 33), ((4233, 3, 2), 33),
+                                            ((4224, 4, 2), 4224), ((4233, 3, 2), 4233),
+                                            ((6000, 2, 1), 100)])
+def test_stft_istft_any_length(shape, nperseg):
+    """reference tests/test_contrib.py:22-41 shapes: odd and non power-of-two nperseg."""
+    import pulsarbat_b200 as pb
+    u = pb.units
+    rng = np.random.default_rng(shape[0] + nperseg)
+    x = np.exp(1j * rng.uniform(-np.pi, np.pi, shape)).astype(np.complex64)
+    z = pb.BasebandSignal(x, sample_rate=1 * u.Hz, center_freq=1e3 * u.Hz)
+    y = pb.contrib.stft(z, nperseg=nperseg)
+    nseg = shape[0] // nperseg
+    assert y.shape == (nseg, shape[1] * nperseg) + shape[2:]
+    assert y.freq_align == ("center" if nperseg % 2 else "bottom")
+    want = orc.stft(x.astype(np.complex128), nperseg)
+    assert relerr(np.asarray(y.data), want) < 3e-6
+    back = pb.contrib.istft(y, nperseg=nperseg)
+    assert back.shape == (nseg * nperseg,) + shape[1:]
+    assert relerr(np.asarray(back.data), x[: nseg * nperseg]) < 5e-6
+    assert np.allclose(back.channel_freqs_hz, z.channel_freqs_hz)
+
+
+@pytest.mark.parametrize("N, C, P", [(12000, 3, 2), (4233, 2, 1), (3 * 2 ** 15, 4, 2), (8191, 1, 1)])
+def test_dedisp_any_length(N, C, P):
+    """Coherent dedispersion of lengths that are not powers of two, through the public API, with
+    the reference's crop; also the fused Stokes-I / time-sum output."""
+    import pulsarbat_b200 as pb
+    u = pb.units
+    rng = np.random.default_rng(N)
+    sr, fcen, dm = 1e6, 600e6, 0.05
+    x = crandn(rng, (N, C, P) if P > 1 else (N, C))
+    cls = pb.DualPolarizationSignal if P == 2 else pb.BasebandSignal
+    kw = dict(sample_rate=sr * u.Hz, center_freq=fcen * u.Hz, start_time=pb.Time(58000.0))
+    if P == 2:
+        kw["pol_type"] = "linear"
+    z = cls(x, **kw)
+    y = pb.coherent_dedispersion(z, pb.DM(dm))
+    want, s0, s1 = orc.coherent_dedispersion(x.astype(np.complex128), dm, sample_rate=sr,
+                                             center_freq=fcen)
+    assert y.shape == want.shape and s1 > s0
+    assert relerr(np.asarray(y.data), want) < 1e-5
+    assert y.start_time.isclose(z.start_time + s0 / (sr * u.Hz))
+    if P == 2:
+        i4 = pb.dedisperse_detect(z, pb.DM(dm), stokes_I=True, downsample=4)
+        wi = orc.downsample(orc.stokes_I(want), 4)
+        assert relerr(np.asarray(i4.data), wi) < 1e-5
 
 
 # ------------------------------------------------------------------------------ stft / istft
