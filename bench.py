@@ -46,8 +46,12 @@ WORKLOADS = {
     "cfg2_c64": dict(N=2 ** 22, C=64, P=2, dm=100.0, sr=6.25e6, fcen=600e6, stokes=None, ds=1,
                      int8=False, text="cfg2 geometry, complex64 voltages out"),
     "cfg3_shard": dict(N=2 ** 22, C=128, P=2, dm=100.0, sr=390625.0, fcen=600e6, stokes=None,
-                       ds=1, int8=True,
+                       ds=1, int8=True, Call=1024,
                        text="one GPU's shard of cfg3: int8 complex 2^22 x 128 chan x 2 pol -> c64"),
+    "cfg5_shard": dict(N=2 ** 26, C=32, P=2, dm=1000.0, sr=400e6 / 256, fcen=600e6, stokes=False,
+                       ds=1, int8=False, Call=256,
+                       text="one GPU's shard of cfg5: 2^26 x 32 chan (of 256) x 2 pol c64, DM=1000, "
+                            "per-pol intensity out"),
     "cfg1": dict(N=2 ** 20, C=1, P=1, dm=71.0, sr=16e6, fcen=400e6, stokes=None, ds=1, int8=False,
                  text="BasebandSignal 2^20 x 1 chan c64, 400 MHz, 16 MHz, DM=71"),
     "small": dict(N=2 ** 16, C=16, P=2, dm=3.0, sr=6.25e6, fcen=600e6, stokes=True, ds=64,
@@ -64,8 +68,10 @@ def peaks():
 
 
 def chan_freqs(w):
-    """Channel centre frequencies, freq_align='center' (reference core.py:569-574)."""
-    return w["fcen"] + w["sr"] * (np.arange(w["C"]) + 0.5 - w["C"] / 2)
+    """Channel centre frequencies, freq_align='center' (reference core.py:569-574); a shard of a
+    wider band (``Call`` channels in total) takes the lowest ``C`` of them."""
+    call = w.get("Call", w["C"])
+    return (w["fcen"] + w["sr"] * (np.arange(call) + 0.5 - call / 2))[: w["C"]]
 
 
 # ------------------------------------------------------------------------------------------
@@ -257,7 +263,9 @@ def run_b200(args, w):
     if w["int8"]:
         x = torch.randint(-127, 128, (N, C, P, 2), device=dev, dtype=torch.int8, generator=g)
     else:
-        x = torch.randn((N, C, P, 2), device=dev, dtype=torch.float32, generator=g)
+        x = torch.empty((N, C, P, 2), device=dev, dtype=torch.float32)
+        for i in range(0, N, 2 ** 22):
+            x[i:i + 2 ** 22].normal_(generator=g)
     in_bytes = x.numel() * x.element_size()
     out_bytes = plan.out_rows * plan.row_elems * plan.elem_bytes
     out = torch.empty(max(out_bytes, 16), device=dev, dtype=torch.uint8)
@@ -334,7 +342,29 @@ def run_b200(args, w):
     del x
     torch.cuda.empty_cache()
     e2e = None
-    if not args.no_e2e and not w["int8"]:
+    if not args.no_e2e and w["int8"]:
+        hx = torch.empty((N, C, P, 2), dtype=torch.int8, pin_memory=True)
+        hx.random_(-127, 128, generator=torch.Generator().manual_seed(8 + rank))
+        hraw = hx.numpy()
+
+        def call8():
+            return pb.kernels.dedisperse(hraw, dm=w["dm"], sample_rate_hz=w["sr"],
+                                         chan_freq_hz=freqs, ref_freq_hz=w["fcen"], crop=None,
+                                         int8=True)
+        ke = max(1, min(K, args.e2e_steps))
+        r = call8()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            r = call8()
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": world * nsamp * ke / dt / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": int(hraw.nbytes), "d2h_bytes_per_step": int(r.nbytes),
+               "steps": ke, "ms_per_step": dt / ke * 1e3,
+               "api": "pulsarbat_b200.kernels.dedisperse(int8 numpy, pinned)"}
+        del hx, hraw, r
+    elif not args.no_e2e and N * C * P <= 2 ** 30:
         hx = torch.empty((N, C, P, 2), dtype=torch.float32, pin_memory=True)
         hx.normal_(generator=torch.Generator().manual_seed(8 + rank))
         hnp = hx.numpy().view(np.complex64).reshape(N, C, P)
@@ -365,10 +395,34 @@ def run_b200(args, w):
         dt = max_over_ranks(time.perf_counter() - t0)
         rbytes = int(np.asarray(r.data if hasattr(r, "data") and not isinstance(r, np.ndarray)
                                 else r).nbytes)
-        e2e = {"value": world * nsamp * ke / dt / 1e9, "unit": UNIT,
+        single = {"value": world * nsamp * ke / dt / 1e9, "ms_per_step": dt / ke * 1e3,
+                  "api": "pulsarbat_b200.dedisperse_detect(DualPolarizationSignal(numpy, pinned))"
+                         " -- one synchronous call per block"}
+        # the same blocks as a stream: H2D of block i+1 overlaps the kernels of block i
+        out_kind_s = L.OUT_C64 if w["stokes"] is None else (L.OUT_STOKES_I if w["stokes"] else
+                                                            L.OUT_INTENSITY)
+
+        def stream(nblk):
+            tot = 0.0
+            for y in pb.streaming.dedisperse_blocks(
+                    (hnp for _ in range(nblk)), dm=w["dm"], sample_rate_hz=w["sr"],
+                    chan_freq_hz=freqs, ref_freq_hz=w["fcen"], crop=None, out_kind=out_kind_s,
+                    downsample=w["ds"], device=local, pinned_out=True):
+                tot += float(y.ravel()[0])          # the result of every block is read on the host
+            return tot
+        stream(2)
+        barrier()
+        t0 = time.perf_counter()
+        stream(ke)
+        torch.cuda.synchronize()
+        dts = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": world * nsamp * ke / dts / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": int(hnp.nbytes), "d2h_bytes_per_step": rbytes,
-               "steps": ke, "ms_per_step": dt / ke * 1e3,
-               "api": "pulsarbat_b200.dedisperse_detect(DualPolarizationSignal(numpy, pinned))"}
+               "steps": ke, "ms_per_step": dts / ke * 1e3,
+               "api": "pulsarbat_b200.streaming.dedisperse_blocks(pinned numpy blocks): H2D of "
+                      "block i+1 overlaps the kernels of block i; plan creation inside the timed "
+                      "region",
+               "single_call": single}
         del hx, hnp, z
 
     # ---- CPU baseline (rank 0, single-GPU run only) --------------------------------------
@@ -411,7 +465,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

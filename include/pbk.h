@@ -219,6 +219,10 @@ int pbk_malloc(void** dptr, size_t bytes, int32_t device);
 int pbk_free(void* dptr, int32_t device);
 int pbk_memcpy_h2d(void* dst, const void* src, size_t bytes, int32_t device);
 int pbk_memcpy_d2h(void* dst, const void* src, size_t bytes, int32_t device);
+/* cudaMemcpyAsync on `stream` (to_device != 0: host -> device, else device -> host); truly
+ * asynchronous only for pinned host memory */
+int pbk_memcpy_async(void* dst, const void* src, size_t bytes, int32_t to_device, int32_t device,
+                     void* stream);
 int pbk_device_sync(int32_t device);
 
 #ifdef __cplusplus

@@ -17,11 +17,11 @@ from . import transforms
 from .transforms import *  # noqa: F401,F403
 from . import pulsar
 from .pulsar import *  # noqa: F401,F403
-from . import contrib, fft, kernels, sharding, utils  # noqa: F401
+from . import contrib, fft, kernels, sharding, streaming, utils  # noqa: F401
 from .device import DeviceArray  # noqa: F401
 
 __version__ = "0.1.0"
 
-__all__ = ["fft", "contrib", "kernels", "sharding", "utils", "units", "Time", "DeviceArray", "PbkError",
+__all__ = ["fft", "contrib", "kernels", "sharding", "streaming", "utils", "units", "Time", "DeviceArray", "PbkError",
            "PbkUnsupported"]
 __all__ += core.__all__ + transforms.__all__ + pulsar.__all__

@@ -21,7 +21,7 @@ EXPORTS = [
     "pbk_stokes", "pbk_pol_basis", "pbk_chirp", "pbk_ramp_plan_create", "pbk_mix", "pbk_decimate2",
     "pbk_plan_destroy", "pbk_plan_info", "pbk_plan_describe", "pbk_plan_profile",
     "pbk_plan_profile_read", "pbk_plan_segments", "pbk_malloc", "pbk_free", "pbk_memcpy_h2d",
-    "pbk_memcpy_d2h", "pbk_device_sync",
+    "pbk_memcpy_d2h", "pbk_memcpy_async", "pbk_device_sync",
 ]
 
 
@@ -106,6 +106,7 @@ def lib():
         L.pbk_free.argtypes = [vp, i32]
         L.pbk_memcpy_h2d.argtypes = [vp, vp, ctypes.c_size_t, i32]
         L.pbk_memcpy_d2h.argtypes = [vp, vp, ctypes.c_size_t, i32]
+        L.pbk_memcpy_async.argtypes = [vp, vp, ctypes.c_size_t, i32, i32, vp]
         L.pbk_device_sync.argtypes = [i32]
         _lib = L
     return _lib

@@ -1691,6 +1691,13 @@ extern "C" int pbk_memcpy_d2h(void* dst, const void* src, size_t bytes, int32_t 
   CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
   return PBK_OK;
 }
+extern "C" int pbk_memcpy_async(void* dst, const void* src, size_t bytes, int32_t to_device,
+                                int32_t device, void* stream) {
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost,
+                           reinterpret_cast<cudaStream_t>(stream)));
+  return PBK_OK;
+}
 extern "C" int pbk_device_sync(int32_t device) {
   CUDA_TRY(cudaSetDevice(device));
   CUDA_TRY(cudaDeviceSynchronize());

@@ -1,0 +1,108 @@
+"""Block streams: overlap the host->device copy of block i+1 with the kernels of block i.
+
+The reference processes a long observation as a sequence of blocks (dask chunks along channels,
+or overlap-save blocks along time); each block goes host -> GPU -> host.
+A single synchronous call cannot hide the PCIe copy behind the kernels, so this module runs the
+same plan over an iterator of blocks with two device input buffers, a copy stream and a compute
+stream (CUDA events between them).  The arithmetic is exactly that of ``kernels.dedisperse``.
+"""
+
+import numpy as np
+
+from . import _lib as L
+from . import kernels
+
+__all__ = ["dedisperse_blocks"]
+
+
+def dedisperse_blocks(blocks, *, dm, sample_rate_hz, chan_freq_hz, ref_freq_hz, crop=None,
+                      out_kind=L.OUT_C64, downsample=1, int8=False, device=None, pinned_out=False):
+    """Generator: dedisperse every block of ``blocks`` (numpy arrays of one common shape, ideally
+    in pinned memory) and yield the results in order as numpy arrays.
+
+    Equivalent to ``[kernels.dedisperse(b, ...) for b in blocks]``; the copy of the next block
+    overlaps the kernels of the current one.  With ``pinned_out=True`` each result is a view of
+    one of two alternating pinned host buffers and is only valid until the next item is requested
+    (no extra host copy); by default a fresh array is returned.
+    """
+    import torch
+    dev = kernels.default_device() if device is None else device
+    tdev = torch.device(f"cuda:{dev}")
+    it = iter(blocks)
+    try:
+        first = next(it)
+    except StopIteration:
+        return
+    first = np.ascontiguousarray(first, dtype=np.int8 if int8 else np.complex64)
+    shape = first.shape
+    body = shape[:-1] if int8 else shape
+    nsamp, nchan = body[0], body[1]
+    trailing = body[2:]
+    npol = int(np.prod(trailing)) if trailing else 1
+    start, stop = (0, nsamp) if crop is None else (int(crop[0]), int(crop[1]))
+    if stop <= start:
+        start, stop = 0, 0
+    freqs = np.ascontiguousarray(chan_freq_hz, dtype=np.float64)
+    plan = L.DedispPlan(nsamp=nsamp, nchan=nchan, npol=npol, dm=dm, sample_rate_hz=sample_rate_hz,
+                        ref_freq_hz=ref_freq_hz, chan_freq_hz=freqs, crop=(start, stop),
+                        in_dtype=L.PBK_I8X2 if int8 else L.PBK_C64, out_kind=out_kind,
+                        downsample=downsample, device=dev)
+    out_trailing = (nchan,) if out_kind == L.OUT_STOKES_I else (nchan,) + tuple(trailing)
+    out_shape = (plan.out_rows,) + out_trailing
+    out_t = torch.complex64 if out_kind == L.OUT_C64 else torch.float32
+    in_t = torch.int8 if int8 else torch.complex64
+    try:
+        with torch.cuda.device(tdev):
+            d_in = [torch.empty(shape, dtype=in_t, device=tdev) for _ in range(2)]
+            d_out = [torch.empty(out_shape, dtype=out_t, device=tdev) for _ in range(2)]
+            h_out = [torch.empty(out_shape, dtype=out_t, pin_memory=True) for _ in range(2)]
+            s_copy, s_comp = torch.cuda.Stream(tdev), torch.cuda.Stream(tdev)
+            copied = [torch.cuda.Event() for _ in range(2)]
+            consumed = [torch.cuda.Event() for _ in range(2)]    # kernels done reading d_in[i]
+            done = [torch.cuda.Event() for _ in range(2)]        # result i is in h_out[i]
+
+            def upload(block, slot, reuse):
+                hb = np.ascontiguousarray(block, dtype=first.dtype)
+                if hb.shape != shape:
+                    raise ValueError(f"block shape {hb.shape} differs from the first {shape}")
+                if reuse:
+                    s_copy.wait_event(consumed[slot])
+                # cudaMemcpyAsync straight from the caller's (ideally pinned) memory
+                L.check(L.lib().pbk_memcpy_async(d_in[slot].data_ptr(), hb.ctypes.data, hb.nbytes,
+                                                 1, dev, s_copy.cuda_stream))
+                copied[slot].record(s_copy)
+                return hb                                       # keep the host block alive
+
+            def compute(slot):
+                with torch.cuda.stream(s_comp):
+                    s_comp.wait_event(copied[slot])
+                    plan.exec_device(d_in[slot].data_ptr(), d_out[slot].data_ptr(), None,
+                                     s_comp.cuda_stream)
+                    consumed[slot].record(s_comp)
+                    L.check(L.lib().pbk_memcpy_async(h_out[slot].data_ptr(), d_out[slot].data_ptr(),
+                                                     h_out[slot].numel() * h_out[slot].element_size(),
+                                                     0, dev, s_comp.cuda_stream))
+                    done[slot].record(s_comp)
+
+            keep = [None, None]
+            keep[0] = upload(first, 0, False)
+            i = 0
+            nxt = next(it, None)
+            while True:
+                slot = i & 1
+                if nxt is not None:
+                    keep[slot ^ 1] = upload(nxt, slot ^ 1, i >= 1)
+                compute(slot)
+                if i >= 1:
+                    done[slot ^ 1].synchronize()
+                    r = h_out[slot ^ 1].numpy()
+                    yield r if pinned_out else r.copy()
+                if nxt is None:
+                    done[slot].synchronize()
+                    r = h_out[slot].numpy()
+                    yield r if pinned_out else r.copy()
+                    break
+                i += 1
+                nxt = next(it, None)
+    finally:
+        plan.destroy()

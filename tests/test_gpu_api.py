@@ -227,3 +227,27 @@ def test_shifts_and_real_to_complex_any_length():
         for p in [-np.pi, 0, np.pi / 2]:
             y = np.exp(1j * ((w - 511 / 4) * t[::2] + p))
             assert np.allclose(pb.utils.real_to_complex(np.cos(w * t + p)), y, atol=3e-5)
+
+
+def test_block_stream_matches_single_calls():
+    """streaming.dedisperse_blocks (copy of block i+1 overlapped with the kernels of block i)
+    returns exactly what kernels.dedisperse returns block by block."""
+    import pulsarbat_b200 as pb
+    from pulsarbat_b200 import _lib as L
+    rng = np.random.default_rng(11)
+    N, C = 2 ** 14, 16
+    sr, fcen, dm = 1e6, 600e6, 0.3
+    freqs = orc.channel_freqs(fcen, sr, C)
+    blocks = [crandn(rng, (N, C, 2)) for _ in range(5)]
+    for kind, ds in [(L.OUT_C64, 1), (L.OUT_STOKES_I, 4)]:
+        kw = dict(dm=dm, sample_rate_hz=sr, chan_freq_hz=freqs, ref_freq_hz=fcen,
+                  crop=(100, N - 300), out_kind=kind, downsample=ds)
+        got = list(pb.streaming.dedisperse_blocks(iter(blocks), **kw))
+        assert len(got) == 5
+        for b, g in zip(blocks, got):
+            assert np.array_equal(g, np.asarray(pb.kernels.dedisperse(b, **kw)))
+    assert list(pb.streaming.dedisperse_blocks(iter([]), dm=dm, sample_rate_hz=sr,
+                                               chan_freq_hz=freqs, ref_freq_hz=fcen)) == []
+    one = list(pb.streaming.dedisperse_blocks([blocks[0]], dm=dm, sample_rate_hz=sr,
+                                              chan_freq_hz=freqs, ref_freq_hz=fcen))
+    assert len(one) == 1 and one[0].shape == (N, C, 2)

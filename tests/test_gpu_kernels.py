@@ -584,3 +584,67 @@ def test_freq_shift_matches_oracle_and_reference_kats():
             pb.freq_shift(zs, np.ones(bad_shape) * u.Hz)
     for good_shape in [(), (1,), (1, 1), (4,), (4, 2), (1, 2)]:
         pb.freq_shift(zs, np.ones(good_shape) * u.Hz)
+
+
+# ------------------------------------------------------------------------------ full-size cfg5 shard
+def test_cfg5_shard_2pow26_device_resident():
+    """BASELINE configs[4] (DM = 1000, 2^26-sample per-channel FFTs, 256 channels x 2 pol over
+    400-800 MHz) -- one GPU's shard of 32 channels at FULL length, generated and kept on the
+    device (34 GB in, 34 GB scratch, 34 GB out): Parseval per column, two sampled columns against
+    the float64 oracle (phase up to 1.15e9 cycles, 26-bit twiddle indices), and the fused
+    per-pol intensity with the reference's global crop."""
+    import torch
+    L = _lib()
+    free, _ = torch.cuda.mem_get_info()
+    if free < 125 * 2 ** 30:
+        pytest.skip("needs ~120 GB of free device memory")
+    N, Call, C, P = 2 ** 26, 256, 32, 2
+    sr, fcen, dm = 400e6 / Call, 600e6, 1000.0
+    freqs_all = orc.channel_freqs(fcen, sr, Call)
+    freqs = freqs_all[:C]                                  # lowest 32 channels: largest phases
+    start, stop = orc.crop_range(dm, N, fcen, sr, Call, fcen)
+    assert (start, stop) == (7879135, 44597049)            # SURVEY 8d
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev)
+    g.manual_seed(23)
+    x = torch.empty((N, C, P, 2), device=dev, dtype=torch.float32)
+    for i in range(0, N, 2 ** 22):                          # chunked: no 34 GB temporaries
+        x[i:i + 2 ** 22].normal_(generator=g)
+    y = torch.empty_like(x)
+    st = torch.cuda.current_stream().cuda_stream
+    plan = L.DedispPlan(nsamp=N, nchan=C, npol=P, dm=dm, sample_rate_hz=sr, ref_freq_hz=fcen,
+                        chan_freq_hz=freqs, crop=(0, N))
+    assert "fast-r16" in plan.describe()
+    plan.exec_device(x.data_ptr(), y.data_ptr(), None, st)
+    torch.cuda.synchronize()
+    plan.destroy()
+
+    def col_power(t):
+        acc = torch.zeros((C, P), device=dev, dtype=torch.float64)
+        for i in range(0, N, 2 ** 22):
+            acc += (t[i:i + 2 ** 22].double() ** 2).sum(dim=(0, 3))
+        return acc
+    assert torch.allclose(col_power(x), col_power(y), rtol=1e-5)
+    for c in (0, C - 1):
+        xc = x[:, c, 0].cpu().numpy().view(np.complex64).reshape(N)
+        yc = y[:, c, 0].cpu().numpy().view(np.complex64).reshape(N)
+        chirp = orc.transfer_function(dm, N, sr, freqs[c], fcen)
+        want = scipy.fft.ifft(scipy.fft.fft(xc.astype(np.complex128)) * chirp)
+        assert relerr(yc, want) < 1e-5, c
+        del xc, yc, chirp, want
+    # fused per-pol intensity with the global crop of the whole 256-channel band
+    rows = stop - start
+    out = torch.empty((rows, C, P), device=dev, dtype=torch.float32)
+    plan = L.DedispPlan(nsamp=N, nchan=C, npol=P, dm=dm, sample_rate_hz=sr, ref_freq_hz=fcen,
+                        chan_freq_hz=freqs, crop=(start, stop), out_kind=1)
+    plan.exec_device(x.data_ptr(), out.data_ptr(), None, st)
+    torch.cuda.synchronize()
+    plan.destroy()
+    num = torch.zeros((), device=dev, dtype=torch.float64)
+    den = torch.zeros((), device=dev, dtype=torch.float64)
+    for i in range(0, rows, 2 ** 22):
+        ref = (y[start + i:start + i + 2 ** 22].double() ** 2).sum(dim=3)[: rows - i]
+        d = out[i:i + 2 ** 22].double() - ref
+        num += (d ** 2).sum()
+        den += (ref ** 2).sum()
+    assert float(torch.sqrt(num / den)) < 1e-5
