@@ -69,6 +69,7 @@ CFGS = {
     "cfg2": dict(N=2 ** 22, C=64, P=2, dm=100.0, sr=6.25e6, fcen=600e6, out_kind=2,
                  downsample=64),
     "cfg3_1gpu": dict(N=2 ** 22, C=128, P=2, dm=100.0, sr=390625.0, fcen=600e6, in_dtype=1),
+    "cfg5_shard": dict(N=2 ** 26, C=32, P=2, dm=1000.0, sr=400e6 / 256, fcen=410e6, out_kind=1),
     "n12": dict(N=2 ** 12, C=4096, P=2, dm=1.0, sr=1e6, fcen=1e9),
     "n16": dict(N=2 ** 16, C=1024, P=2, dm=1.0, sr=1e6, fcen=1e9),
 }
