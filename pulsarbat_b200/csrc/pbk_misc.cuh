@@ -342,46 +342,167 @@ __device__ __forceinline__ int fold_bin(const FoldArgs& a, long long n) {
   return (int)(b % a.nbin);
 }
 
-constexpr int kFoldRows = 32;  // time samples per CTA
+// ---- wide rows (row_elems >= 32): one CTA owns SPAN consecutive samples x up to 256 elements.
+// Bins of a chunk of 64 samples are computed once into shared memory; every thread walks its
+// element down the chunk (coalesced row segments, 8 loads in flight) and keeps the running sum of
+// the current bin in a register, so a global float atomic is issued only when the bin changes
+// (every ~200 samples for a slow pulsar) instead of once per sample.  Counts go through a
+// per-CTA shared-memory histogram that is flushed once.
+constexpr int kFoldChunk = 64;
 
-// One CTA folds kFoldRows consecutive samples: their bins are computed once into shared memory,
-// then threads sweep the row elements (coalesced) and add into profile[bin] with float atomics.
-// Consecutive samples usually fall in the same or adjacent bins, so runs are summed in registers
-// before each atomic.
-__global__ void __launch_bounds__(256) fold_kernel(const __grid_constant__ FoldArgs a) {
-  __shared__ int sbin[kFoldRows];
-  const long long nb = (long long)blockIdx.x * kFoldRows;
-  const int nrows = (int)min((long long)kFoldRows, a.nsamp - nb);
-  if (threadIdx.x < nrows) {
-    const int b = fold_bin(a, nb + threadIdx.x);
-    sbin[threadIdx.x] = b;
-    if (a.bins_out) a.bins_out[nb + threadIdx.x] = b;
-    if (blockIdx.y == 0) atomicAdd(a.counts + b, 1ull);
-  }
-  __syncthreads();
+__global__ void __launch_bounds__(256) fold_wide_kernel(const __grid_constant__ FoldArgs a,
+                                                        int span, int smem_counts) {
+  extern __shared__ int fsm[];
+  int* sbin = fsm;                  // [2][kFoldChunk]
+  int* scnt = fsm + 2 * kFoldChunk; // [nbin] (only CTAs with blockIdx.y == 0 use it)
+  const long long nb = (long long)blockIdx.x * span;
+  const int nrows = (int)min((long long)span, a.nsamp - nb);
+  const bool counting = blockIdx.y == 0;
+  if (counting && smem_counts)
+    for (int i = threadIdx.x; i < a.nbin; i += blockDim.x) scnt[i] = 0;
   const long long e = (long long)blockIdx.y * blockDim.x + threadIdx.x;
-  if (e >= a.row_elems) return;
-  const float* src = a.in + nb * a.row_elems + e;
-  int cur = sbin[0];
+  const bool live = e < a.row_elems;
+  const float* src = a.in + nb * a.row_elems + (live ? e : 0);
+  int cur = -1;
   float acc = 0.f;
-  for (int r = 0; r < nrows; ++r) {
-    const int b = sbin[r];
-    if (b != cur) {
-      atomicAdd(a.profile + (long long)cur * a.row_elems + e, acc);
-      acc = 0.f;
-      cur = b;
+  __syncthreads();
+  for (int c0 = 0, buf = 0; c0 < nrows; c0 += kFoldChunk, buf ^= 1) {
+    const int nr = min(kFoldChunk, nrows - c0);
+    int* sb = sbin + buf * kFoldChunk;
+    for (int t = threadIdx.x; t < nr; t += blockDim.x) {
+      const int b = fold_bin(a, nb + c0 + t);
+      sb[t] = b;
+      if (counting) {
+        if (a.bins_out) a.bins_out[nb + c0 + t] = b;
+        if (smem_counts) atomicAdd(scnt + b, 1);
+        else atomicAdd(a.counts + b, 1ull);     // histogram too large for shared memory
+      }
     }
-    acc += __ldg(src + (long long)r * a.row_elems);
+    __syncthreads();   // one barrier per chunk: the bins are double-buffered
+    if (live) {
+      const float* p = src + (long long)c0 * a.row_elems;
+      int r = 0;
+      for (; r + 8 <= nr; r += 8) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __ldg(p + (long long)(r + i) * a.row_elems);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int b = sb[r + i];
+          if (b != cur) {
+            if (cur >= 0) atomicAdd(a.profile + (long long)cur * a.row_elems + e, acc);
+            acc = 0.f;
+            cur = b;
+          }
+          acc += v[i];
+        }
+      }
+      for (; r < nr; ++r) {
+        const int b = sb[r];
+        if (b != cur) {
+          if (cur >= 0) atomicAdd(a.profile + (long long)cur * a.row_elems + e, acc);
+          acc = 0.f;
+          cur = b;
+        }
+        acc += __ldg(p + (long long)r * a.row_elems);
+      }
+    }
   }
-  atomicAdd(a.profile + (long long)cur * a.row_elems + e, acc);
+  if (live && cur >= 0) atomicAdd(a.profile + (long long)cur * a.row_elems + e, acc);
+  __syncthreads();
+  if (counting && smem_counts)
+    for (int i = threadIdx.x; i < a.nbin; i += blockDim.x)
+      if (scnt[i]) atomicAdd(a.counts + i, (unsigned long long)scnt[i]);
+}
+
+// ---- narrow rows (row_elems <= 32 and nbin * row_elems floats fit in shared memory): per-CTA
+// shared-memory histogram.  A CTA owns SPAN samples, reads them fully coalesced (consecutive
+// floats = several samples x all elements), pre-reduces a warp in registers when all its samples
+// share one bin (the common case) and adds into the histogram with shared-memory atomics; the
+// histogram is flushed to the global profile once per CTA.
+constexpr int kFoldNarrowRows = 256;   // samples per chunk (one bin computed per thread)
+
+__global__ void __launch_bounds__(256) fold_narrow_kernel(const __grid_constant__ FoldArgs a,
+                                                          int span) {
+  extern __shared__ int fsm[];
+  const int E = (int)a.row_elems;
+  float* hist = reinterpret_cast<float*>(fsm);              // [nbin][E]
+  int* scnt = fsm + (size_t)a.nbin * E;                     // [nbin]
+  int* sbin = scnt + a.nbin;                                // [kFoldNarrowRows]
+  for (int i = threadIdx.x; i < a.nbin * E; i += blockDim.x) hist[i] = 0.f;
+  for (int i = threadIdx.x; i < a.nbin; i += blockDim.x) scnt[i] = 0;
+  const long long nb = (long long)blockIdx.x * span;
+  const int nrows = (int)min((long long)span, a.nsamp - nb);
+  const bool pow2 = (32 % E) == 0;      // a warp then holds whole samples: 32/E of them
+  const int lane = threadIdx.x & 31;
+  __syncthreads();
+  for (int c0 = 0; c0 < nrows; c0 += kFoldNarrowRows) {
+    const int nr = min(kFoldNarrowRows, nrows - c0);
+    if (threadIdx.x < nr) {
+      const int b = fold_bin(a, nb + c0 + threadIdx.x);
+      sbin[threadIdx.x] = b;
+      if (a.bins_out) a.bins_out[nb + c0 + threadIdx.x] = b;
+      atomicAdd(scnt + b, 1);
+    }
+    __syncthreads();
+    const float* p = a.in + (nb + c0) * (long long)E;
+    const int total = nr * E;
+    for (int i0 = 0; i0 < total; i0 += blockDim.x) {       // uniform trip count per warp
+      const int i = i0 + threadIdx.x;
+      const bool ok = i < total;
+      const int r = ok ? i / E : 0, el = ok ? i - r * E : 0;
+      float v = ok ? __ldg(p + i) : 0.f;
+      const int b = ok ? sbin[r] : -1;
+      const int b0 = __shfl_sync(0xffffffffu, b, 0);
+      if (pow2 && __all_sync(0xffffffffu, b == b0)) {
+        for (int s = E; s < 32; s <<= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+        if (lane < E && b0 >= 0) atomicAdd(hist + b0 * E + el, v);
+      } else if (ok) {
+        atomicAdd(hist + b * E + el, v);
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < a.nbin * E; i += blockDim.x)
+    if (hist[i] != 0.f) atomicAdd(a.profile + i, hist[i]);
+  for (int i = threadIdx.x; i < a.nbin; i += blockDim.x)
+    if (scnt[i]) atomicAdd(a.counts + i, (unsigned long long)scnt[i]);
+}
+
+static inline int fold_pick_span(long long nsamp, long long ctas_per_span, int lo, int hi) {
+  // enough CTAs to fill the 148 SMs several times over, long enough spans to amortise atomics
+  long long span = hi;
+  while (span > lo && (nsamp + span - 1) / span * ctas_per_span < 148ll * 8) span >>= 1;
+  return (int)span;
 }
 
 static inline cudaError_t launch_fold(const FoldArgs& a, cudaStream_t st) {
-  const long long gx = (a.nsamp + kFoldRows - 1) / kFoldRows;
-  const long long gy = (a.row_elems + 255) / 256;
+  if (a.nsamp <= 0) return cudaSuccess;
+  const size_t narrow_smem = ((size_t)a.nbin * a.row_elems + a.nbin + kFoldNarrowRows) * 4;
+  if (a.row_elems <= 32 && narrow_smem <= 160 * 1024) {
+    static bool attr_done[16] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 16 && !attr_done[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(fold_narrow_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      if (e != cudaSuccess) return e;
+      attr_done[dev] = true;
+    }
+    // a span must be long against nbin so that the flush is amortised
+    const int span = fold_pick_span(a.nsamp, 1, 4096, 65536);
+    const long long gx = (a.nsamp + span - 1) / span;
+    fold_narrow_kernel<<<(unsigned)gx, 256, narrow_smem, st>>>(a, span);
+    return cudaGetLastError();
+  }
+  const int threads = a.row_elems >= 256 ? 256 : (int)((a.row_elems + 31) / 32 * 32);
+  const long long gy = (a.row_elems + threads - 1) / threads;
   if (gy > 65535) return cudaErrorInvalidValue;
-  dim3 grid((unsigned)gx, (unsigned)gy);
-  fold_kernel<<<grid, 256, 0, st>>>(a);
+  const int smem_counts = a.nbin <= 11000;                // else count with global atomics
+  const size_t smem = (2 * kFoldChunk + (smem_counts ? (size_t)a.nbin : 0)) * 4;
+  const int span = fold_pick_span(a.nsamp, gy, 256, 4096);
+  dim3 grid((unsigned)((a.nsamp + span - 1) / span), (unsigned)gy);
+  fold_wide_kernel<<<grid, threads, smem, st>>>(a, span, smem_counts);
   return cudaGetLastError();
 }
 

@@ -648,3 +648,28 @@ def test_cfg5_shard_2pow26_device_resident():
         num += (d ** 2).sum()
         den += (ref ** 2).sum()
     assert float(torch.sqrt(num / den)) < 1e-5
+
+
+@pytest.mark.parametrize("nsamp, elems, nbin, f0", [(100_003, 2, 1024, 29.7), (70_000, 1, 64, 641.9),
+                                                    (50_000, 3, 128, 5.3), (9_001, 32, 1024, 29.7),
+                                                    (20_011, 40, 256, 641.9), (4_099, 300, 1024, 29.7),
+                                                    (70_000, 2, 40000, 29.7)])
+def test_fold_shapes_bit_exact_counts(nsamp, elems, nbin, f0):
+    """Both fold kernels (shared-memory histogram for narrow rows, long-span register
+    accumulation for wide rows) and their edge shapes: bins and counts bit-exact, sums to float32
+    tolerance, accumulation into an existing profile."""
+    from pulsarbat_b200 import kernels
+    rng = np.random.default_rng(nsamp + elems)
+    x = rng.random((nsamp, elems), dtype=np.float32)
+    coeffs = [0.321, f0, 2e-7]
+    sr = 1e4
+    prof, counts, bins = kernels.fold(x, coeffs, sr, nbin, n0=17, want_bins=True)
+    ref_bins = orc.fold_bins(nsamp, coeffs, sr, nbin, n0=17)
+    assert np.array_equal(bins, ref_bins)
+    want_p, want_c = orc.fold(x, coeffs, sr, nbin, n0=17)
+    assert np.array_equal(counts, want_c)
+    assert relerr(prof, want_p) < 1e-5
+    prof2, counts2 = kernels.fold(x, coeffs, sr, nbin, n0=17, profile=prof.copy(),
+                                  counts=counts.copy())
+    assert np.array_equal(counts2, 2 * want_c)
+    assert relerr(prof2, 2 * want_p) < 1e-5
