@@ -205,7 +205,9 @@ static void set_geometry(Pass& ps, int log2L, long long Q, long long RI, int I, 
   while (lpw > 0 && (1ll << (lpw - 1)) >= pairs) --lpw;
   a.log2pw = lpw;
   a.log2Kprev = log2Kprev;
-  ps.smem = a.nstages > 1 ? ((size_t)1 << (log2L + lpw)) * sizeof(float4) : 0;
+  // tile (multi-stage tiles only) + per-tile level-twiddle table [lanes][16]
+  ps.smem = (a.nstages > 1 ? ((size_t)1 << (log2L + lpw)) * sizeof(float4) : 0) +
+            ((size_t)2 << lpw) * 16 * sizeof(float2);
   const long long W = 2ll << lpw;
   ps.grid = (unsigned)((Q + W - 1) / W);
 }

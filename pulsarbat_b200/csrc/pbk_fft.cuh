@@ -396,6 +396,7 @@ __device__ __forceinline__ void store_row_epi(const PassArgs& p, const LaneCtx& 
 // ------------------------------------------------------------------------------------------
 struct Tile {
   float4* s;
+  const float2* G;   // per-tile level-twiddle table [lane][16] (apply_level_tw)
   int log2pw;
   int swzmask;  // (points per 128 B) - 1
   __device__ __forceinline__ int idx(int pt, int pr) const {
@@ -430,38 +431,35 @@ __device__ __forceinline__ void apply_stage_tw(c2* v, const float2* __restrict__
   }
 }
 
-// inter-level twiddle for register m of a radix-R group: W_M^(nrest * (kbase + m*kstep)).
-// Built as E_a * F_c with m = 4a + c from exact roots, so every factor is one multiply deep.
+// inter-level twiddle for register m of a radix-R group: W_M^(nrest * (kbase + m*kstep))
+//   = E * G[lane][m],  E = W_M^(nrest*kbase) (one exact root per task and lane),
+//   G[lane][m] = W_M^(nrest_lane * kstep * m): a per-tile table in shared memory (the tile's kstep
+//   is fixed), so a task needs one sincospif per lane instead of seven.
 template <int R, bool CONJ, bool FAST>
 __device__ __forceinline__ void apply_level_tw(const PassArgs& p, const LaneCtx& L, c2* v,
-                                               unsigned int kbase, unsigned int kstep) {
+                                               unsigned int kbase, const float2* Gtab, int pr) {
   if (p.log2M == 0) return;
-  constexpr int NA = (R + 3) / 4;
-  constexpr int NC = R < 4 ? R : 4;
-  float2 E0[NA], F0[NC], E1[NA], F1[NC];
-  {
-    const unsigned long long nr = L.nrest[0];
-#pragma unroll
-    for (int a = 0; a < NA; ++a) E0[a] = unit_root(nr * (kbase + 4ull * a * kstep), p.log2M);
-#pragma unroll
-    for (int c = 1; c < NC; ++c) F0[c] = unit_root(nr * ((unsigned long long)c * kstep), p.log2M);
-  }
-  if (!FAST) {
-    const unsigned long long nr = L.nrest[1];
-#pragma unroll
-    for (int a = 0; a < NA; ++a) E1[a] = unit_root(nr * (kbase + 4ull * a * kstep), p.log2M);
-#pragma unroll
-    for (int c = 1; c < NC; ++c) F1[c] = unit_root(nr * ((unsigned long long)c * kstep), p.log2M);
-  }
+  const float2 E0 = unit_root((unsigned long long)L.nrest[0] * kbase, p.log2M);
+  const float2 E1 = FAST ? E0 : unit_root((unsigned long long)L.nrest[1] * kbase, p.log2M);
+  // table layout [m][lane]: the 16-byte pair entries of a warp are consecutive (no bank conflicts)
+  const float4* G4 = reinterpret_cast<const float4*>(Gtab) + pr;
+  const int npairs = 1 << p.log2pw;
 #pragma unroll
   for (int m = 0; m < R; ++m) {
-    const int a = m >> 2, c = m & 3;
-    float2 w0 = (c == 0) ? E0[a] : cmul1(E0[a], F0[c]);
-    float2 w1 = w0;
-    if (!FAST) w1 = (c == 0) ? E1[a] : cmul1(E1[a], F1[c]);
+    const float4 g = m == 0 ? make_float4(1.f, 0.f, 1.f, 0.f) : G4[m * npairs];
+    float2 w0 = m == 0 ? E0 : cmul1(E0, make_float2(g.x, g.y));
+    float2 w1 = FAST ? w0 : (m == 0 ? E1 : cmul1(E1, make_float2(g.z, g.w)));
     if (CONJ) { w0.y = -w0.y; w1.y = -w1.y; }
     v[m] = cmul(v[m], make_float2(w0.x, w1.x), make_float2(w0.y, w1.y));
   }
+}
+
+// nrest of an arbitrary lane of this CTA's tile (same arithmetic as lane_setup)
+__device__ __forceinline__ unsigned int lane_nrest(const PassArgs& p, int lane) {
+  long long q = ((long long)blockIdx.x << (p.log2pw + 1)) + lane;
+  if (q >= p.Q) q = 0;
+  const long long o = q / p.RI;
+  return (unsigned int)((q - o * p.RI) / p.I);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -621,7 +619,7 @@ __device__ __forceinline__ void first_stage(const PassArgs& p, const LaneCtx& L,
       for (int i = 0; i < R; ++i) T.st(b + (i << log2S), pr, v[i]);
     } else {
       // single-stage tile (L == R): FWD mode only; registers hold k = m
-      apply_level_tw<R, SIGNINV, FAST>(p, L, v, 0u, 1u);
+      apply_level_tw<R, SIGNINV, FAST>(p, L, v, 0u, T.G, pr);
       if (p.scale != 1.0f) {
         const float2 sc = p_bc(p.scale);
 #pragma unroll
@@ -702,7 +700,20 @@ __global__ void __launch_bounds__(kThreads, 2) pass_kernel(const __grid_constant
 
   const int ns = p.nstages;
   const int nb16 = 1 << (p.log2L - 4);            // radix-16 groups per lane pair
-  const unsigned int kstep = 1u << (p.log2L - 4);  // k spacing between registers of the last stage
+  const unsigned int kstep = ns > 1 ? 1u << (p.log2L - 4) : 1u;  // k spacing of last-stage registers
+
+  // level-twiddle table of this tile: G[lane][m] = W_M^(nrest_lane * kstep * m), behind the tile
+  {
+    float2* G = reinterpret_cast<float2*>(smem_dyn + (ns > 1 ? ((size_t)1 << (p.log2L + p.log2pw)) : 0));
+    T.G = G;
+    if (p.log2M != 0 && MODE != MODE_MID) {
+      for (int idx = threadIdx.x; idx < (2 * pw) * 16; idx += kThreads) {
+        const int m = idx / (2 * pw), lane = idx - m * (2 * pw);   // [m][lane]
+        G[idx] = unit_root((unsigned long long)lane_nrest(p, lane) * (kstep * (unsigned)m), p.log2M);
+      }
+      __syncthreads();
+    }
+  }
 
   if (MODE == MODE_FWD) {
     // level transform, DIF: first stage from global, middle stages in smem, last stage to global
@@ -740,7 +751,7 @@ __global__ void __launch_bounds__(kThreads, 2) pass_kernel(const __grid_constant
       for (int i = 0; i < 16; ++i) v[i] = T.ld((b << 4) + i, pr);
       Butterfly<16, SIGNINV>::run(v);
       const unsigned int klo = klo_of_block((unsigned int)b, ns, p.log2r1);
-      apply_level_tw<16, SIGNINV, FAST>(p, L, v, klo, kstep);
+      apply_level_tw<16, SIGNINV, FAST>(p, L, v, klo, T.G, pr);
       if (p.scale != 1.0f) {
         const float2 sc = p_bc(p.scale);
 #pragma unroll
@@ -795,7 +806,7 @@ __global__ void __launch_bounds__(kThreads, 2) pass_kernel(const __grid_constant
       c2 v[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = load_row<FAST>(p, L, (long long)(klo + i * kstep));
-      apply_level_tw<16, true, FAST>(p, L, v, klo, kstep);
+      apply_level_tw<16, true, FAST>(p, L, v, klo, T.G, pr);
       Butterfly<16, true>::run(v);
       if (ns > 1) {
 #pragma unroll
