@@ -251,3 +251,40 @@ def test_block_stream_matches_single_calls():
     one = list(pb.streaming.dedisperse_blocks([blocks[0]], dm=dm, sample_rate_hz=sr,
                                               chan_freq_hz=freqs, ref_freq_hz=fcen))
     assert len(one) == 1 and one[0].shape == (N, C, 2)
+
+
+def test_fold_across_polyco_spans():
+    """A signal longer than one polyco entry (90 min spans in the reference's fixture): each
+    stretch is folded with the entry the reference would select (predictor.py:108-119).  Bins are
+    bit-exact against the oracle stretch by stretch, and a pulse train generated from the
+    per-sample phase of the ORIGINAL polynomials stays in its phase window across the boundaries."""
+    import pulsarbat_b200 as pb
+    from pulsarbat_b200.pulsar.folding import fold_segments
+    u = pb.units
+    here = os.path.dirname(os.path.abspath(__file__))
+    path = os.path.join(here, "golden", "timing.dat")
+    pred = pb.PhasePredictor.from_polyco(path)
+    with open(path) as f:
+        entries = orc.parse_polyco(f.read())
+    t0 = pb.Time(pred.entries[0].tmid.mjd + 0.02)
+    sr, nsamp, nbin = 500.0, 6_000_000, 64               # 200 minutes: four entries
+    z0 = pb.Signal(np.zeros((nsamp, 1), np.float32), sample_rate=sr * u.Hz, start_time=t0)
+    segs = fold_segments(z0, pred)
+    assert len(segs) == 4 and sum(c for _, c, _ in segs) == nsamp
+    # independent per-sample phase from the original polynomials, entry by entry
+    frac = np.empty(nsamp)
+    for first, count, _ in segs:
+        tf = t0 + (first / sr) * u.s
+        _, fr = orc.predict_phase(entries, (tf.jd1, tf.jd2), np.arange(count) / sr)
+        frac[first:first + count] = fr - np.floor(fr)
+    x = ((frac >= 0.2) & (frac < 0.25)).astype(np.float32)[:, None]
+    z = pb.Signal(x, sample_rate=sr * u.Hz, start_time=t0)
+    prof, counts, bins = pb.fold(z, pred, nbin, want_bins=True)
+    ref_bins = np.concatenate([
+        orc.fold_bins(c, orc.phasepol(entries, ((t0 + (f / sr) * u.s).jd1,
+                                                (t0 + (f / sr) * u.s).jd2))[0], sr, nbin)
+        for f, c, _ in segs])
+    assert np.array_equal(bins, ref_bins)
+    assert np.array_equal(counts, np.bincount(ref_bins, minlength=nbin))
+    inside = prof[12:16, 0].sum()
+    assert inside / prof.sum() > 0.999 and prof.sum() == pytest.approx(x.sum(), rel=1e-6)
