@@ -8,7 +8,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libpbk.so")
+_LIB_PATH = os.environ.get("PBK_LIBRARY") or os.path.join(_HERE, "libpbk.so")
 
 PBK_C64, PBK_I8X2 = 0, 1
 OUT_C64, OUT_INTENSITY, OUT_STOKES_I = 0, 1, 2

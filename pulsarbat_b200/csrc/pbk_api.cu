@@ -76,7 +76,8 @@ enum PlanKind { PLAN_DEDISP = 0, PLAN_FFT = 1 };
 
 struct Pass {
   int mode = MODE_FWD;
-  bool fast = false;
+  bool fast = false;      // uniform lane pairs (same time offset AND channel): vector generic path
+  bool pair_ok = false;   // lane pairs usable by the fast family (P even, or P == 1: two channels)
   bool signinv = false;
   int in_role = ROLE_USER_IN, out_role = ROLE_SCRATCH;
   PassArgs a;
@@ -256,6 +257,18 @@ static double level_chunk_bytes(int l, long long lanes_avail) {
   return w * 8.0;
 }
 
+namespace pbk { bool fast_info(int family, int log2L, FastInfo* info); }
+static int preferred_family();
+
+// true when a pass of tile length 2^l over I lanes can run on a compile-time-shaped kernel
+static bool level_is_fast(int l, long long I) {
+  const int fam = preferred_family();
+  FastInfo fi;
+  if (fam < 0 || (I & 1) || !pbk::fast_info(fam, l, &fi)) return false;
+  const long long W = 2ll << fi.log2pw;
+  return I % W == 0 || W % I == 0;
+}
+
 static int choose_levels(int n, long long I, int* l, bool need_mid16) {
   const char* e = getenv("PBK_LEVELS");   // developer override, e.g. PBK_LEVELS=11,11
   if (e) {
@@ -287,7 +300,9 @@ static int choose_levels(int n, long long I, int* l, bool need_mid16) {
       if (i + 1 < m) {
         if (need_mid16 && ls[i] < lo) return;   // inverse passes start with a radix-16 stage
         // tiles longer than 2^8 need a third butterfly stage per pass
-        const double stages = ls[i] <= 8 ? 1.0 : 1.0 + 0.15 * (ls[i] - 8);
+        // the runtime-shaped generic kernel issues ~3.5x the instructions of a fast one
+        const double stages = (ls[i] <= 8 ? 1.0 : 1.0 + 0.15 * (ls[i] - 8)) *
+                              (need_mid16 && !level_is_fast(ls[i], I) ? 2.2 : 1.0);
         cost += 2.0 * (stages * pass_tb / bw_s(level_chunk_bytes(ls[i], R * I)) + pass_fixed);
       } else {
         // the fused fft*chirp*ifft pass does two transforms of 2^l plus the chirp per tile and is
@@ -295,7 +310,7 @@ static int choose_levels(int n, long long I, int* l, bool need_mid16) {
         // against 1.45 ms for a plain pass); below 2^6 only the generic kernel exists
         static const double mid_factor[13] = {3.0,  3.0, 3.0, 3.0, 3.0, 3.0, 1.05,
                                               1.3,  1.6, 1.9, 2.2, 2.5, 2.8};
-        const double f = need_mid16 ? mid_factor[ls[i]]
+        const double f = need_mid16 ? mid_factor[ls[i]] * (level_is_fast(ls[i], I) ? 1.0 : 2.2)
                                     : (ls[i] <= 8 ? 1.0 : 1.0 + 0.15 * (ls[i] - 8));
         cost += f * pass_tb / bw_r(level_chunk_bytes(ls[i], I)) + pass_fixed;
       }
@@ -349,33 +364,24 @@ static cudaError_t launch_pass(const Pass& ps, bool fast, cudaStream_t st) {
 // fast-kernel dispatch (instantiations in pbk_fast_r8.cu / pbk_fast_r16.cu)
 // ------------------------------------------------------------------------------------------
 namespace pbk {
-bool fast_info_r8(int log2L, FastInfo* info);
+// one family is built: radix-16 stages, <= 128 registers per thread.  (A radix-8 / 64-register /
+// 512-thread family was measured 4-8 % slower on every configuration and was removed.)
 bool fast_info_r16(int log2L, FastInfo* info);
-void fast_tables_r8(int log2L, float2* dst);
 void fast_tables_r16(int log2L, float2* dst);
-cudaError_t fast_launch_r8(int log2L, int mode, const PassArgs& a, const float2* d_tables,
-                           long long ntiles, int num_sms, cudaStream_t st);
 cudaError_t fast_launch_r16(int log2L, int mode, const PassArgs& a, const float2* d_tables,
                             long long ntiles, int num_sms, cudaStream_t st);
-bool fast_info(int family, int log2L, FastInfo* info) {
-  return family == FAMILY_R8 ? fast_info_r8(log2L, info) : fast_info_r16(log2L, info);
-}
-void fast_tables(int family, int log2L, float2* dst) {
-  if (family == FAMILY_R8) fast_tables_r8(log2L, dst); else fast_tables_r16(log2L, dst);
-}
+bool fast_info(int family, int log2L, FastInfo* info) { return fast_info_r16(log2L, info); }
+void fast_tables(int family, int log2L, float2* dst) { fast_tables_r16(log2L, dst); }
 cudaError_t fast_launch(int family, int log2L, int mode, const PassArgs& a, const float2* d_tables,
                         long long ntiles, int num_sms, cudaStream_t st) {
-  return family == FAMILY_R8 ? fast_launch_r8(log2L, mode, a, d_tables, ntiles, num_sms, st)
-                             : fast_launch_r16(log2L, mode, a, d_tables, ntiles, num_sms, st);
+  return fast_launch_r16(log2L, mode, a, d_tables, ntiles, num_sms, st);
 }
 }  // namespace pbk
 
-// developer knob: PBK_FAMILY=8|16|0 picks the fast-kernel family (0 = generic kernels only)
+// developer knob: PBK_FAMILY=0 forces the generic runtime-shaped kernels everywhere
 static int preferred_family() {
   const char* e = getenv("PBK_FAMILY");
-  if (!e) return FAMILY_R16;
-  if (!strcmp(e, "8")) return FAMILY_R8;
-  if (!strcmp(e, "0")) return -1;
+  if (e && !strcmp(e, "0")) return -1;
   return FAMILY_R16;
 }
 
@@ -385,7 +391,7 @@ static int setup_fast(pbk_plan* pl) {
   std::vector<float2> host;
   for (auto& ps : pl->passes) {
     ps.family = -1;
-    if (fam < 0 || !ps.fast || ps.signinv || ps.a.fxor || ps.a.kxor) continue;
+    if (fam < 0 || !ps.pair_ok || ps.signinv || ps.a.fxor || ps.a.kxor) continue;
     // the fast kernels are specialised to the dedispersion passes (see pbk_fast.cuh)
     if (ps.a.scale != 1.0f && ps.mode != MODE_MID) continue;
     if (ps.mode != MODE_MID && ps.a.log2M == 0) continue;
@@ -397,7 +403,12 @@ static int setup_fast(pbk_plan* pl) {
     FastInfo fi;
     if (!fast_info(fam, ps.a.log2L, &fi)) continue;
     const long long W = 2ll << fi.log2pw;
-    if (ps.a.I % W || ps.a.Q % W || W % ps.a.P) continue;
+    // a tile is W adjacent lanes: inside one row of the (.., I) array (I % W == 0), or, for arrays
+    // with few channels, W / I whole rows (consecutive time offsets / consecutive kprev blocks)
+    const bool wide = ps.a.I % W == 0 && W % ps.a.P == 0;
+    const bool narrow = ps.a.I < W && W % ps.a.I == 0 && ps.a.I % 2 == 0 &&
+                        (ps.mode == MODE_MID ? pl->kind == PLAN_DEDISP : ps.a.RI % W == 0);
+    if (!(wide || narrow) || ps.a.Q % W) continue;
     if (ps.a.min.a_row * 8 >= (1ll << 32) || ps.a.mout.a_row * 8 >= (1ll << 32)) continue;
     ps.family = fam;
     ps.finfo = fi;
@@ -562,6 +573,7 @@ static int dedisp_plan_create_impl(const pbk_dedisp_desc* d, const RampSpec* ram
 
   TableSet ts;
   const bool fast_ok = (I % 2 == 0) && (P % 2 == 0);
+  const bool pair_ok = (I % 2 == 0) && (P % 2 == 0 || P == 1);
   long long Kprev[3], R[3];
   {
     long long k = 1;
@@ -601,6 +613,7 @@ static int dedisp_plan_create_impl(const pbk_dedisp_desc* d, const RampSpec* ram
     if (i == 0)
       ps.a.load_kind = d->in_dtype == PBK_I8X2 ? LOAD_I8X2 : d->in_dtype == PBK_F32 ? LOAD_F32 : LOAD_C64;
     ps.fast = fast_ok;
+    ps.pair_ok = pair_ok;
     ts.ensure(l[i]);
     pl->passes.push_back(ps);
   }
@@ -634,6 +647,7 @@ static int dedisp_plan_create_impl(const pbk_dedisp_desc* d, const RampSpec* ram
       final_epilogue(ps, 0);
     }
     ps.fast = fast_ok;
+    ps.pair_ok = pair_ok;
     ts.ensure(l[i]);
     pl->passes.push_back(ps);
   }
@@ -651,6 +665,7 @@ static int dedisp_plan_create_impl(const pbk_dedisp_desc* d, const RampSpec* ram
     ps.out_role = ROLE_SCRATCH;
     if (i == 0) final_epilogue(ps, 0);
     ps.fast = fast_ok;
+    ps.pair_ok = pair_ok;
     pl->passes.push_back(ps);
   }
 
@@ -948,6 +963,7 @@ static int build_fft_plan(long long O, long long n, long long C, long long P, bo
     ps.out_role = i == m - 1 ? ROLE_USER_OUT : ROLE_SCRATCH;
     ps.fast = (I % 2 == 0) && map_even(ps.a.min, P) && map_even(ps.a.mout, P) &&
               ((O * Kprev[i] * R[i] * I) % 2 == 0);
+    ps.pair_ok = ps.fast;
     ts.ensure(l[i]);
     pl->passes.push_back(ps);
   }
@@ -1325,7 +1341,7 @@ extern "C" int pbk_plan_describe(const pbk_plan* pl, char* buf, size_t n) {
     const char* sep = i == 0 ? "" : (blocked && (i == 2 || i == 3)) ? "+" : ";";
     if (ps.family >= 0)
       w = snprintf(buf + off, n - off, "%s%s:L=2^%d:%s:W=%d:tiles=%lld:threads=%d", sep,
-                   mode, ps.a.log2L, ps.family == FAMILY_R8 ? "fast-r8" : "fast-r16",
+                   mode, ps.a.log2L, "fast-r16",
                    2 << ps.finfo.log2pw, ps.ntiles, ps.finfo.threads);
     else
       w = snprintf(buf + off, n - off, "%s%s:L=2^%d:%s:W=%d:tiles=%u:threads=%d", sep,

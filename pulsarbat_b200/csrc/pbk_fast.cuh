@@ -53,10 +53,15 @@ struct FastCfg {
   }
   static constexpr int TW_TOTAL = tw_off(NS - 1) > 0 ? tw_off(NS - 1) : 1;
   static constexpr size_t TILE_BYTES = (size_t)L * PW * sizeof(float4);
-  // tile | stage tables (padded to 16 B) | level-twiddle table G (RL float4) | TileInfo
+  // tile | stage tables (padded to 16 B) | level-twiddle tables G (one of RL float4 per row of
+  // lanes in the tile: up to W/2 rows when the array has only 2 lanes per row) | TileInfo
   static constexpr int TW_PAD = (TW_TOTAL + 1) & ~1;
-  static constexpr size_t SMEM_BYTES = TILE_BYTES + (size_t)TW_PAD * sizeof(float2) +
-                                       (size_t)RL * sizeof(float4) + 64;
+  static constexpr int G_ROWS = W / 2;
+  static constexpr size_t SMEM_BASE = TILE_BYTES + (size_t)TW_PAD * sizeof(float2) + 64;
+  __host__ __device__ static constexpr size_t smem_bytes(bool narrow) {
+    return SMEM_BASE + (size_t)RL * (narrow ? G_ROWS : 1) * sizeof(float4);
+  }
+  static constexpr size_t SMEM_BYTES = smem_bytes(true);
 };
 
 // host-side builder of the stage tables in the layout the kernel expects:
@@ -151,10 +156,10 @@ enum { LK_C64 = 0, LK_I8 = 1, LK_PLANAR = 2 };
 // arithmetic has 64-bit divisions) and broadcast through shared memory
 struct TileInfo {
   long long bi, bo;     // byte offsets of lane pair 0, row 0 in the input / output array
-  unsigned nrest, klow;
+  unsigned nrest, klow; // of lane 0
+  unsigned kprev;       // of lane 0 (MID tiles narrower than W lanes span several of them)
   int chan0;
-  unsigned row_lo, row_cnt;
-  int pad;
+  unsigned row_lo, row_cnt;   // crop row range of lane 0 (all lanes when the tile is one row)
 };
 
 template <class C, int EPI>
@@ -164,7 +169,7 @@ __device__ __forceinline__ void fast_tile_info(const PassArgs& p, long long tile
   const long long o = q0 / p.RI;
   const long long r0 = q0 - o * p.RI;
   const long long nrest = r0 / p.I;
-  const int col0 = (int)(r0 - nrest * p.I);      // multiple of W, hence of P (host checks W % P)
+  const int col0 = (int)(r0 - nrest * p.I);      // multiple of W (hence of P), or 0 when I < W
   const long long o_orig = o >> p.log2Kprev;
   const long long kprev = o & ((1ll << p.log2Kprev) - 1);
   const long long klow = (kprev >> p.kl_sa) + ((kprev & p.kl_mb) << p.kl_sb);
@@ -172,6 +177,7 @@ __device__ __forceinline__ void fast_tile_info(const PassArgs& p, long long tile
   long long bo = map_base(p.mout, o_orig, kprev, klow, nrest, col0, p.P) * out_elem_bytes;
   ti.nrest = (unsigned)nrest;
   ti.klow = (unsigned)klow;
+  ti.kprev = (unsigned)kprev;
   ti.chan0 = col0 / p.P;
   ti.row_lo = 0;
   ti.row_cnt = C::L;
@@ -284,32 +290,48 @@ __device__ __forceinline__ void level_twiddle(const PassArgs& p, c2* v, unsigned
 //    the host only selects this kernel when |x| <= 1/16), so there is no FP64 division.
 //    cc = {(fc-fr)/fr, df/fc, D/fc} per channel, p.bd = df/fr.
 //  * phi is reduced exactly (phi - rint(phi), |.| <= 1/2 cycle) before the FP32 sine/cosine.
-template <int R, class C>
+// FP64 phase of one channel at signed bin ks (see the comment above), reduced to [-0.5, 0.5]
+__device__ __forceinline__ float2 fast_chirp_value(const PassArgs& p, const double* cc, double ks) {
+  const double a = fma(ks, p.bd, cc[0]);
+  const double x = ks * cc[1];
+  const double u = 1.0 + x;
+  double r = fma(x, fma(x, 1.0 - x, -1.0), 1.0);
+  r = fma(r, fma(-u, r, 1.0), r);
+  r = fma(r, fma(-u, r, 1.0), r);
+  const double phi = (a * a) * (r * cc[2]);             // cycles
+  const double fr = phi - rint(phi);                    // exact reduction to [-0.5, 0.5]
+  float sn, cs;
+#ifdef PBK_ACCURATE_SINCOS
+  sincospif(2.0f * (float)fr, &sn, &cs);
+#else
+  __sincosf(6.283185307179586f * (float)fr, &sn, &cs);   // MUFU, |error| < 5e-7 on |x| <= pi
+#endif
+  return make_float2(cs * p.scale, -sn * p.scale);
+}
+
+// TWOCH: single-polarisation data (P = 1) -- the two lanes of a pair are two adjacent channels,
+// each with its own chirp; otherwise the pair is the two pols of one channel and shares it.
+template <int R, class C, bool TWOCH>
 __device__ __forceinline__ void fast_chirp(const PassArgs& p, const FastTile& T, c2* v, int klo) {
   const double k0 = (double)((long long)T.klow + ((long long)klo << p.log2Kmul));
   const double Nd = (double)p.N;
-  const double cA = p.chan_const[3 * T.chan + 0];
-  const double cX = p.chan_const[3 * T.chan + 1];
-  const double cD = p.chan_const[3 * T.chan + 2];
+  double cc0[3], cc1[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    cc0[i] = p.chan_const[3 * T.chan + i];
+    cc1[i] = TWOCH ? p.chan_const[3 * (T.chan + 1) + i] : 0.0;
+  }
 #pragma unroll
   for (int m = 0; m < R; ++m) {
     const double cm = (double)m / R - (m >= R / 2 ? 1.0 : 0.0);
     const double ks = fma(cm, Nd, k0);
-    const double a = fma(ks, p.bd, cA);
-    const double x = ks * cX;
-    const double u = 1.0 + x;
-    double r = fma(x, fma(x, 1.0 - x, -1.0), 1.0);
-    r = fma(r, fma(-u, r, 1.0), r);
-    r = fma(r, fma(-u, r, 1.0), r);
-    const double phi = (a * a) * (r * cD);              // cycles
-    const double fr = phi - rint(phi);                  // exact reduction to [-0.5, 0.5]
-    float sn, cs;
-#ifdef PBK_ACCURATE_SINCOS
-    sincospif(2.0f * (float)fr, &sn, &cs);
-#else
-    __sincosf(6.283185307179586f * (float)fr, &sn, &cs);   // MUFU, |error| < 5e-7 on |x| <= pi
-#endif
-    v[m] = cmul(v[m], p_bc(cs * p.scale), p_bc(-sn * p.scale));
+    const float2 h0 = fast_chirp_value(p, cc0, ks);
+    if (TWOCH) {
+      const float2 h1 = fast_chirp_value(p, cc1, ks);
+      v[m] = cmul(v[m], make_float2(h0.x, h1.x), make_float2(h0.y, h1.y));
+    } else {
+      v[m] = cmul(v[m], p_bc(h0.x), p_bc(h0.y));
+    }
   }
 }
 
@@ -414,7 +436,7 @@ __device__ __forceinline__ void inv_last(const FastTile& T, float4* tile, const 
 // ------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------
-template <int MODE, class C, int LOADK, int EPI>
+template <int MODE, class C, int LOADK, int EPI, bool TWOCH = false, bool NARROW = false>
 __global__ void __launch_bounds__(C::NT, C::MINB)
 fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ tables,
                  long long ntiles) {
@@ -423,7 +445,7 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
   float4* tile = smem_dyn;
   float2* tws = reinterpret_cast<float2*>(tile + (size_t)C::L * C::PW);
   float4* G4 = reinterpret_cast<float4*>(tws + C::TW_PAD);
-  TileInfo* sinfo = reinterpret_cast<TileInfo*>(G4 + C::RL);
+  TileInfo* sinfo = reinterpret_cast<TileInfo*>(G4 + C::RL * (NARROW ? C::G_ROWS : 1));
   const int tid = threadIdx.x;
   const int pr = tid & (C::PW - 1);
 
@@ -438,12 +460,22 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
   if (tid == 0 && t < ntiles) fast_tile_info<C, EPI>(p, t, *sinfo, in_eb, out_eb);
   __syncthreads();
 
-  // per-thread part of the addresses: lane pair 2*pr inside the tile (col0 is a multiple of P)
-  const int colt = 2 * pr;
-  const long long off_in = ((long long)(colt / p.P) * p.min.a_c + (colt % p.P) * p.min.a_p) * in_eb;
+  // Per-thread part of the addresses.  A tile is W adjacent lanes; a lane is (row jr, column) of
+  // the (.., I) array.  Normally (I a multiple of W) the tile sits inside one row (jr = 0, col0 a
+  // multiple of P).  NARROW kernels serve arrays with few channels (I < W): the tile then spans
+  // nrows = W / I consecutive rows -- consecutive inner time offsets for the strided levels,
+  // consecutive kprev blocks for the MID level -- and everything row-dependent is per thread.
+  const int nrows = NARROW ? C::W / p.I : 1;
+  const int jr = NARROW ? (2 * pr) / p.I : 0;
+  const int colt = NARROW ? (2 * pr) % p.I : 2 * pr;
+  const long long row_in = MODE == MODE_MID ? p.min.a_kp : p.min.a_n;
+  const long long row_out = MODE == MODE_MID ? p.mout.a_kp : p.mout.a_n;
+  const long long off_in =
+      (jr * row_in + (long long)(colt / p.P) * p.min.a_c + (colt % p.P) * p.min.a_p) * in_eb;
   const long long off_out =
-      ((long long)(colt / p.P) * p.mout.a_c + (colt % p.P) * p.mout.a_p) * out_eb;
+      (jr * row_out + (long long)(colt / p.P) * p.mout.a_c + (colt % p.P) * p.mout.a_p) * out_eb;
   const int chant = colt / p.P;
+  const float4* G4t = G4 + jr * C::RL;   // this thread's row of the level-twiddle tables
 
   constexpr int RL = C::RL;
   constexpr int LTASKS = (C::L / RL) * C::PW;
@@ -451,19 +483,44 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
 
   for (; t < ntiles; t += gridDim.x) {
     FastTile T;
+    unsigned nrest0;
     {
       const TileInfo ti = *sinfo;
       T.gin = reinterpret_cast<const char*>(p.in) + ti.bi + off_in;
       T.gout = reinterpret_cast<char*>(p.out) + ti.bo + off_out;
-      T.nrest = ti.nrest;
-      T.klow = ti.klow;
+      nrest0 = ti.nrest;
+      T.nrest = ti.nrest + (MODE == MODE_MID ? 0 : jr);
+      if (MODE == MODE_MID && NARROW) {
+        const unsigned kprev = ti.kprev + jr;
+        T.klow = (kprev >> p.kl_sa) + ((kprev & p.kl_mb) << p.kl_sb);
+      } else {
+        T.klow = ti.klow;
+      }
       T.chan = ti.chan0 + chant;
       T.row_lo = ti.row_lo;
       T.row_cnt = ti.row_cnt;
+      if (EPI != EPI_SCRATCH && NARROW) {   // the crop row range depends on the lane's row
+        const long long add = (1ll << p.log2nmul) - 1;
+        long long lo = (p.crop_start - (long long)T.nrest + add) >> p.log2nmul;
+        long long hi = (p.crop_stop - (long long)T.nrest + add) >> p.log2nmul;
+        lo = lo < 0 ? 0 : lo;
+        hi = hi > C::L ? C::L : hi;
+        T.row_lo = (unsigned)lo;
+        T.row_cnt = hi > lo ? (unsigned)(hi - lo) : 0u;
+      }
     }
-    if (MODE != MODE_MID && tid < RL) {
-      const float2 g = unit_root((unsigned long long)T.nrest * (unsigned)(C::KS * tid), p.log2M);
-      G4[tid] = make_float4(g.x, g.y, g.y, g.x);
+    if (MODE != MODE_MID) {
+      if (NARROW) {
+        for (int i = tid; i < RL * nrows; i += C::NT) {
+          const int j = i / RL, m = i - j * RL;
+          const float2 g =
+              unit_root((unsigned long long)(nrest0 + j) * (unsigned)(C::KS * m), p.log2M);
+          G4[i] = make_float4(g.x, g.y, g.y, g.x);
+        }
+      } else if (tid < RL) {
+        const float2 g = unit_root((unsigned long long)nrest0 * (unsigned)(C::KS * tid), p.log2M);
+        G4[tid] = make_float4(g.x, g.y, g.y, g.x);
+      }
     }
     if (MODE == MODE_INV) __syncthreads();  // INV consumes G in its first phase
     // every thread has copied *sinfo by the first barrier of this tile; thread 0 then prepares
@@ -488,7 +545,7 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
         for (int i = 0; i < RL; ++i) v[i] = lds_c2(tile, last_idx<C>(b, i, pr));
         Butterfly<RL, SIGNINV>::run(v);
         const int klo = klo_of<C>(b);
-        level_twiddle<RL, SIGNINV>(p, v, T.nrest, (unsigned)klo, G4);
+        level_twiddle<RL, SIGNINV>(p, v, T.nrest, (unsigned)klo, G4t);
 #pragma unroll
         for (int i = 0; i < RL; ++i) fast_store_c64(T, (unsigned)(klo + i * C::KS), rb_out, v[i]);
       }
@@ -506,7 +563,7 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
 #pragma unroll
         for (int i = 0; i < RL; ++i) v[i] = lds_c2(tile, last_idx<C>(b, i, pr));
         Butterfly<RL, false>::run(v);
-        fast_chirp<RL, C>(p, T, v, klo_of<C>(b));
+        fast_chirp<RL, C, TWOCH>(p, T, v, klo_of<C>(b));
         Butterfly<RL, true>::run(v);
 #pragma unroll
         for (int i = 0; i < RL; ++i) sts_c2(tile, last_idx<C>(b, i, pr), v[i]);
@@ -524,7 +581,7 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
         c2 v[RL];
 #pragma unroll
         for (int i = 0; i < RL; ++i) v[i] = fast_load<LK_PLANAR>(T, (unsigned)(klo + i * C::KS), rb_in);
-        level_twiddle<RL, true>(p, v, T.nrest, (unsigned)klo, G4);
+        level_twiddle<RL, true>(p, v, T.nrest, (unsigned)klo, G4t);
         Butterfly<RL, true>::run(v);
 #pragma unroll
         for (int i = 0; i < RL; ++i) sts_c2(tile, last_idx<C>(b, i, pr), v[i]);

@@ -16,23 +16,34 @@ static void cfg_info(FastInfo* info) {
   info->smem = C::SMEM_BYTES;
 }
 
-template <int MODE, class C, int LOADK, int EPI>
-static cudaError_t cfg_launch_mode(const PassArgs& a, const float2* d_tables, long long ntiles,
-                                   int num_sms, cudaStream_t st) {
-  auto kern = fast_pass_kernel<MODE, C, LOADK, EPI>;
+template <int MODE, class C, int LOADK, int EPI, bool TWOCH, bool NARROW>
+static cudaError_t cfg_launch_variant(const PassArgs& a, const float2* d_tables, long long ntiles,
+                                      int num_sms, cudaStream_t st) {
+  auto kern = fast_pass_kernel<MODE, C, LOADK, EPI, TWOCH, NARROW>;
+  constexpr size_t smem = C::smem_bytes(NARROW);
   static bool attr_done[16] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 16 && !attr_done[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)C::SMEM_BYTES);
+                                         (int)smem);
     if (e != cudaSuccess) return e;
     attr_done[dev] = true;
   }
   const long long resident = (long long)num_sms * C::MINB;
   const unsigned grid = (unsigned)std::min<long long>(ntiles - a.tile0, resident);
-  kern<<<grid, C::NT, C::SMEM_BYTES, st>>>(a, d_tables, ntiles);
+  kern<<<grid, C::NT, smem, st>>>(a, d_tables, ntiles);
   return cudaGetLastError();
+}
+
+// NARROW (arrays with fewer lanes per row than the tile is wide) is a separate instantiation so
+// that the common wide case keeps tile-uniform bookkeeping
+template <int MODE, class C, int LOADK, int EPI, bool TWOCH = false>
+static cudaError_t cfg_launch_mode(const PassArgs& a, const float2* d_tables, long long ntiles,
+                                   int num_sms, cudaStream_t st) {
+  if (a.I < C::W)
+    return cfg_launch_variant<MODE, C, LOADK, EPI, TWOCH, true>(a, d_tables, ntiles, num_sms, st);
+  return cfg_launch_variant<MODE, C, LOADK, EPI, TWOCH, false>(a, d_tables, ntiles, num_sms, st);
 }
 
 // inverse passes always read the scratch array; a MID pass reads the user's complex64 input only
@@ -49,6 +60,16 @@ static cudaError_t cfg_launch(int mode, const PassArgs& a, const float2* d_table
                                                                     st);
       return cfg_launch_mode<MODE_FWD, C, LK_C64, EPI_SCRATCH>(a, d_tables, ntiles, num_sms, st);
     case MODE_MID:
+      if (a.P == 1) {   // single-polarisation data: a lane pair is two channels
+        if (!a.final_epi)
+          return cfg_launch_mode<MODE_MID, C, LK_PLANAR, EPI_SCRATCH, true>(a, d_tables, ntiles,
+                                                                            num_sms, st);
+        if (a.epi_kind == EPI_C64)
+          return cfg_launch_mode<MODE_MID, C, LK_C64, EPI_C64, true>(a, d_tables, ntiles, num_sms,
+                                                                     st);
+        return cfg_launch_mode<MODE_MID, C, LK_C64, EPI_INTENSITY, true>(a, d_tables, ntiles,
+                                                                         num_sms, st);
+      }
       if (!a.final_epi)
         return cfg_launch_mode<MODE_MID, C, LK_PLANAR, EPI_SCRATCH>(a, d_tables, ntiles, num_sms,
                                                                     st);

@@ -1,0 +1,16 @@
+// Fast pass kernels for tiles of 2^10 points (1024 pts x 8 lanes); one translation unit per tile length so
+// that the units build in parallel.
+#include "pbk_fast_inst.cuh"
+
+namespace pbk {
+
+using Cfg = FastCfg<4, 16, 16, 1, 2, 256, 2>;
+
+void fast_info_l10(FastInfo* info) { cfg_info<Cfg>(info); }
+void fast_tables_l10(float2* dst) { fast_build_tables<Cfg>(dst); }
+cudaError_t fast_launch_l10(int mode, const PassArgs& a, const float2* d_tables, long long ntiles,
+                            int num_sms, cudaStream_t st) {
+  return cfg_launch<Cfg>(mode, a, d_tables, ntiles, num_sms, st);
+}
+
+}  // namespace pbk
