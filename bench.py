@@ -420,8 +420,8 @@ def run_b200(args, w):
                "h2d_bytes_per_step": int(hnp.nbytes), "d2h_bytes_per_step": rbytes,
                "steps": ke, "ms_per_step": dts / ke * 1e3,
                "api": "pulsarbat_b200.streaming.dedisperse_blocks(pinned numpy blocks): H2D of "
-                      "block i+1 overlaps the kernels of block i; plan creation inside the timed "
-                      "region",
+                      "block i+1 overlaps the kernels of block i (plan and buffers cached after the "
+                      "warm-up stream)",
                "single_call": single}
         del hx, hnp, z
 

@@ -12,7 +12,26 @@ import numpy as np
 from . import _lib as L
 from . import kernels
 
-__all__ = ["dedisperse_blocks"]
+__all__ = ["dedisperse_blocks", "clear_stream_cache"]
+
+# the plan, device buffers, pinned result buffers, streams and events of the last stream shape:
+# allocating ~13 GB per call would otherwise cost several milliseconds per block
+_state = {"key": None, "val": None}
+
+
+def clear_stream_cache():
+    """Free the cached plan and buffers of :func:`dedisperse_blocks`."""
+    if _state["val"] is not None:
+        _state["val"][0].destroy()
+    _state["key"] = _state["val"] = None
+
+
+def _get_state(key, make):
+    if _state["key"] != key:
+        clear_stream_cache()
+        _state["val"] = make()
+        _state["key"] = key
+    return _state["val"]
 
 
 def dedisperse_blocks(blocks, *, dm, sample_rate_hz, chan_freq_hz, ref_freq_hz, crop=None,
@@ -43,66 +62,72 @@ def dedisperse_blocks(blocks, *, dm, sample_rate_hz, chan_freq_hz, ref_freq_hz, 
     if stop <= start:
         start, stop = 0, 0
     freqs = np.ascontiguousarray(chan_freq_hz, dtype=np.float64)
-    plan = L.DedispPlan(nsamp=nsamp, nchan=nchan, npol=npol, dm=dm, sample_rate_hz=sample_rate_hz,
-                        ref_freq_hz=ref_freq_hz, chan_freq_hz=freqs, crop=(start, stop),
-                        in_dtype=L.PBK_I8X2 if int8 else L.PBK_C64, out_kind=out_kind,
-                        downsample=downsample, device=dev)
-    out_trailing = (nchan,) if out_kind == L.OUT_STOKES_I else (nchan,) + tuple(trailing)
-    out_shape = (plan.out_rows,) + out_trailing
-    out_t = torch.complex64 if out_kind == L.OUT_C64 else torch.float32
     in_t = torch.int8 if int8 else torch.complex64
-    try:
+    out_t = torch.complex64 if out_kind == L.OUT_C64 else torch.float32
+
+    def make():
+        plan = L.DedispPlan(nsamp=nsamp, nchan=nchan, npol=npol, dm=dm,
+                            sample_rate_hz=sample_rate_hz, ref_freq_hz=ref_freq_hz,
+                            chan_freq_hz=freqs, crop=(start, stop),
+                            in_dtype=L.PBK_I8X2 if int8 else L.PBK_C64, out_kind=out_kind,
+                            downsample=downsample, device=dev)
+        out_trailing = (nchan,) if out_kind == L.OUT_STOKES_I else (nchan,) + tuple(trailing)
+        out_shape = (plan.out_rows,) + out_trailing
         with torch.cuda.device(tdev):
-            d_in = [torch.empty(shape, dtype=in_t, device=tdev) for _ in range(2)]
-            d_out = [torch.empty(out_shape, dtype=out_t, device=tdev) for _ in range(2)]
-            h_out = [torch.empty(out_shape, dtype=out_t, pin_memory=True) for _ in range(2)]
-            s_copy, s_comp = torch.cuda.Stream(tdev), torch.cuda.Stream(tdev)
-            copied = [torch.cuda.Event() for _ in range(2)]
-            consumed = [torch.cuda.Event() for _ in range(2)]    # kernels done reading d_in[i]
-            done = [torch.cuda.Event() for _ in range(2)]        # result i is in h_out[i]
+            return (plan,
+                    [torch.empty(shape, dtype=in_t, device=tdev) for _ in range(2)],
+                    [torch.empty(out_shape, dtype=out_t, device=tdev) for _ in range(2)],
+                    [torch.empty(out_shape, dtype=out_t, pin_memory=True) for _ in range(2)],
+                    torch.cuda.Stream(tdev), torch.cuda.Stream(tdev),
+                    [torch.cuda.Event() for _ in range(6)])
 
-            def upload(block, slot, reuse):
-                hb = np.ascontiguousarray(block, dtype=first.dtype)
-                if hb.shape != shape:
-                    raise ValueError(f"block shape {hb.shape} differs from the first {shape}")
-                if reuse:
-                    s_copy.wait_event(consumed[slot])
-                # cudaMemcpyAsync straight from the caller's (ideally pinned) memory
-                L.check(L.lib().pbk_memcpy_async(d_in[slot].data_ptr(), hb.ctypes.data, hb.nbytes,
-                                                 1, dev, s_copy.cuda_stream))
-                copied[slot].record(s_copy)
-                return hb                                       # keep the host block alive
+    key = (shape, bool(int8), float(dm), float(sample_rate_hz), float(ref_freq_hz),
+           freqs.tobytes(), start, stop, int(out_kind), int(downsample), dev)
+    plan, d_in, d_out, h_out, s_copy, s_comp, ev = _get_state(key, make)
+    copied, consumed, done = ev[0:2], ev[2:4], ev[4:6]   # per slot: H2D done / kernels done / D2H done
+    s_copy.synchronize()      # an earlier, abandoned generator may have left work in flight
+    s_comp.synchronize()
 
-            def compute(slot):
-                with torch.cuda.stream(s_comp):
-                    s_comp.wait_event(copied[slot])
-                    plan.exec_device(d_in[slot].data_ptr(), d_out[slot].data_ptr(), None,
-                                     s_comp.cuda_stream)
-                    consumed[slot].record(s_comp)
-                    L.check(L.lib().pbk_memcpy_async(h_out[slot].data_ptr(), d_out[slot].data_ptr(),
-                                                     h_out[slot].numel() * h_out[slot].element_size(),
-                                                     0, dev, s_comp.cuda_stream))
-                    done[slot].record(s_comp)
+    def upload(block, slot, reuse):
+        hb = np.ascontiguousarray(block, dtype=first.dtype)
+        if hb.shape != shape:
+            raise ValueError(f"block shape {hb.shape} differs from the first {shape}")
+        if reuse:
+            s_copy.wait_event(consumed[slot])
+        # cudaMemcpyAsync straight from the caller's (ideally pinned) memory
+        L.check(L.lib().pbk_memcpy_async(d_in[slot].data_ptr(), hb.ctypes.data, hb.nbytes, 1, dev,
+                                         s_copy.cuda_stream))
+        copied[slot].record(s_copy)
+        return hb                                             # keeps the host block alive
 
-            keep = [None, None]
-            keep[0] = upload(first, 0, False)
-            i = 0
+    def compute(slot):
+        s_comp.wait_event(copied[slot])
+        plan.exec_device(d_in[slot].data_ptr(), d_out[slot].data_ptr(), None, s_comp.cuda_stream)
+        consumed[slot].record(s_comp)
+        L.check(L.lib().pbk_memcpy_async(h_out[slot].data_ptr(), d_out[slot].data_ptr(),
+                                         h_out[slot].numel() * h_out[slot].element_size(), 0, dev,
+                                         s_comp.cuda_stream))
+        done[slot].record(s_comp)
+
+    def result(slot):
+        done[slot].synchronize()
+        r = h_out[slot].numpy()
+        return r if pinned_out else r.copy()
+
+    with torch.cuda.device(tdev):
+        keep = [upload(first, 0, False), None]
+        i = 0
+        nxt = next(it, None)
+        while True:
+            slot = i & 1
+            if nxt is not None:
+                keep[slot ^ 1] = upload(nxt, slot ^ 1, i >= 1)
+            compute(slot)
+            if i >= 1:
+                yield result(slot ^ 1)
+            if nxt is None:
+                yield result(slot)
+                break
+            i += 1
             nxt = next(it, None)
-            while True:
-                slot = i & 1
-                if nxt is not None:
-                    keep[slot ^ 1] = upload(nxt, slot ^ 1, i >= 1)
-                compute(slot)
-                if i >= 1:
-                    done[slot ^ 1].synchronize()
-                    r = h_out[slot ^ 1].numpy()
-                    yield r if pinned_out else r.copy()
-                if nxt is None:
-                    done[slot].synchronize()
-                    r = h_out[slot].numpy()
-                    yield r if pinned_out else r.copy()
-                    break
-                i += 1
-                nxt = next(it, None)
-    finally:
-        plan.destroy()
+    del keep
