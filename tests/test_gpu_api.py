@@ -288,3 +288,34 @@ def test_fold_across_polyco_spans():
     assert np.array_equal(counts, np.bincount(ref_bins, minlength=nbin))
     inside = prof[12:16, 0].sum()
     assert inside / prof.sum() > 0.999 and prof.sum() == pytest.approx(x.sum(), rel=1e-6)
+
+
+def test_explicit_chirp_equals_generated_chirp():
+    """reference tests/test_dedispersion.py:141-164 through the public API: the chirp returned by
+    ``DM.chirp_from_signal`` passed back as ``chirp=`` gives the same result as the generated one,
+    for every reference frequency, also when squeezed to 2-D; and it matches the oracle's
+    complex64 chirp of dedispersion.py:19-23."""
+    import pulsarbat_b200 as pb
+    u = pb.units
+    rng = np.random.default_rng(5)
+    shape = (8192, 4, 2)
+    x = crandn(rng, shape)
+    z = pb.DualPolarizationSignal(x, sample_rate=1e6 * u.Hz, center_freq=1e9 * u.Hz,
+                                  pol_type="linear")
+    dm = pb.DM(10.0)
+    for rf in [z.center_freq, z.min_freq, z.max_freq]:
+        chirp = dm.chirp_from_signal(z, ref_freq=rf)
+        assert chirp.shape == (8192, 4, 1) and chirp.dtype == np.complex64
+        want_c = orc.chirp_from_signal(10.0, 8192, 1e6, z.channel_freqs_hz,
+                                       float(u.to_value(rf, u.Hz)))
+        assert np.max(np.abs(chirp[:, :, 0] - want_c)) < 2e-6
+        y1 = pb.coherent_dedispersion(z, dm, ref_freq=rf)
+        y2 = pb.coherent_dedispersion(z, dm, ref_freq=rf, chirp=chirp)
+        y3 = pb.coherent_dedispersion(z, dm, ref_freq=rf, chirp=chirp[:, :, 0])
+        assert y1.shape == y2.shape == y3.shape
+        assert relerr(np.asarray(y2.data), np.asarray(y1.data)) < 2e-6
+        assert np.array_equal(np.asarray(y3.data), np.asarray(y2.data))
+    one = dm.chirp_function(8192, z.dt, z.channel_freqs[0], z.center_freq)
+    assert one.shape == (8192,)
+    assert np.max(np.abs(one - orc.transfer_function(10.0, 8192, 1e6, z.channel_freqs_hz[0],
+                                                     1e9))) < 2e-6
