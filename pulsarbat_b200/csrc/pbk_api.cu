@@ -391,10 +391,14 @@ static int setup_fast(pbk_plan* pl) {
   std::vector<float2> host;
   for (auto& ps : pl->passes) {
     ps.family = -1;
-    if (fam < 0 || !ps.pair_ok || ps.signinv || ps.a.fxor || ps.a.kxor) continue;
-    // the fast kernels are specialised to the dedispersion passes (see pbk_fast.cuh)
-    if (ps.a.scale != 1.0f && ps.mode != MODE_MID) continue;
-    if (ps.mode != MODE_MID && ps.a.log2M == 0) continue;
+    if (fam < 0 || !ps.pair_ok || ps.signinv || ps.a.fxor) continue;
+    // the fast kernels are specialised to the dedispersion passes (see pbk_fast.cuh) plus the
+    // last pass of a forward FFT / STFT plan (FWD-last: no level twiddle, scale, fftshift)
+    const bool fwd_last = ps.mode == MODE_FWD && ps.a.log2M == 0 && ps.out_role == ROLE_USER_OUT &&
+                          pl->kind == PLAN_FFT && ps.a.load_kind != LOAD_I8X2;
+    if (ps.a.kxor && !fwd_last) continue;
+    if (ps.a.scale != 1.0f && ps.mode != MODE_MID && !fwd_last) continue;
+    if (ps.mode != MODE_MID && ps.a.log2M == 0 && !fwd_last) continue;
     if (ps.mode == MODE_MID && (ps.a.chirp_kind != CHIRP_COMPUTED || ps.a.load_kind == LOAD_I8X2 ||
                                 !pl->chirp_series_ok))
       continue;
@@ -406,9 +410,24 @@ static int setup_fast(pbk_plan* pl) {
     // a tile is W adjacent lanes: inside one row of the (.., I) array (I % W == 0), or, for arrays
     // with few channels, W / I whole rows (consecutive time offsets / consecutive kprev blocks)
     const bool wide = ps.a.I % W == 0 && W % ps.a.P == 0;
+    // (last-level passes -- MID, FWD-last -- have RI == I: their tiles then span W / I consecutive
+    // kprev blocks, which must not run over into the next outer block)
+    const bool lastlevel = ps.mode == MODE_MID || fwd_last;
     const bool narrow = ps.a.I < W && W % ps.a.I == 0 && ps.a.I % 2 == 0 &&
-                        (ps.mode == MODE_MID ? pl->kind == PLAN_DEDISP : ps.a.RI % W == 0);
+                        (lastlevel ? (1ll << ps.a.log2Kprev) % (W / ps.a.I) == 0
+                                   : ps.a.RI % W == 0);
     if (!(wide || narrow) || ps.a.Q % W) continue;
+    if (fwd_last) {
+      // output addressing: either the lane pair is adjacent in the output and rows are strided
+      // (plain FFT, multi-level STFT of few channels), or every pair owns a contiguous run of rows
+      // (single-level STFT: transposed through shared memory)
+      const AddrMap& mo = ps.a.mout;
+      const bool rows_contig = mo.a_row == 2 && ps.a.P == 2 && mo.a_p == 1;
+      if (mo.a_row * 8 >= (1ll << 32)) continue;
+      ps.a.out_transpose = (rows_contig && !narrow) ? 1 : 0;
+      ps.a.final_epi = 1;
+      ps.a.epi_kind = EPI_C64;
+    }
     if (ps.a.min.a_row * 8 >= (1ll << 32) || ps.a.mout.a_row * 8 >= (1ll << 32)) continue;
     ps.family = fam;
     ps.finfo = fi;

@@ -468,8 +468,12 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
   const int nrows = NARROW ? C::W / p.I : 1;
   const int jr = NARROW ? (2 * pr) / p.I : 0;
   const int colt = NARROW ? (2 * pr) % p.I : 2 * pr;
-  const long long row_in = MODE == MODE_MID ? p.min.a_kp : p.min.a_n;
-  const long long row_out = MODE == MODE_MID ? p.mout.a_kp : p.mout.a_n;
+  // FWDLAST: the last pass of a plain forward FFT / STFT (no inter-level twiddle; scaled,
+  // optionally fftshift-ed, natural-order complex64 written to the user's array)
+  constexpr bool FWDLAST = MODE == MODE_FWD && EPI != EPI_SCRATCH;
+  constexpr bool LASTLEVEL = MODE == MODE_MID || FWDLAST;   // rows of lanes are kprev blocks
+  const long long row_in = LASTLEVEL ? p.min.a_kp : p.min.a_n;
+  const long long row_out = LASTLEVEL ? p.mout.a_kp : p.mout.a_n;
   const long long off_in =
       (jr * row_in + (long long)(colt / p.P) * p.min.a_c + (colt % p.P) * p.min.a_p) * in_eb;
   const long long off_out =
@@ -489,17 +493,19 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
       T.gin = reinterpret_cast<const char*>(p.in) + ti.bi + off_in;
       T.gout = reinterpret_cast<char*>(p.out) + ti.bo + off_out;
       nrest0 = ti.nrest;
-      T.nrest = ti.nrest + (MODE == MODE_MID ? 0 : jr);
-      if (MODE == MODE_MID && NARROW) {
+      T.nrest = ti.nrest + (LASTLEVEL ? 0 : jr);
+      if (LASTLEVEL && NARROW) {
         const unsigned kprev = ti.kprev + jr;
         T.klow = (kprev >> p.kl_sa) + ((kprev & p.kl_mb) << p.kl_sb);
+        if (FWDLAST)   // natural-order output: the low part of the frequency index is per lane row
+          T.gout += ((long long)T.klow - (long long)ti.klow) * p.mout.a_kl * out_eb;
       } else {
         T.klow = ti.klow;
       }
       T.chan = ti.chan0 + chant;
       T.row_lo = ti.row_lo;
       T.row_cnt = ti.row_cnt;
-      if (EPI != EPI_SCRATCH && NARROW) {   // the crop row range depends on the lane's row
+      if (EPI != EPI_SCRATCH && NARROW && !FWDLAST) {   // the crop row range depends on the lane's row
         const long long add = (1ll << p.log2nmul) - 1;
         long long lo = (p.crop_start - (long long)T.nrest + add) >> p.log2nmul;
         long long hi = (p.crop_stop - (long long)T.nrest + add) >> p.log2nmul;
@@ -509,7 +515,7 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
         T.row_cnt = hi > lo ? (unsigned)(hi - lo) : 0u;
       }
     }
-    if (MODE != MODE_MID) {
+    if (MODE != MODE_MID && !FWDLAST) {
       if (NARROW) {
         for (int i = tid; i < RL * nrows; i += C::NT) {
           const int j = i / RL, m = i - j * RL;
@@ -535,19 +541,75 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
       __syncthreads();
       PBK_NEXT_TILE_INFO();
       mid_stages<C, false, SIGNINV>(tile, tws, tid);
+      if constexpr (!FWDLAST) {
 #pragma unroll
-      for (int it = 0; it < LITERS; ++it) {
-        const int tau = tid + it * C::NT;
-        if (LTASKS % C::NT != 0 && tau >= LTASKS) break;
-        const int b = tau >> C::LOG2PW;
-        c2 v[RL];
+        for (int it = 0; it < LITERS; ++it) {
+          const int tau = tid + it * C::NT;
+          if (LTASKS % C::NT != 0 && tau >= LTASKS) break;
+          const int b = tau >> C::LOG2PW;
+          c2 v[RL];
 #pragma unroll
-        for (int i = 0; i < RL; ++i) v[i] = lds_c2(tile, last_idx<C>(b, i, pr));
-        Butterfly<RL, SIGNINV>::run(v);
-        const int klo = klo_of<C>(b);
-        level_twiddle<RL, SIGNINV>(p, v, T.nrest, (unsigned)klo, G4t);
+          for (int i = 0; i < RL; ++i) v[i] = lds_c2(tile, last_idx<C>(b, i, pr));
+          Butterfly<RL, SIGNINV>::run(v);
+          const int klo = klo_of<C>(b);
+          level_twiddle<RL, SIGNINV>(p, v, T.nrest, (unsigned)klo, G4t);
 #pragma unroll
-        for (int i = 0; i < RL; ++i) fast_store_c64(T, (unsigned)(klo + i * C::KS), rb_out, v[i]);
+          for (int i = 0; i < RL; ++i) fast_store_c64(T, (unsigned)(klo + i * C::KS), rb_out, v[i]);
+        }
+      } else {
+        // last pass of a forward FFT / STFT: no level twiddle; scale, fftshift (row xor) and
+        // natural-order complex64 to the user's array
+        static_assert(!FWDLAST || LTASKS % C::NT == 0, "whole last-stage tasks per thread");
+        c2 v[LITERS][RL];
+        int klo[LITERS];
+        const float2 sc = p_bc(p.scale);
+#pragma unroll
+        for (int it = 0; it < LITERS; ++it) {
+          const int b = (tid + it * C::NT) >> C::LOG2PW;
+#pragma unroll
+          for (int i = 0; i < RL; ++i) v[it][i] = lds_c2(tile, last_idx<C>(b, i, pr));
+          Butterfly<RL, SIGNINV>::run(v[it]);
+          klo[it] = klo_of<C>(b);
+#pragma unroll
+          for (int i = 0; i < RL; ++i) {
+            v[it][i].re = p_mul(v[it][i].re, sc);
+            v[it][i].im = p_mul(v[it][i].im, sc);
+          }
+        }
+        if (!p.out_transpose) {
+          // output lanes are adjacent in memory: one natural-order 16-byte store per row
+#pragma unroll
+          for (int it = 0; it < LITERS; ++it)
+#pragma unroll
+            for (int i = 0; i < RL; ++i) {
+              const unsigned row = (unsigned)(klo[it] + i * C::KS) ^ (unsigned)p.kxor;
+              *reinterpret_cast<float4*>(T.gout + (unsigned long long)row * rb_out) =
+                  make_float4(v[it][i].re.x, v[it][i].im.x, v[it][i].re.y, v[it][i].im.y);
+            }
+        } else {
+          // STFT output (misc.py:50): every lane pair owns a CONTIGUOUS run of L rows and the
+          // pairs are far apart, so the tile is transposed through shared memory and copied out
+          // with consecutive threads on consecutive rows
+          __syncthreads();                       // all last-stage reads of the tile are done
+#pragma unroll
+          for (int it = 0; it < LITERS; ++it)
+#pragma unroll
+            for (int i = 0; i < RL; ++i) {
+              const int k = (klo[it] + i * C::KS) ^ p.kxor;
+              tile[pr * C::L + (k ^ (pr & 7))] =
+                  make_float4(v[it][i].re.x, v[it][i].im.x, v[it][i].re.y, v[it][i].im.y);
+            }
+          __syncthreads();
+          char* gt = T.gout - off_out;           // tile base (lane pair 0)
+          for (int j = tid; j < C::PW * C::L; j += C::NT) {
+            const int pair = j >> C::LOG2L, kk = j & (C::L - 1);
+            const int cp = 2 * pair;
+            const long long po =
+                ((long long)(cp / p.P) * p.mout.a_c + (cp % p.P) * p.mout.a_p) * out_eb;
+            *reinterpret_cast<float4*>(gt + po + (unsigned long long)kk * rb_out) =
+                tile[pair * C::L + (kk ^ (pair & 7))];
+          }
+        }
       }
     } else if (MODE == MODE_MID) {
       fwd_first<C, LOADK>(T, tile, tws, tid, rb_in);

@@ -53,6 +53,11 @@ static cudaError_t cfg_launch(int mode, const PassArgs& a, const float2* d_table
                               long long ntiles, int num_sms, cudaStream_t st) {
   switch (mode) {
     case MODE_FWD:
+      if (a.final_epi) {   // last pass of a forward FFT / STFT plan: scaled natural-order output
+        if (a.load_kind == LOAD_PLANAR)
+          return cfg_launch_mode<MODE_FWD, C, LK_PLANAR, EPI_C64>(a, d_tables, ntiles, num_sms, st);
+        return cfg_launch_mode<MODE_FWD, C, LK_C64, EPI_C64>(a, d_tables, ntiles, num_sms, st);
+      }
       if (a.load_kind == LOAD_I8X2)
         return cfg_launch_mode<MODE_FWD, C, LK_I8, EPI_SCRATCH>(a, d_tables, ntiles, num_sms, st);
       if (a.load_kind == LOAD_PLANAR)

@@ -71,6 +71,7 @@ struct PassArgs {
   int log2nmul;       // n_mul = 2^log2nmul (fast kernels)
   int final_epi;      // this pass writes the user-visible output (crop + epilogue kind apply)
   int store_planar;   // output is the scratch array in pair-planar form {re0,re1,im0,im1}
+  int out_transpose;  // fast FWD-last pass: lane pairs own contiguous runs of rows in the output
   // chirp
   int chirp_kind;
   int log2Kmul;       // kfull = klow + (k << log2Kmul)
