@@ -78,6 +78,7 @@ struct Pass {
   int mode = MODE_FWD;
   bool fast = false;      // uniform lane pairs (same time offset AND channel): vector generic path
   bool pair_ok = false;   // lane pairs usable by the fast family (P even, or P == 1: two channels)
+  bool fast_load_transposed = false;   // fast FWD pass reads its tile through the transposing loader
   bool signinv = false;
   int in_role = ROLE_USER_IN, out_role = ROLE_SCRATCH;
   PassArgs a;
@@ -391,12 +392,18 @@ static int setup_fast(pbk_plan* pl) {
   std::vector<float2> host;
   for (auto& ps : pl->passes) {
     ps.family = -1;
-    if (fam < 0 || !ps.pair_ok || ps.signinv || ps.a.fxor) continue;
+    if (fam < 0 || !ps.pair_ok) continue;
+    if (ps.signinv && (ps.mode != MODE_FWD || pl->kind != PLAN_FFT)) continue;
     // the fast kernels are specialised to the dedispersion passes (see pbk_fast.cuh) plus the
     // last pass of a forward FFT / STFT plan (FWD-last: no level twiddle, scale, fftshift)
     const bool fwd_last = ps.mode == MODE_FWD && ps.a.log2M == 0 && ps.out_role == ROLE_USER_OUT &&
                           pl->kind == PLAN_FFT && ps.a.load_kind != LOAD_I8X2;
     if (ps.a.kxor && !fwd_last) continue;
+    // ifftshift on the load rows (ISTFT first pass) is only done by the transposed loader, whose
+    // tile is a whole level: single-level plans whose lane pairs own contiguous runs of rows
+    const bool in_rows_contig = ps.a.min.a_row == 2 && ps.a.P == 2 && ps.a.min.a_p == 1 &&
+                                ps.in_role == ROLE_USER_IN && ps.a.load_kind == LOAD_C64;
+    if (ps.a.fxor && !(fwd_last && in_rows_contig)) continue;
     if (ps.a.scale != 1.0f && ps.mode != MODE_MID && !fwd_last) continue;
     if (ps.mode != MODE_MID && ps.a.log2M == 0 && !fwd_last) continue;
     if (ps.mode == MODE_MID && (ps.a.chirp_kind != CHIRP_COMPUTED || ps.a.load_kind == LOAD_I8X2 ||
@@ -427,6 +434,12 @@ static int setup_fast(pbk_plan* pl) {
       ps.a.out_transpose = (rows_contig && !narrow) ? 1 : 0;
       ps.a.final_epi = 1;
       ps.a.epi_kind = EPI_C64;
+      if (in_rows_contig && ps.a.min.a_c != ps.a.P) {   // ISTFT input: pairs far apart
+        if (narrow) continue;
+        ps.fast_load_transposed = true;
+      }
+    } else if (in_rows_contig && ps.a.min.a_c != ps.a.P) {
+      continue;   // would need the transposed loader in a non-final pass
     }
     if (ps.a.min.a_row * 8 >= (1ll << 32) || ps.a.mout.a_row * 8 >= (1ll << 32)) continue;
     ps.family = fam;
@@ -785,9 +798,11 @@ static int launch_one(pbk_plan* pl, const Pass& ps, const void* d_in, void* d_ou
   p.a.tile0 = tile0;
   const bool aligned = (((uintptr_t)p.a.in | (uintptr_t)p.a.out) & 15) == 0;
   cudaError_t e;
-  if (ps.family >= 0 && aligned)
+  if (ps.family >= 0 && aligned) {
+    if (ps.fast_load_transposed) p.a.load_kind = LOAD_TRANSP;
     e = fast_launch(ps.family, ps.a.log2L, ps.mode, p.a, pl->d_ftab + ps.ftab_off,
                     tile_end < 0 ? ps.ntiles : tile_end, pl->num_sms, st);
+  }
   else
     e = launch_pass(p, ps.fast && aligned, st);
   if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));

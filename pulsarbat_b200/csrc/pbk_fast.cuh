@@ -150,7 +150,9 @@ constexpr int EPI_SCRATCH = 3;   // not a final pass: pair-planar complex64 to t
 // how a pass reads its input: user complex64 (re,im interleaved), user int8 pairs, or the scratch
 // array, where each 16-byte lane pair is stored as {re0, re1, im0, im1} ("pair-planar") so that a
 // 128-bit access is exactly the packed register layout of c2 and needs no shuffling
-enum { LK_C64 = 0, LK_I8 = 1, LK_PLANAR = 2 };
+enum { LK_C64 = 0, LK_I8 = 1, LK_PLANAR = 2,
+       LK_TRANSP = 3 /* user complex64 where every lane pair owns a contiguous run of rows
+                        (ISTFT input): transposed through shared memory */ };
 
 // everything about a tile that is uniform across the CTA; computed by one thread (the address
 // arithmetic has 64-bit divisions) and broadcast through shared memory
@@ -339,10 +341,9 @@ __device__ __forceinline__ void fast_chirp(const PassArgs& p, const FastTile& T,
 // stages
 // ------------------------------------------------------------------------------------------
 // first forward stage: global -> registers -> smem (DIF, stage table 0)
-template <class C, int LOADK>
+template <class C, int LOADK, bool SIGNINV = false>
 __device__ __forceinline__ void fwd_first(const FastTile& T, float4* tile, const float2* tws,
                                           int tid, unsigned rowbytes_in) {
-  constexpr bool SIGNINV = false;
   constexpr int R = C::radix(0), S = C::stride(0);
   constexpr int TASKS = S * C::PW;
   constexpr int ITERS = (TASKS + C::NT - 1) / C::NT;
@@ -359,6 +360,50 @@ __device__ __forceinline__ void fwd_first(const FastTile& T, float4* tile, const
     stage_twiddle<R, S, SIGNINV>(v, tws + C::tw_off(0), b);
 #pragma unroll
     for (int i = 0; i < R; ++i) sts_c2(tile, (phys_pt<C, S>(b, i) << C::LOG2PW) + pr, v[i]);
+  }
+}
+
+// first stage of a tile whose lane pairs each own a CONTIGUOUS run of L rows in global memory
+// while the pairs are far apart (ISTFT input, misc.py:81-86): the tile is copied in with
+// consecutive threads on consecutive rows, transposed through shared memory, then the stage runs
+// from there.  `fxor` is the ifftshift (row index xor) of the reference's np.fft.ifftshift.
+template <class C, bool SIGNINV>
+__device__ __forceinline__ void fwd_first_transposed(const PassArgs& p, const char* gin_tile,
+                                                     float4* tile, const float2* tws, int tid,
+                                                     unsigned rowbytes_in) {
+  constexpr int R = C::radix(0), S = C::stride(0);
+  constexpr int TASKS = S * C::PW;
+  static_assert(TASKS % C::NT == 0, "whole first-stage tasks per thread");
+  constexpr int ITERS = TASKS / C::NT;
+  const int pr = tid & (C::PW - 1);
+  for (int j = tid; j < C::PW * C::L; j += C::NT) {
+    const int pair = j >> C::LOG2L, kk = j & (C::L - 1);
+    const int cp = 2 * pair;
+    const long long po = ((long long)(cp / p.P) * p.min.a_c + (cp % p.P) * p.min.a_p) * 8;
+    tile[pair * C::L + (kk ^ (pair & 7))] =
+        __ldcg(reinterpret_cast<const float4*>(gin_tile + po + (unsigned long long)kk * rowbytes_in));
+  }
+  __syncthreads();
+  c2 v[ITERS][R];
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int b = (tid + it * C::NT) >> C::LOG2PW;
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const int row = (b + i * S) ^ p.fxor;
+      const float4 t = tile[pr * C::L + (row ^ (pr & 7))];
+      v[it][i].re = make_float2(t.x, t.z);
+      v[it][i].im = make_float2(t.y, t.w);
+    }
+  }
+  __syncthreads();   // every thread holds its inputs: the tile buffer can take the stage output
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int b = (tid + it * C::NT) >> C::LOG2PW;
+    Butterfly<R, SIGNINV>::run(v[it]);
+    stage_twiddle<R, S, SIGNINV>(v[it], tws + C::tw_off(0), b);
+#pragma unroll
+    for (int i = 0; i < R; ++i) sts_c2(tile, (phys_pt<C, S>(b, i) << C::LOG2PW) + pr, v[it][i]);
   }
 }
 
@@ -436,7 +481,8 @@ __device__ __forceinline__ void inv_last(const FastTile& T, float4* tile, const 
 // ------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------
-template <int MODE, class C, int LOADK, int EPI, bool TWOCH = false, bool NARROW = false>
+template <int MODE, class C, int LOADK, int EPI, bool TWOCH = false, bool NARROW = false,
+          bool SIGNINV = false>
 __global__ void __launch_bounds__(C::NT, C::MINB)
 fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ tables,
                  long long ntiles) {
@@ -449,7 +495,6 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
   const int tid = threadIdx.x;
   const int pr = tid & (C::PW - 1);
 
-  constexpr bool SIGNINV = false;
   constexpr int in_eb = LOADK == LK_I8 ? 2 : 8;
   constexpr int out_eb = (EPI == EPI_INTENSITY || EPI == EPI_STOKES_I) ? 4 : 8;
   const unsigned rb_in = (unsigned)(p.min.a_row * in_eb);
@@ -537,7 +582,10 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
     if (MODE == MODE_INV) PBK_NEXT_TILE_INFO();
 
     if (MODE == MODE_FWD) {
-      fwd_first<C, LOADK>(T, tile, tws, tid, rb_in);
+      if constexpr (LOADK == LK_TRANSP)
+        fwd_first_transposed<C, SIGNINV>(p, T.gin - off_in, tile, tws, tid, rb_in);
+      else
+        fwd_first<C, LOADK, SIGNINV>(T, tile, tws, tid, rb_in);
       __syncthreads();
       PBK_NEXT_TILE_INFO();
       mid_stages<C, false, SIGNINV>(tile, tws, tid);

@@ -16,10 +16,10 @@ static void cfg_info(FastInfo* info) {
   info->smem = C::SMEM_BYTES;
 }
 
-template <int MODE, class C, int LOADK, int EPI, bool TWOCH, bool NARROW>
+template <int MODE, class C, int LOADK, int EPI, bool TWOCH, bool NARROW, bool SIGNINV = false>
 static cudaError_t cfg_launch_variant(const PassArgs& a, const float2* d_tables, long long ntiles,
                                       int num_sms, cudaStream_t st) {
-  auto kern = fast_pass_kernel<MODE, C, LOADK, EPI, TWOCH, NARROW>;
+  auto kern = fast_pass_kernel<MODE, C, LOADK, EPI, TWOCH, NARROW, SIGNINV>;
   constexpr size_t smem = C::smem_bytes(NARROW);
   static bool attr_done[16] = {};
   int dev = 0;
@@ -38,12 +38,14 @@ static cudaError_t cfg_launch_variant(const PassArgs& a, const float2* d_tables,
 
 // NARROW (arrays with fewer lanes per row than the tile is wide) is a separate instantiation so
 // that the common wide case keeps tile-uniform bookkeeping
-template <int MODE, class C, int LOADK, int EPI, bool TWOCH = false>
+template <int MODE, class C, int LOADK, int EPI, bool TWOCH = false, bool SIGNINV = false>
 static cudaError_t cfg_launch_mode(const PassArgs& a, const float2* d_tables, long long ntiles,
                                    int num_sms, cudaStream_t st) {
   if (a.I < C::W)
-    return cfg_launch_variant<MODE, C, LOADK, EPI, TWOCH, true>(a, d_tables, ntiles, num_sms, st);
-  return cfg_launch_variant<MODE, C, LOADK, EPI, TWOCH, false>(a, d_tables, ntiles, num_sms, st);
+    return cfg_launch_variant<MODE, C, LOADK, EPI, TWOCH, true, SIGNINV>(a, d_tables, ntiles,
+                                                                         num_sms, st);
+  return cfg_launch_variant<MODE, C, LOADK, EPI, TWOCH, false, SIGNINV>(a, d_tables, ntiles,
+                                                                        num_sms, st);
 }
 
 // inverse passes always read the scratch array; a MID pass reads the user's complex64 input only
@@ -53,6 +55,23 @@ static cudaError_t cfg_launch(int mode, const PassArgs& a, const float2* d_table
                               long long ntiles, int num_sms, cudaStream_t st) {
   switch (mode) {
     case MODE_FWD:
+      if (a.sign > 0) {    // inverse exponent (ifft / ISTFT plans): conjugated butterflies and twiddles
+        if (a.final_epi) {
+          if (a.load_kind == LOAD_PLANAR)
+            return cfg_launch_mode<MODE_FWD, C, LK_PLANAR, EPI_C64, false, true>(a, d_tables, ntiles,
+                                                                                 num_sms, st);
+          if (a.load_kind == LOAD_TRANSP)
+            return cfg_launch_mode<MODE_FWD, C, LK_TRANSP, EPI_C64, false, true>(a, d_tables, ntiles,
+                                                                                 num_sms, st);
+          return cfg_launch_mode<MODE_FWD, C, LK_C64, EPI_C64, false, true>(a, d_tables, ntiles,
+                                                                            num_sms, st);
+        }
+        if (a.load_kind == LOAD_PLANAR)
+          return cfg_launch_mode<MODE_FWD, C, LK_PLANAR, EPI_SCRATCH, false, true>(a, d_tables,
+                                                                                   ntiles, num_sms, st);
+        return cfg_launch_mode<MODE_FWD, C, LK_C64, EPI_SCRATCH, false, true>(a, d_tables, ntiles,
+                                                                              num_sms, st);
+      }
       if (a.final_epi) {   // last pass of a forward FFT / STFT plan: scaled natural-order output
         if (a.load_kind == LOAD_PLANAR)
           return cfg_launch_mode<MODE_FWD, C, LK_PLANAR, EPI_C64>(a, d_tables, ntiles, num_sms, st);

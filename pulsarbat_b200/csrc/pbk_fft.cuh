@@ -33,7 +33,8 @@
 namespace pbk {
 
 enum { MODE_FWD = 0, MODE_MID = 1, MODE_INV = 2 };
-enum { LOAD_C64 = 0, LOAD_I8X2 = 1, LOAD_PLANAR = 2, LOAD_F32 = 3 /* real input, im = 0 */ };
+enum { LOAD_C64 = 0, LOAD_I8X2 = 1, LOAD_PLANAR = 2, LOAD_F32 = 3 /* real input, im = 0 */,
+       LOAD_TRANSP = 4 /* fast kernels only: complex64 input transposed through shared memory */ };
 enum { EPI_C64 = 0, EPI_INTENSITY = 1, EPI_STOKES_I = 2 };
 enum { CHIRP_NONE = 0, CHIRP_COMPUTED = 1, CHIRP_ARRAY = 2, CHIRP_RAMP = 3 };
 

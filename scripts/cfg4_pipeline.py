@@ -2,7 +2,7 @@
 -> fold into 1024 phase bins x 1024 channels; time slices sharded over ranks, ONE all-reduce of
 the folded profile and counts over NCCL.  Run with torchrun; prints one line of timings (rank 0).
 
-    python -m torch.distributed.run --nproc-per-node N scripts/cfg4_pipeline.py [log2_samples_per_rank]
+    python -m torch.distributed.run --nproc-per-node N scripts/cfg4_pipeline.py [log2_samples_per_rank [npol]]
 """
 import os
 import sys
@@ -26,12 +26,13 @@ if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 
 lg = int(sys.argv[1]) if len(sys.argv) > 1 else 26
+npol = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 n_per_rank, nper, fsum, nbin = 2 ** lg, 2 ** 16, 64, 1024
 sr = 400e6
 g = torch.Generator(device=dev)
 g.manual_seed(16 + rank)
-x = torch.randn((n_per_rank, 1, 2), device=dev, dtype=torch.float32, generator=g)
-xd = pb.DeviceArray(torch.view_as_complex(x))
+x = torch.randn((n_per_rank, 1, npol, 2), device=dev, dtype=torch.float32, generator=g)
+xd = pb.DeviceArray(torch.view_as_complex(x) if npol > 1 else torch.view_as_complex(x)[:, :, 0])
 coeffs = [0.123, 29.7, 1e-6]
 seg_per_rank = n_per_rank // nper
 
@@ -62,8 +63,8 @@ if world > 1:
 total = int(np.asarray(cnt).sum())
 if rank == 0:
     assert total == world * seg_per_rank, (total, world * seg_per_rank)
-    print(f"cfg4: {world} GPU(s) x 2^{lg} samples: {float(t.item()):.3f} ms per step -> "
-          f"{world * n_per_rank / float(t.item()) / 1e6:.1f} Gsamples/s; profile "
+    print(f"cfg4: {world} GPU(s) x 2^{lg} samples x {npol} pol: {float(t.item()):.3f} ms per step -> "
+          f"{world * n_per_rank * npol / float(t.item()) / 1e6:.1f} Gsamples/s; profile "
           f"{tuple(np.asarray(prof).shape)}, counts sum {total} (exact)", flush=True)
 if world > 1:
     dist.destroy_process_group()
