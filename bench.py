@@ -253,7 +253,9 @@ def run_b200(args, w):
                         in_dtype=L.PBK_I8X2 if w["int8"] else L.PBK_C64, out_kind=out_kind,
                         downsample=w["ds"], device=local)
     info = plan.info()
-    desc = plan.describe().split(";") + (["downsample"] if w["ds"] > 1 else [])
+    # the time sum is a separate launch unless the plan fused it into the last pass (":timesum")
+    sep_ds = w["ds"] > 1 and ":timesum" not in plan.describe()
+    desc = plan.describe().split(";") + (["downsample"] if sep_ds else [])
     desc = [f"{i}:{d}" for i, d in enumerate(desc)]      # unique names (two passes can look alike)
     K, W = args.steps, args.warmup
 
@@ -309,11 +311,12 @@ def run_b200(args, w):
     peak, peak_src = peaks()
     # every FFT pass reads the block once and writes it once: first pass reads the input dtype,
     # the last pass writes the output kind, the others move complex64 (8 B) both ways
-    npass = len(desc) - (1 if w["ds"] > 1 else 0)
+    npass = len(desc) - (1 if sep_ds else 0)
     rd = [in_bytes if i == 0 else nsamp * 8 for i in range(npass)]
     full_out = plan.row_elems * N * plan.elem_bytes
-    wr = [full_out if i == npass - 1 else nsamp * 8 for i in range(npass)]
-    if w["ds"] > 1:
+    wr = [(full_out if sep_ds or w["ds"] == 1 else out_bytes) if i == npass - 1 else nsamp * 8
+          for i in range(npass)]
+    if sep_ds:
         rd.append(full_out)
         wr.append(out_bytes)
     kbytes = rd[top] + wr[top]

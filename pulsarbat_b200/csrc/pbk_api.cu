@@ -114,6 +114,7 @@ struct pbk_plan {
   int num_sms = 148;
   void* d_tmpf = nullptr;       // pre-downsample float buffer
   size_t tmpf_bytes = 0;
+  bool fused_tsum = false;      // the time sum runs in the epilogue of the last pass (no d_tmpf)
   // lazily allocated staging buffers for *_host execution
   void* h_din = nullptr;
   void* h_dout = nullptr;
@@ -723,7 +724,25 @@ static int dedisp_plan_create_impl(const pbk_dedisp_desc* d, const RampSpec* ram
       return cleanup(fail(PBK_ERR_NOMEM, "scratch (%zu bytes): %s", pl->scratch_bytes,
                           cudaGetErrorString(e)));
   }
-  if (d->downsample > 1 && crop_rows > 0) {
+  // Time sum fused into the last inverse pass (fast_pass_kernel TSUM): power-of-two factor that
+  // divides the inner extent of the outermost level, groups aligned with the inner time offset
+  // (crop_start a multiple of the factor), wide tiles on the compile-time-shaped kernels.
+  if (d->downsample > 1 && pl->out_rows > 0 && m > 1 && !getenv("PBK_NO_FUSED_SUM")) {
+    Pass& last = pl->passes.back();
+    const int lm = ilog2_exact(d->downsample);
+    const long long W = 2ll << last.finfo.log2pw;
+    if (last.family >= 0 && last.mode == MODE_INV && lm > 0 && lm <= last.a.log2nmul &&
+        d->crop_start % d->downsample == 0 && I % W == 0 && W % P == 0 &&
+        last.finfo.tsum_ok) {
+      last.a.tsum_log2 = lm;
+      const long long ncg = I / W;   // column groups per row; q of them are read side by side
+      last.a.tsum_q = ncg % 4 == 0 ? 4 : ncg % 2 == 0 ? 2 : 1;
+      last.a.crop_stop = d->crop_start + pl->out_rows * d->downsample;
+      last.out_role = ROLE_USER_OUT;
+      pl->fused_tsum = true;
+    }
+  }
+  if (d->downsample > 1 && crop_rows > 0 && !pl->fused_tsum) {
     pl->tmpf_bytes = (size_t)crop_rows * pl->row_elems * 4;
     cudaError_t e = cudaMalloc(&pl->d_tmpf, pl->tmpf_bytes);
     if (e != cudaSuccess)
@@ -759,7 +778,7 @@ static int dedisp_plan_create_impl(const pbk_dedisp_desc* d, const RampSpec* ram
                                          : (d->sample_rate_hz / (double)N) / d->ref_freq_hz;
   }
   if (m == 3) setup_l2_blocking(pl, (N >> l[0]) * I * 8, 1 << l[0]);
-  const int ds = d->downsample > 1 ? 1 : 0;
+  const int ds = (d->downsample > 1 && !pl->fused_tsum) ? 1 : 0;
   if (pl->l2_chunks > 0) {
     pl->launches = 2 + 3 * pl->l2_chunks + ds;
     pl->segments = 3 + ds;
@@ -878,9 +897,11 @@ extern "C" int pbk_dedisp_exec_device(pbk_plan* pl, const void* d_in, void* d_ou
   CUDA_TRY(cudaSetDevice(pl->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (pl->blue) return blue_exec(pl, d_in, d_out, d_chirp, st);
+  if (pl->fused_tsum)   // the last pass adds its group sums to the output
+    CUDA_TRY(cudaMemsetAsync(d_out, 0, pl->out_bytes, st));
   int rc = run_passes(pl, d_in, d_out, d_chirp, st);
   if (rc != PBK_OK) return rc;
-  if (pl->desc.downsample > 1) {
+  if (pl->desc.downsample > 1 && !pl->fused_tsum) {
     cudaError_t e = launch_downsample(reinterpret_cast<const float*>(pl->d_tmpf),
                                       reinterpret_cast<float*>(d_out), pl->out_rows,
                                       pl->row_elems, pl->desc.downsample, st);
@@ -1374,9 +1395,10 @@ extern "C" int pbk_plan_describe(const pbk_plan* pl, char* buf, size_t n) {
     const bool blocked = pl->l2_chunks > 0;
     const char* sep = i == 0 ? "" : (blocked && (i == 2 || i == 3)) ? "+" : ";";
     if (ps.family >= 0)
-      w = snprintf(buf + off, n - off, "%s%s:L=2^%d:%s:W=%d:tiles=%lld:threads=%d", sep,
+      w = snprintf(buf + off, n - off, "%s%s:L=2^%d:%s:W=%d:tiles=%lld:threads=%d%s", sep,
                    mode, ps.a.log2L, "fast-r16",
-                   2 << ps.finfo.log2pw, ps.ntiles, ps.finfo.threads);
+                   2 << ps.finfo.log2pw, ps.ntiles, ps.finfo.threads,
+                   ps.a.tsum_log2 > 0 ? ":timesum" : "");
     else
       w = snprintf(buf + off, n - off, "%s%s:L=2^%d:%s:W=%d:tiles=%u:threads=%d", sep,
                    mode, ps.a.log2L, ps.fast ? "generic-vec" : "generic", 2 << ps.a.log2pw,

@@ -18,6 +18,8 @@
 // |f - fc| <= fc/16.  Everything else runs on the generic kernel in pbk_fft.cuh, which is the
 // same algorithm with runtime tile parameters.
 #pragma once
+#include <type_traits>
+
 #include "pbk_fft.cuh"
 
 namespace pbk {
@@ -478,11 +480,95 @@ __device__ __forceinline__ void inv_last(const FastTile& T, float4* tile, const 
   }
 }
 
+// last inverse stage of a TSUM pass: the detected power of every surviving row is added to the
+// thread's running sums instead of being stored (one accumulator per tile row the thread owns;
+// consecutive tiles of a TSUM CTA are consecutive time offsets of the same columns)
+template <class C, int EPI>
+struct TsumAcc {
+  static constexpr int R = C::radix(0);
+  static constexpr int ITERS = (C::stride(0) * C::PW + C::NT - 1) / C::NT;
+  using acc_t = typename std::conditional<EPI == EPI_STOKES_I, float, float2>::type;
+  acc_t a[ITERS][R];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it)
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        if constexpr (EPI == EPI_STOKES_I) a[it][i] = 0.f;
+        else a[it][i] = make_float2(0.f, 0.f);
+      }
+  }
+};
+
+template <class C, int EPI>
+__device__ __forceinline__ void inv_last_sum(const FastTile& T, float4* tile, const float2* tws,
+                                             int tid, TsumAcc<C, EPI>& acc) {
+  constexpr int R = C::radix(0), S = C::stride(0);
+  constexpr int TASKS = S * C::PW;
+  static_assert(TASKS % C::NT == 0, "whole last-stage tasks per thread");
+  constexpr int ITERS = TASKS / C::NT;
+  const int pr = tid & (C::PW - 1);
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int b = (tid + it * C::NT) >> C::LOG2PW;
+    c2 v[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) v[i] = lds_c2(tile, (phys_pt<C, S>(b, i) << C::LOG2PW) + pr);
+    stage_twiddle<R, S, true>(v, tws + C::tw_off(0), b);
+    Butterfly<R, true>::run(v);
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      if ((unsigned)(b + i * S) - T.row_lo >= T.row_cnt) continue;
+      if constexpr (EPI == EPI_STOKES_I) {
+        float s = acc.a[it][i];
+        s = fmaf(v[i].re.x, v[i].re.x, s);
+        s = fmaf(v[i].im.x, v[i].im.x, s);
+        s = fmaf(v[i].re.y, v[i].re.y, s);
+        s = fmaf(v[i].im.y, v[i].im.y, s);
+        acc.a[it][i] = s;
+      } else {
+        acc.a[it][i] = p_fma(v[i].re, v[i].re, p_fma(v[i].im, v[i].im, acc.a[it][i]));
+      }
+    }
+  }
+}
+
+// adds the running sums of a finished (or interrupted) group of 2^tsum_log2 time rows to the output.
+// `colbase` points at this thread's column(s) in output row 0; tile row r at inner offset nrest is
+// time n = (r << log2nmul) + nrest and lands in output row (n - crop_start) >> tsum_log2.  A group
+// receives at most two contributions (a CTA's run of tiles is at least one group long), so the
+// float atomics give the same result in either order.
+template <class C, int EPI>
+__device__ __forceinline__ void tsum_flush(const PassArgs& p, TsumAcc<C, EPI>& acc, char* colbase,
+                                           unsigned nrest, int tid, long long out_row_bytes) {
+  constexpr int R = C::radix(0), S = C::stride(0);
+#pragma unroll
+  for (int it = 0; it < TsumAcc<C, EPI>::ITERS; ++it) {
+    const int b = (tid + it * C::NT) >> C::LOG2PW;
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const long long n = ((long long)(b + i * S) << p.log2nmul) + nrest;
+      char* a = colbase + ((n - p.crop_start) >> p.tsum_log2) * out_row_bytes;
+      if constexpr (EPI == EPI_STOKES_I) {
+        if (acc.a[it][i] != 0.f) atomicAdd(reinterpret_cast<float*>(a), acc.a[it][i]);
+      } else {
+        if (acc.a[it][i].x != 0.f) atomicAdd(reinterpret_cast<float*>(a), acc.a[it][i].x);
+        if (acc.a[it][i].y != 0.f) atomicAdd(reinterpret_cast<float*>(a) + 1, acc.a[it][i].y);
+      }
+    }
+  }
+  acc.clear();
+}
+
 // ------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------
+// TSUM (final INV pass with a detected output and a time sum, row R of SURVEY 8a): a CTA owns a
+// CONTIGUOUS run of tiles ordered (column group, inner time offset), keeps the power sums of the
+// current group of 2^tsum_log2 consecutive time rows in registers and adds them to the (zeroed)
+// output when the group ends -- the full-resolution intensity array never exists.
 template <int MODE, class C, int LOADK, int EPI, bool TWOCH = false, bool NARROW = false,
-          bool SIGNINV = false>
+          bool SIGNINV = false, bool TSUM = false>
 __global__ void __launch_bounds__(C::NT, C::MINB)
 fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ tables,
                  long long ntiles) {
@@ -500,9 +586,26 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
   const unsigned rb_in = (unsigned)(p.min.a_row * in_eb);
   const unsigned rb_out = (unsigned)(p.mout.a_row * out_eb);
 
-  long long t = p.tile0 + blockIdx.x;
+  static_assert(!TSUM || (MODE == MODE_INV && !NARROW &&
+                          (EPI == EPI_INTENSITY || EPI == EPI_STOKES_I)), "TSUM is a final INV pass");
+  // iteration space: plain passes stride over tiles by the grid.  TSUM passes: q = tsum_q adjacent
+  // CTAs share a contiguous run of (column-group block, inner time offset) and take one column
+  // group of the block each, so that together they read whole rows (DRAM page locality)
+  const int ncg = TSUM ? p.I / C::W : 1;
+  const int tq = TSUM ? p.tsum_q : 1;
+  const int cgq = TSUM ? (int)(blockIdx.x % tq) : 0;
+  auto tile_at = [&](long long i) -> long long {
+    if (!TSUM) return i;
+    const long long cb = i >> p.log2nmul, nr = i & ((1ll << p.log2nmul) - 1);
+    return nr * ncg + cb * tq + cgq;
+  };
+  const long long ts_total = TSUM ? ntiles / tq : 0;              // runs are split over grid / q
+  const long long ts_r = TSUM ? blockIdx.x / tq : 0, ts_nr = TSUM ? gridDim.x / tq : 1;
+  long long t = TSUM ? ts_total * ts_r / ts_nr : p.tile0 + blockIdx.x;
+  const long long t_end = TSUM ? ts_total * (ts_r + 1) / ts_nr : ntiles;
+  const long long t_step = TSUM ? 1 : gridDim.x;
   for (int i = tid; i < C::TW_TOTAL; i += C::NT) tws[i] = tables[i];
-  if (tid == 0 && t < ntiles) fast_tile_info<C, EPI>(p, t, *sinfo, in_eb, out_eb);
+  if (tid == 0 && t < t_end) fast_tile_info<C, EPI>(p, tile_at(t), *sinfo, in_eb, out_eb);
   __syncthreads();
 
   // Per-thread part of the addresses.  A tile is W adjacent lanes; a lane is (row jr, column) of
@@ -530,13 +633,28 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
   constexpr int LTASKS = (C::L / RL) * C::PW;
   constexpr int LITERS = (LTASKS + C::NT - 1) / C::NT;
 
-  for (; t < ntiles; t += gridDim.x) {
+  TsumAcc<C, TSUM ? EPI : EPI_STOKES_I> tacc;
+  char* ts_colbase = nullptr;   // TSUM: output columns and inner offset of the running sums
+  unsigned ts_nrest = 0;
+  const long long ts_rowbytes = p.mout.a_n * out_eb;
+  if (TSUM) tacc.clear();
+
+  for (; t < t_end; t += t_step) {
     FastTile T;
     unsigned nrest0;
     {
       const TileInfo ti = *sinfo;
       T.gin = reinterpret_cast<const char*>(p.in) + ti.bi + off_in;
       T.gout = reinterpret_cast<char*>(p.out) + ti.bo + off_out;
+      if constexpr (TSUM) {
+        // ti.bo = (nrest - crop_start) rows + the column offset; keep the column part only
+        char* colbase = T.gout - ((long long)ti.nrest - p.crop_start) * ts_rowbytes;
+        if (ts_colbase != nullptr &&
+            (colbase != ts_colbase || (ti.nrest & ((1u << p.tsum_log2) - 1)) == 0))
+          tsum_flush<C, EPI>(p, tacc, ts_colbase, ts_nrest, tid, ts_rowbytes);
+        ts_colbase = colbase;
+        ts_nrest = ti.nrest;
+      }
       nrest0 = ti.nrest;
       T.nrest = ti.nrest + (LASTLEVEL ? 0 : jr);
       if (LASTLEVEL && NARROW) {
@@ -577,8 +695,8 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
     // every thread has copied *sinfo by the first barrier of this tile; thread 0 then prepares
     // the next tile's record, which the end-of-tile barrier publishes
 #define PBK_NEXT_TILE_INFO()                                                        \
-  if (tid == 0 && t + gridDim.x < ntiles)                                           \
-    fast_tile_info<C, EPI>(p, t + gridDim.x, *sinfo, in_eb, out_eb)
+  if (tid == 0 && t + t_step < t_end)                                               \
+    fast_tile_info<C, EPI>(p, tile_at(t + t_step), *sinfo, in_eb, out_eb)
     if (MODE == MODE_INV) PBK_NEXT_TILE_INFO();
 
     if (MODE == MODE_FWD) {
@@ -698,9 +816,13 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
       }
       __syncthreads();
       mid_stages<C, true, false>(tile, tws, tid);
-      inv_last<C, EPI>(T, tile, tws, tid, rb_out);
+      if constexpr (TSUM) inv_last_sum<C, EPI>(T, tile, tws, tid, tacc);
+      else inv_last<C, EPI>(T, tile, tws, tid, rb_out);
     }
     __syncthreads();  // tile buffer, G and the tile record are reused by the next tile
+  }
+  if constexpr (TSUM) {
+    if (ts_colbase != nullptr) tsum_flush<C, EPI>(p, tacc, ts_colbase, ts_nrest, tid, ts_rowbytes);
   }
 #undef PBK_NEXT_TILE_INFO
 }

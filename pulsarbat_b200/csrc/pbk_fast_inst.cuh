@@ -14,12 +14,14 @@ static void cfg_info(FastInfo* info) {
   info->threads = C::NT;
   info->minb = C::MINB;
   info->smem = C::SMEM_BYTES;
+  info->tsum_ok = (C::stride(0) * C::PW) % C::NT == 0;
 }
 
-template <int MODE, class C, int LOADK, int EPI, bool TWOCH, bool NARROW, bool SIGNINV = false>
+template <int MODE, class C, int LOADK, int EPI, bool TWOCH, bool NARROW, bool SIGNINV = false,
+          bool TSUM = false>
 static cudaError_t cfg_launch_variant(const PassArgs& a, const float2* d_tables, long long ntiles,
                                       int num_sms, cudaStream_t st) {
-  auto kern = fast_pass_kernel<MODE, C, LOADK, EPI, TWOCH, NARROW, SIGNINV>;
+  auto kern = fast_pass_kernel<MODE, C, LOADK, EPI, TWOCH, NARROW, SIGNINV, TSUM>;
   constexpr size_t smem = C::smem_bytes(NARROW);
   static bool attr_done[16] = {};
   int dev = 0;
@@ -31,7 +33,13 @@ static cudaError_t cfg_launch_variant(const PassArgs& a, const float2* d_tables,
     attr_done[dev] = true;
   }
   const long long resident = (long long)num_sms * C::MINB;
-  const unsigned grid = (unsigned)std::min<long long>(ntiles - a.tile0, resident);
+  unsigned grid = (unsigned)std::min<long long>(ntiles - a.tile0, resident);
+  // a TSUM CTA's contiguous run of tiles must span at least one whole group of summed rows
+  if (TSUM) {
+    const long long q = a.tsum_q;
+    grid = (unsigned)(q * std::max<long long>(1, std::min<long long>(resident / q,
+                                                                      (ntiles / q) >> a.tsum_log2)));
+  }
   kern<<<grid, C::NT, smem, st>>>(a, d_tables, ntiles);
   return cudaGetLastError();
 }
@@ -111,6 +119,13 @@ static cudaError_t cfg_launch(int mode, const PassArgs& a, const float2* d_table
       if (!a.final_epi)
         return cfg_launch_mode<MODE_INV, C, LK_PLANAR, EPI_SCRATCH>(a, d_tables, ntiles, num_sms,
                                                                     st);
+      if (a.tsum_log2 > 0) {   // detected output with the time sum fused into the epilogue
+        if (a.epi_kind == EPI_INTENSITY)
+          return cfg_launch_variant<MODE_INV, C, LK_PLANAR, EPI_INTENSITY, false, false, false, true>(
+              a, d_tables, ntiles, num_sms, st);
+        return cfg_launch_variant<MODE_INV, C, LK_PLANAR, EPI_STOKES_I, false, false, false, true>(
+            a, d_tables, ntiles, num_sms, st);
+      }
       switch (a.epi_kind) {
         case EPI_C64:
           return cfg_launch_mode<MODE_INV, C, LK_PLANAR, EPI_C64>(a, d_tables, ntiles, num_sms, st);

@@ -14,6 +14,7 @@ struct FastInfo {
   int tw_count;      // float2 entries of the stage tables
   int threads, minb; // launch shape
   size_t smem;
+  bool tsum_ok;      // the final INV pass has a time-summing variant (whole tasks per thread)
 };
 
 // false when this family has no instantiation for the tile length

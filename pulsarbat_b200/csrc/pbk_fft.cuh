@@ -88,6 +88,9 @@ struct PassArgs {
   const long long* ramp_zero;   // [lo, hi) per column in fftshift-ed bin order; lo >= hi = none
   int ramp_hilbert;             // analytic-signal weights 1,2,..,2,1,0,..,0 (utils.py:50-54)
   long long tile0;    // fast kernels: first tile of this launch (tiles [tile0, ntiles) are processed)
+  int tsum_log2;      // fast final INV pass: > 0 = sum 2^tsum_log2 consecutive time rows of the
+                      // detected output in the epilogue (row R fused; see fast_pass_kernel TSUM)
+  int tsum_q;         // ... with groups of tsum_q adjacent CTAs covering adjacent column groups
 };
 
 // ------------------------------------------------------------------------------------------

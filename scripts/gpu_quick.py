@@ -52,7 +52,8 @@ def time_plan(name, N, C, P, dm, sr, fcen, out_kind=0, downsample=1, in_dtype=0,
           f"median {ms:.3f} ms best {min(ts):.3f} ms -> {nsmp / ms / 1e6:.1f} Gsamples/s, "
           f"alg {(in_b + nout) / ms / 1e6:.0f} GB/s", flush=True)
     seg = np.array([plan.profile_read(i) for i in range(iters)]).mean(axis=0)
-    names = plan.describe().split(";") + (["downsample"] if downsample > 1 else [])
+    names = plan.describe().split(";") + (
+        ["downsample"] if downsample > 1 and ":timesum" not in plan.describe() else [])
     for nm, t in zip(names, seg):
         print(f"      {t:7.3f} ms  {nm}", flush=True)
     plan.destroy()

@@ -1,6 +1,7 @@
 """GPU parity tests of the raw kernels (through the C ABI) against the CPU oracle."""
 
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -726,3 +727,51 @@ def test_dedisp_fast_kernels_single_pol(N, C):
     plan.destroy()
     want = np.abs(got[start:stop].astype(np.complex128)) ** 2
     assert relerr(it, orc.downsample(want, 8)) < 1e-5
+
+
+@pytest.mark.parametrize("N, C, M, crop", [
+    (2 ** 16, 16, 64, (0, 2 ** 16)),                 # whole block, groups aligned: fused
+    (2 ** 16, 16, 64, (4096, 2 ** 16 - 1000)),       # aligned start, ragged stop: fused, tail dropped
+    (2 ** 16, 16, 64, (4100, 2 ** 16 - 1000)),       # start not a multiple of M: two-kernel path
+    (2 ** 18, 32, 16, (1024, 2 ** 18 - 7)),
+    (2 ** 18, 64, 256, (256 * 11, 2 ** 18)),
+    (2 ** 20, 64, 4, (0, 2 ** 20)),
+    (2 ** 16, 64, 1024, (0, 2 ** 16)),               # factor larger than the inner extent: not fused
+])
+@pytest.mark.parametrize("out_kind", [1, 2])
+def test_dedisp_fused_time_sum(N, C, M, crop, out_kind):
+    """Time sum (out[j] = sum_m in[j*M+m], tail dropped) fused into the epilogue
+    of the last inverse pass, against the oracle on the cropped rows; the fused and the two-kernel
+    paths must agree, and the fused result must be reproducible bit for bit."""
+    L = _lib()
+    rng = np.random.default_rng(N // 1024 + C + M)
+    sr, fcen, dm = 6.25e6, 625e6, 0.5
+    x = crandn(rng, (N, C, 2))
+    freqs = orc.channel_freqs(fcen, sr, C, "center")
+    want, _, _ = orc.coherent_dedispersion(x, dm, sample_rate=sr, center_freq=fcen, crop=False)
+    det = orc.to_intensity(want) if out_kind == 1 else orc.stokes_I(want)
+    ref = orc.downsample(det[crop[0]:crop[1]], M)
+
+    def run():
+        plan = L.DedispPlan(nsamp=N, nchan=C, npol=2, dm=dm, sample_rate_hz=sr, ref_freq_hz=fcen,
+                            chan_freq_hz=freqs, crop=crop, out_kind=out_kind, downsample=M)
+        out = plan.exec_host(x, plan.out_array())
+        desc = plan.describe()
+        plan.destroy()
+        return out, desc
+
+    got, desc = run()
+    assert got.shape == ref.shape
+    assert relerr(got, ref) < 1e-5, desc
+    fused = "timesum" in desc
+    assert fused == (crop[0] % M == 0 and M <= 2 ** 8), desc   # N = L1 * inner: inner >= 2^8 here
+    if fused:
+        again, _ = run()
+        assert np.array_equal(got, again)
+        os.environ["PBK_NO_FUSED_SUM"] = "1"
+        try:
+            plain, desc2 = run()
+        finally:
+            del os.environ["PBK_NO_FUSED_SUM"]
+        assert "timesum" not in desc2
+        assert relerr(got, plain) < 2e-6
