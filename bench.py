@@ -362,10 +362,31 @@ def run_b200(args, w):
             r = call8()
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - t0)
-        e2e = {"value": world * nsamp * ke / dt / 1e9, "unit": UNIT,
+        single = {"value": world * nsamp * ke / dt / 1e9, "ms_per_step": dt / ke * 1e3,
+                  "api": "pulsarbat_b200.kernels.dedisperse(int8 numpy, pinned) -- one synchronous "
+                         "call per block, result in fresh pageable memory"}
+        single["pinned_results"] = time_pinned_results(call8, ke, world, nsamp, max_over_ranks)
+
+        def stream8(nblk):
+            tot = 0.0
+            for y in pb.streaming.dedisperse_blocks(
+                    (hraw for _ in range(nblk)), dm=w["dm"], sample_rate_hz=w["sr"],
+                    chan_freq_hz=freqs, ref_freq_hz=w["fcen"], crop=None, int8=True,
+                    device=local, pinned_out=True):
+                tot += float(y.ravel()[0].real)
+            return tot
+        stream8(2)
+        barrier()
+        t0 = time.perf_counter()
+        stream8(ke)
+        torch.cuda.synchronize()
+        dts = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": world * nsamp * ke / dts / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": int(hraw.nbytes), "d2h_bytes_per_step": int(r.nbytes),
-               "steps": ke, "ms_per_step": dt / ke * 1e3,
-               "api": "pulsarbat_b200.kernels.dedisperse(int8 numpy, pinned)"}
+               "steps": ke, "ms_per_step": dts / ke * 1e3,
+               "api": "pulsarbat_b200.streaming.dedisperse_blocks(pinned int8 blocks): upload of "
+                      "block i+1, kernels of block i and download of block i-1 overlap",
+               "single_call": single}
         del hx, hraw, r
     elif not args.no_e2e and N * C * P <= 2 ** 30:
         hx = torch.empty((N, C, P, 2), dtype=torch.float32, pin_memory=True)
@@ -401,6 +422,8 @@ def run_b200(args, w):
         single = {"value": world * nsamp * ke / dt / 1e9, "ms_per_step": dt / ke * 1e3,
                   "api": "pulsarbat_b200.dedisperse_detect(DualPolarizationSignal(numpy, pinned))"
                          " -- one synchronous call per block"}
+        if rbytes > 2 ** 26:
+            single["pinned_results"] = time_pinned_results(call, ke, world, nsamp, max_over_ranks)
         # the same blocks as a stream: H2D of block i+1 overlaps the kernels of block i
         out_kind_s = L.OUT_C64 if w["stokes"] is None else (L.OUT_STOKES_I if w["stokes"] else
                                                             L.OUT_INTENSITY)
@@ -411,7 +434,7 @@ def run_b200(args, w):
                     (hnp for _ in range(nblk)), dm=w["dm"], sample_rate_hz=w["sr"],
                     chan_freq_hz=freqs, ref_freq_hz=w["fcen"], crop=None, out_kind=out_kind_s,
                     downsample=w["ds"], device=local, pinned_out=True):
-                tot += float(y.ravel()[0])          # the result of every block is read on the host
+                tot += float(y.ravel()[0].real)     # the result of every block is read on the host
             return tot
         stream(2)
         barrier()
@@ -422,9 +445,9 @@ def run_b200(args, w):
         e2e = {"value": world * nsamp * ke / dts / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": int(hnp.nbytes), "d2h_bytes_per_step": rbytes,
                "steps": ke, "ms_per_step": dts / ke * 1e3,
-               "api": "pulsarbat_b200.streaming.dedisperse_blocks(pinned numpy blocks): H2D of "
-                      "block i+1 overlaps the kernels of block i (plan and buffers cached after the "
-                      "warm-up stream)",
+               "api": "pulsarbat_b200.streaming.dedisperse_blocks(pinned numpy blocks): upload of "
+                      "block i+1, kernels of block i and download of block i-1 overlap (plan and "
+                      "buffers cached after the warm-up stream)",
                "single_call": single}
         del hx, hnp, z
 
@@ -459,6 +482,25 @@ def run_b200(args, w):
     plan.destroy()
     if world > 1:
         dist.destroy_process_group()
+
+
+def time_pinned_results(call, ke, world, nsamp, max_over_ranks):
+    """The same synchronous call with page-locked result arrays (kernels.pinned_results)."""
+    import torch
+    import pulsarbat_b200 as pb
+    old = pb.kernels.pinned_results(True)
+    try:
+        r = call()
+        del r
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            r = call()
+            del r
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+    finally:
+        pb.kernels.pinned_results(old)
+    return {"value": world * nsamp * ke / dt / 1e9, "ms_per_step": dt / ke * 1e3}
 
 
 def main():

@@ -19,7 +19,7 @@ from . import _lib as L
 from .device import DeviceArray
 
 __all__ = ["default_device", "dedisperse", "chirp", "detect", "shift_channels", "phase_ramp", "mix", "analytic_decimate", "stokes", "pol_basis",
-           "downsample", "fft", "stft", "istft", "fold", "clear_plan_cache"]
+           "downsample", "fft", "stft", "istft", "fold", "clear_plan_cache", "pinned_results"]
 
 
 def default_device():
@@ -94,6 +94,35 @@ def _host_c64(x):
     return np.ascontiguousarray(x, dtype=np.complex64), x.dtype
 
 
+_pinned_results = os.environ.get("PBK_PINNED_RESULTS", "0") not in ("", "0")
+
+
+def pinned_results(enable=None):
+    """Result arrays of host-array calls: pageable ``np.empty`` (default) or page-locked memory.
+
+    A fresh pageable array costs a page fault per 4 KiB on its first write and a staged device ->
+    host copy (about 4 GB/s for a multi-gigabyte result); page-locked results copy at PCIe speed.
+    They come from torch's caching host allocator, so the first call of a given size pays the
+    pinning once and later calls reuse the block when the previous result has been released.
+    Returns the previous setting; ``$PBK_PINNED_RESULTS=1`` sets the default."""
+    global _pinned_results
+    old = _pinned_results
+    if enable is not None:
+        _pinned_results = bool(enable)
+    return old
+
+
+def _result(shape, dtype):
+    """Uninitialised host array for a result (see :func:`pinned_results`)."""
+    if not _pinned_results:
+        return np.empty(shape, dtype)
+    import torch
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape, dtype=np.int64)) * dt.itemsize
+    buf = torch.empty(max(n, 1), dtype=torch.uint8, pin_memory=True).numpy()
+    return buf[:n].view(dt).reshape(shape)     # keeps the pinned block alive through .base
+
+
 def _real_of(cdtype):
     return np.float64 if np.dtype(cdtype) == np.complex128 else np.float32
 
@@ -151,7 +180,7 @@ def dedisperse(data, *, dm, sample_rate_hz, chan_freq_hz, ref_freq_hz, crop=None
         x, odt = np.ascontiguousarray(data, dtype=np.int8), np.complex64
     else:
         x, odt = _host_c64(data)
-    out = np.empty(out_shape, np.complex64 if out_kind == L.OUT_C64 else np.float32)
+    out = _result(out_shape, np.complex64 if out_kind == L.OUT_C64 else np.float32)
     ch = None
     if chirp_array is not None:
         ch = np.ascontiguousarray(np.asarray(chirp_array).reshape(nsamp, nchan),
@@ -210,7 +239,7 @@ def detect(data, stokes=False, downsample=1, freq_sum=1, device=None):
         call(L.ptr(x.ptr), L.ptr(out.ptr), 1, x.device, ctypes.c_void_p(_stream()))
         return out
     x, odt = _host_c64(data)
-    out = np.empty(out_shape, np.float32)
+    out = _result(out_shape, np.float32)
     dev = default_device() if device is None else device
     call(L.ptr(x), L.ptr(out), 0, dev, None)
     rdt = _real_of(odt)
@@ -239,7 +268,7 @@ def shift_channels(data, delays, nsamp_out, device=None):
                                            ctypes.c_void_p(_stream())))
         return out
     x = np.ascontiguousarray(data)
-    out = np.empty(out_shape, x.dtype)
+    out = _result(out_shape, x.dtype)
     dev = default_device() if device is None else device
     L.check(L.lib().pbk_shift_channels(L.ptr(x), L.ptr(out), nsamp, int(nsamp_out), nchan, cell,
                                        dp, 0, dev, None))
@@ -271,7 +300,7 @@ def phase_ramp(data, shift_samples=None, zero_lo=None, zero_hi=None, device=None
             ent.plan.exec_device(x.ptr, out.ptr, _stream())
         return out
     x, odt = _host_c64(data)
-    out = np.empty(shape, np.complex64)
+    out = _result(shape, np.complex64)
     with ent.lock:
         ent.plan.exec_host(x, out)
     return out if odt == np.complex64 else out.astype(odt)
@@ -306,7 +335,7 @@ def analytic_decimate(data, device=None):
     tmp = np.empty(shape, np.complex64)
     with ent.lock:
         ent.plan.exec_host(x, tmp)
-    out = np.empty((rows_out, ncols), np.complex64)
+    out = _result((rows_out, ncols), np.complex64)
     L.check(L.lib().pbk_decimate2(L.ptr(tmp), L.ptr(out), nsamp, ncols, 0, dev, None))
     return out
 
@@ -329,7 +358,7 @@ def mix(data, cycles_per_sample, device=None):
                                 ctypes.c_void_p(_stream())))
         return out
     x, odt = _host_c64(data)
-    out = np.empty(shape, np.complex64)
+    out = _result(shape, np.complex64)
     dev = default_device() if device is None else device
     L.check(L.lib().pbk_mix(L.ptr(x), L.ptr(out), shape[0], shape[1], fp, 0, dev, None))
     return out if odt == np.complex64 else out.astype(odt)
@@ -353,7 +382,7 @@ def _pairs_op(data, fn, flag, out_real, device):
         return out
     x, odt = _host_c64(data)
     oshape = shape[:2] + ((4,) if out_real else (2,))
-    out = np.empty(oshape, np.float32 if out_real else np.complex64)
+    out = _result(oshape, np.float32 if out_real else np.complex64)
     dev = default_device() if device is None else device
     L.check(fn(L.ptr(x), L.ptr(out), npairs, flag, 0, dev, None))
     if out_real:
@@ -390,7 +419,7 @@ def downsample(data, factor, device=None):
     x = np.asarray(data)
     odt = x.dtype
     x = np.ascontiguousarray(x, dtype=np.float32)
-    out = np.empty((rows,) + shape[1:], np.float32)
+    out = _result((rows,) + shape[1:], np.float32)
     dev = default_device() if device is None else device
     L.check(L.lib().pbk_downsample(L.ptr(x), L.ptr(out), shape[0], relems, int(factor), 0, dev,
                                    None))
@@ -411,7 +440,7 @@ def _run_fft_plan(key, factory, data, out_shape):
             ent.plan.exec_device(x.ptr, out.ptr, _stream())
         return out
     x, odt = _host_c64(data)
-    out = np.empty(out_shape, np.complex64)
+    out = _result(out_shape, np.complex64)
     with ent.lock:
         ent.plan.exec_host(x, out)
     return out if odt == np.complex64 else out.astype(odt)

@@ -1,10 +1,13 @@
-"""Block streams: overlap the host->device copy of block i+1 with the kernels of block i.
+"""Block streams: overlap the host->device copy of block i+1 and the device->host copy of block
+i-1 with the kernels of block i.
 
 The reference processes a long observation as a sequence of blocks (dask chunks along channels,
 or overlap-save blocks along time); each block goes host -> GPU -> host.
 A single synchronous call cannot hide the PCIe copy behind the kernels, so this module runs the
-same plan over an iterator of blocks with two device input buffers, a copy stream and a compute
-stream (CUDA events between them).  The arithmetic is exactly that of ``kernels.dedisperse``.
+same plan over an iterator of blocks with two device input and output buffers and three streams
+-- upload, compute, download -- chained by CUDA events, so that a step costs the slowest of the
+three (PCIe is full duplex: the two copies run concurrently).  The arithmetic is exactly that of
+``kernels.dedisperse``.
 """
 
 import numpy as np
@@ -78,15 +81,16 @@ def dedisperse_blocks(blocks, *, dm, sample_rate_hz, chan_freq_hz, ref_freq_hz, 
                     [torch.empty(shape, dtype=in_t, device=tdev) for _ in range(2)],
                     [torch.empty(out_shape, dtype=out_t, device=tdev) for _ in range(2)],
                     [torch.empty(out_shape, dtype=out_t, pin_memory=True) for _ in range(2)],
-                    torch.cuda.Stream(tdev), torch.cuda.Stream(tdev),
+                    torch.cuda.Stream(tdev), torch.cuda.Stream(tdev), torch.cuda.Stream(tdev),
                     [torch.cuda.Event() for _ in range(6)])
 
     key = (shape, bool(int8), float(dm), float(sample_rate_hz), float(ref_freq_hz),
            freqs.tobytes(), start, stop, int(out_kind), int(downsample), dev)
-    plan, d_in, d_out, h_out, s_copy, s_comp, ev = _get_state(key, make)
+    plan, d_in, d_out, h_out, s_copy, s_comp, s_down, ev = _get_state(key, make)
     copied, consumed, done = ev[0:2], ev[2:4], ev[4:6]   # per slot: H2D done / kernels done / D2H done
     s_copy.synchronize()      # an earlier, abandoned generator may have left work in flight
     s_comp.synchronize()
+    s_down.synchronize()
 
     def upload(block, slot, reuse):
         hb = np.ascontiguousarray(block, dtype=first.dtype)
@@ -100,14 +104,17 @@ def dedisperse_blocks(blocks, *, dm, sample_rate_hz, chan_freq_hz, ref_freq_hz, 
         copied[slot].record(s_copy)
         return hb                                             # keeps the host block alive
 
-    def compute(slot):
+    def compute(slot, reuse):
         s_comp.wait_event(copied[slot])
+        if reuse:
+            s_comp.wait_event(done[slot])      # the previous result of this slot has left the device
         plan.exec_device(d_in[slot].data_ptr(), d_out[slot].data_ptr(), None, s_comp.cuda_stream)
         consumed[slot].record(s_comp)
+        s_down.wait_event(consumed[slot])
         L.check(L.lib().pbk_memcpy_async(h_out[slot].data_ptr(), d_out[slot].data_ptr(),
                                          h_out[slot].numel() * h_out[slot].element_size(), 0, dev,
-                                         s_comp.cuda_stream))
-        done[slot].record(s_comp)
+                                         s_down.cuda_stream))
+        done[slot].record(s_down)
 
     def result(slot):
         done[slot].synchronize()
@@ -122,7 +129,7 @@ def dedisperse_blocks(blocks, *, dm, sample_rate_hz, chan_freq_hz, ref_freq_hz, 
             slot = i & 1
             if nxt is not None:
                 keep[slot ^ 1] = upload(nxt, slot ^ 1, i >= 1)
-            compute(slot)
+            compute(slot, i >= 2)
             if i >= 1:
                 yield result(slot ^ 1)
             if nxt is None:

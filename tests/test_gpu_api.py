@@ -319,3 +319,29 @@ def test_explicit_chirp_equals_generated_chirp():
     assert one.shape == (8192,)
     assert np.max(np.abs(one - orc.transfer_function(10.0, 8192, 1e6, z.channel_freqs_hz[0],
                                                      1e9))) < 2e-6
+
+
+def test_pinned_result_arrays():
+    """kernels.pinned_results(True): results live in page-locked memory, values unchanged."""
+    import pulsarbat_b200 as pb
+    rng = np.random.default_rng(12)
+    N, C = 2 ** 12, 4
+    sr, fcen, dm = 1e6, 600e6, 0.2
+    x = crandn(rng, (N, C, 2))
+    kw = dict(dm=dm, sample_rate_hz=sr, chan_freq_hz=orc.channel_freqs(fcen, sr, C),
+              ref_freq_hz=fcen, crop=(10, N - 20))
+    plain = pb.kernels.dedisperse(x, **kw)
+    old = pb.kernels.pinned_results(True)
+    try:
+        assert old is False
+        pinned = pb.kernels.dedisperse(x, **kw)
+        spec = pb.kernels.fft(x)
+    finally:
+        assert pb.kernels.pinned_results(old) is True
+    assert pinned.flags.c_contiguous and pinned.flags.writeable and pinned.dtype == plain.dtype
+    assert np.array_equal(pinned, plain)
+    assert spec.shape == x.shape
+    pinned += 1          # ordinary numpy array semantics
+    keep = pinned[5:7].copy()
+    del pinned
+    assert np.isfinite(keep).all()
