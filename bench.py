@@ -229,6 +229,8 @@ def run_b200(args, w):
     torch.cuda.set_device(local)
     os.environ["PBK_DEVICE"] = str(local)
     dev = torch.device(f"cuda:{local}")
+    all_cpus = os.sched_getaffinity(0)
+    numa = pb.sharding.bind_host_to_device(local)   # before any page-locked allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -453,6 +455,7 @@ def run_b200(args, w):
 
     # ---- CPU baseline (rank 0, single-GPU run only) --------------------------------------
     cpu = None
+    os.sched_setaffinity(0, all_cpus)   # the CPU baseline may use every host core
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
         nch = cpu_calibrate(w, freqs, threads, target_s=12.0)
@@ -473,6 +476,7 @@ def run_b200(args, w):
             "config": {"workload": w["text"], "name": args.workload,
                        "levels": info["levels"], "plan": desc,
                        "parallelism": f"time-block sharding x{world}, no collective",
+                       "host_numa_node_rank0": numa,
                        "l2": f"input block {in_bytes / 2**20:.0f} MiB per GPU exceeds the 126 MB "
                              "L2, no flush needed"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,

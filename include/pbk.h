@@ -57,6 +57,9 @@ int pbk_version(void);
 const char* pbk_last_error(void);
 const char* pbk_status_string(int status);
 int pbk_device_count(int* count);
+/* PCI bus id of a CUDA device ("0000:1b:00.0"), for binding the host process to the GPU's NUMA
+ * node (one process per GPU); no reference counterpart */
+int pbk_device_pci_bus_id(int device, char* buf, int n);
 
 /* ---- coherent dedispersion ---------------------------------------------------------------
  * Replaces transforms/dedispersion.py:81-133 `coherent_dedispersion` for numpy/dask blocks and

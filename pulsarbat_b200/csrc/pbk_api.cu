@@ -68,6 +68,12 @@ extern "C" int pbk_device_count(int* count) {
   return PBK_OK;
 }
 
+extern "C" int pbk_device_pci_bus_id(int device, char* buf, int n) {
+  if (!buf || n < 16) return fail(PBK_ERR_INVALID, "buffer of at least 16 bytes expected");
+  CUDA_TRY(cudaDeviceGetPCIBusId(buf, n, device));
+  return PBK_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------

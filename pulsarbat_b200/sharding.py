@@ -20,7 +20,58 @@ import numpy as np
 from . import units as u
 
 __all__ = ["channel_range", "shard_channels", "block_ranges", "time_block_shards",
-           "dedispersion_crop", "allreduce_profiles", "fold_sharded"]
+           "dedispersion_crop", "allreduce_profiles", "fold_sharded", "bind_host_to_device",
+           "numa_node_cpus"]
+
+
+def _parse_cpulist(text):
+    """'0-3,8,10-11' -> [0, 1, 2, 3, 8, 10, 11] (the kernel's cpulist format)."""
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def numa_node_cpus(pci_bus_id, sysfs="/sys"):
+    """(node, cpus) of the NUMA node a PCI device hangs off, read from sysfs; (None, []) when the
+    platform does not say (single-node hosts report -1)."""
+    try:
+        with open(f"{sysfs}/bus/pci/devices/{pci_bus_id.lower()}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None, []
+        with open(f"{sysfs}/devices/system/node/node{node}/cpulist") as f:
+            return node, _parse_cpulist(f.read())
+    except (OSError, ValueError):
+        return None, []
+
+
+def bind_host_to_device(device):
+    """Pin the calling process to the CPUs of ``device``'s NUMA node.
+
+    With one process per GPU every rank stages its blocks through page-locked host memory; the
+    kernel places those pages on the node of the allocating thread, so binding first keeps each
+    rank's PCIe traffic off the inter-socket link.  Returns the node, or None when nothing was
+    changed (unknown topology, or the node has no CPU this process may run on)."""
+    import ctypes
+    import os
+    from . import _lib as L
+    buf = ctypes.create_string_buffer(32)
+    try:
+        L.check(L.lib().pbk_device_pci_bus_id(int(device), buf, 32))
+    except L.PbkError:
+        return None
+    node, cpus = numa_node_cpus(buf.value.decode())
+    if node is None or not hasattr(os, "sched_setaffinity"):
+        return None
+    allowed = set(os.sched_getaffinity(0)) & set(cpus)
+    if not allowed:
+        return None
+    os.sched_setaffinity(0, allowed)
+    return node
 
 
 def channel_range(nchan, world_size, rank):

@@ -107,3 +107,19 @@ def test_allreduce_is_identity_without_process_group():
     p, c = np.ones((4, 2), np.float32), np.ones(4, np.int64)
     p2, c2 = sh.allreduce_profiles(p, c)
     assert p2 is p and c2 is c
+
+
+def test_numa_node_lookup_from_sysfs(tmp_path):
+    """bind_host_to_device reads the GPU's NUMA node and its cpulist from sysfs."""
+    from pulsarbat_b200 import sharding
+    dev = tmp_path / "bus" / "pci" / "devices" / "0000:1b:00.0"
+    dev.mkdir(parents=True)
+    (dev / "numa_node").write_text("1\n")
+    node = tmp_path / "devices" / "system" / "node" / "node1"
+    node.mkdir(parents=True)
+    (node / "cpulist").write_text("16-19,48,50-51\n")
+    assert sharding.numa_node_cpus("0000:1B:00.0", sysfs=str(tmp_path)) == (
+        1, [16, 17, 18, 19, 48, 50, 51])
+    (dev / "numa_node").write_text("-1\n")
+    assert sharding.numa_node_cpus("0000:1b:00.0", sysfs=str(tmp_path)) == (None, [])
+    assert sharding.numa_node_cpus("0000:ff:00.0", sysfs=str(tmp_path)) == (None, [])
