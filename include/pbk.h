@@ -44,7 +44,15 @@ enum pbk_status {
 enum pbk_dtype {
   PBK_C64 = 0,
   PBK_I8X2 = 1, /* interleaved (re, im) int8 pairs */
-  PBK_F32 = 2   /* real float32 (imaginary part zero); ramp plans only */
+  PBK_F32 = 2,  /* real float32 (imaginary part zero); ramp plans only */
+  /* packed raw baseband, decoded in the load of the first pass (builder-defined like PBK_I8X2,
+   * the reference receives decoded samples from `baseband`,
+   * readers/_baseband_readers.py:139-153).  Elements are packed in array order, first element in
+   * the least significant bits; nchan * npol must be even. */
+  PBK_U4X2 = 3, /* one byte per complex sample: low nibble re, high nibble im, offset binary
+                   (value = code - 8) */
+  PBK_U2X2 = 4  /* four bits per complex sample: bits 1:0 re, bits 3:2 im; two complex samples
+                   per byte; codes 0..3 -> -3.3359, -1, +1, +3.3359 (the usual 2-bit levels) */
 };
 
 enum pbk_out_kind {
@@ -196,6 +204,18 @@ int pbk_chirp(int64_t nsamp, int64_t nchan, double dm, double sample_rate_hz,
 int pbk_fold(const void* in, int64_t nsamp, int64_t row_elems, const double* coeffs,
              int32_t ncoef, double sample_rate_hz, int64_t n0, int32_t nbin, void* profile,
              void* counts, void* bins_out, int32_t on_device, int32_t device, void* stream);
+
+/* ---- phase prediction on the device (pulsar/predictor.py:121-147 `PhasePredictor.__call__`
+ * for the samples of one polyco entry) --------------------------------------------------------
+ * ph = polyval(dt) with numpy's Horner order in FP64 (no FMA contraction), split as
+ * pulsar/phase.py:28-78: phase_int = rphase + rint(ph) (int64), phase_frac = ph - rint(ph) (FP64).
+ * dt_s: n offsets in seconds from the entry's tmid, or NULL to generate
+ * dt = dt0_s + (n0 + i) / sample_rate_hz.  The host mirror picks the entry (searchsorted on the
+ * span ends, predictor.py:108-119) and raises the reference's ValueError for times out of range. */
+int pbk_phase_predict(const double* dt_s, int64_t n, double dt0_s, double sample_rate_hz,
+                      int64_t n0, const double* coeffs, int32_t ncoef, int64_t rphase,
+                      void* phase_int, void* phase_frac, int32_t on_device, int32_t device,
+                      void* stream);
 
 void pbk_plan_destroy(pbk_plan* plan);
 

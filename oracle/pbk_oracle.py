@@ -338,6 +338,29 @@ def unpack_int8(raw):
         np.complex64)
 
 
+U2_LEVELS = np.array([-3.3359, -1.0, 1.0, 3.3359], dtype=np.float32)
+
+
+def unpack_u4(raw):
+    """uint8, one byte per complex sample (low nibble re, high nibble im, offset binary:
+    value = code - 8) -> complex64 of the same shape.  Builder-defined (include/pbk.h PBK_U4X2)."""
+    raw = np.asarray(raw)
+    assert raw.dtype == np.uint8
+    re = (raw & 15).astype(np.float32) - 8.0
+    im = (raw >> 4).astype(np.float32) - 8.0
+    return (re + 1j * im).astype(np.complex64)
+
+
+def unpack_u2(raw):
+    """uint8, two complex samples per byte (first in the low nibble; bits 1:0 re, 3:2 im; codes
+    0..3 -> -3.3359, -1, +1, +3.3359) -> complex64 with the last axis doubled.  Builder-defined
+    (include/pbk.h PBK_U2X2)."""
+    raw = np.asarray(raw)
+    assert raw.dtype == np.uint8
+    nib = np.stack([raw & 15, raw >> 4], axis=-1).reshape(raw.shape[:-1] + (2 * raw.shape[-1],))
+    return (U2_LEVELS[nib & 3] + 1j * U2_LEVELS[nib >> 2]).astype(np.complex64)
+
+
 def overlap_save_blocks(nsamp, block_len, start, stop_pad):
     """Block start offsets for overlap-save with block length L and per-block crop
     [start, L - stop_pad): consecutive blocks advance by the valid length."""

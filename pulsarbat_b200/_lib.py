@@ -10,12 +10,12 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.environ.get("PBK_LIBRARY") or os.path.join(_HERE, "libpbk.so")
 
-PBK_C64, PBK_I8X2 = 0, 1
+PBK_C64, PBK_I8X2, PBK_F32, PBK_U4X2, PBK_U2X2 = 0, 1, 2, 3, 4
 OUT_C64, OUT_INTENSITY, OUT_STOKES_I = 0, 1, 2
 
 EXPORTS = [
     "pbk_version", "pbk_last_error", "pbk_status_string", "pbk_device_count",
-    "pbk_device_pci_bus_id",
+    "pbk_device_pci_bus_id", "pbk_phase_predict",
     "pbk_dedisp_plan_create", "pbk_dedisp_out_shape", "pbk_dedisp_exec_host",
     "pbk_dedisp_exec_device", "pbk_fft_plan_create", "pbk_stft_plan_create",
     "pbk_fft_exec_host", "pbk_fft_exec_device", "pbk_detect", "pbk_detect_scrunch", "pbk_shift_channels", "pbk_downsample", "pbk_fold",
@@ -73,6 +73,9 @@ def lib():
         L.pbk_status_string.restype = ctypes.c_char_p
         L.pbk_status_string.argtypes = [ctypes.c_int]
         L.pbk_device_count.argtypes = [ctypes.POINTER(ctypes.c_int)]
+        L.pbk_device_pci_bus_id.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
+        L.pbk_phase_predict.argtypes = [vp, i64, dbl, dbl, i64, ctypes.POINTER(dbl), i32, i64, vp,
+                                        vp, i32, i32, vp]
         L.pbk_dedisp_plan_create.argtypes = [ctypes.POINTER(DedispDesc), ctypes.POINTER(vp)]
         L.pbk_dedisp_out_shape.argtypes = [vp] + [ctypes.POINTER(i64)] * 3
         L.pbk_dedisp_exec_host.argtypes = [vp, vp, vp, vp]

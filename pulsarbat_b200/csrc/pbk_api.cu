@@ -404,7 +404,7 @@ static int setup_fast(pbk_plan* pl) {
     // the fast kernels are specialised to the dedispersion passes (see pbk_fast.cuh) plus the
     // last pass of a forward FFT / STFT plan (FWD-last: no level twiddle, scale, fftshift)
     const bool fwd_last = ps.mode == MODE_FWD && ps.a.log2M == 0 && ps.out_role == ROLE_USER_OUT &&
-                          pl->kind == PLAN_FFT && ps.a.load_kind != LOAD_I8X2;
+                          pl->kind == PLAN_FFT && !load_is_raw(ps.a.load_kind);
     if (ps.a.kxor && !fwd_last) continue;
     // ifftshift on the load rows (ISTFT first pass) is only done by the transposed loader, whose
     // tile is a whole level: single-level plans whose lane pairs own contiguous runs of rows
@@ -413,7 +413,7 @@ static int setup_fast(pbk_plan* pl) {
     if (ps.a.fxor && !(fwd_last && in_rows_contig)) continue;
     if (ps.a.scale != 1.0f && ps.mode != MODE_MID && !fwd_last) continue;
     if (ps.mode != MODE_MID && ps.a.log2M == 0 && !fwd_last) continue;
-    if (ps.mode == MODE_MID && (ps.a.chirp_kind != CHIRP_COMPUTED || ps.a.load_kind == LOAD_I8X2 ||
+    if (ps.mode == MODE_MID && (ps.a.chirp_kind != CHIRP_COMPUTED || load_is_raw(ps.a.load_kind) ||
                                 !pl->chirp_series_ok))
       continue;
     if (ps.mode != MODE_FWD && ps.in_role == ROLE_SCRATCH && ps.a.load_kind != LOAD_PLANAR) continue;
@@ -502,6 +502,16 @@ struct RampSpec {   // linear-phase / band-zeroing transfer function per column 
   int flags;   // PBK_RAMP_HILBERT, PBK_RAMP_REAL_INPUT
 };
 
+static int load_kind_of(int in_dtype) {
+  switch (in_dtype) {
+    case PBK_I8X2: return LOAD_I8X2;
+    case PBK_U4X2: return LOAD_U4X2;
+    case PBK_U2X2: return LOAD_U2X2;
+    case PBK_F32: return LOAD_F32;
+    default: return LOAD_C64;
+  }
+}
+
 static int dedisp_plan_create_impl(const pbk_dedisp_desc* d, const RampSpec* ramp, pbk_plan** out);
 static int blue_dedisp_plan_create(const pbk_dedisp_desc* d, const RampSpec* ramp, pbk_plan** out);
 
@@ -559,8 +569,12 @@ static int dedisp_plan_create_impl(const pbk_dedisp_desc* d, const RampSpec* ram
     return fail(PBK_ERR_INVALID, "shape must be positive");
   if (!d->chan_freq_hz) return fail(PBK_ERR_INVALID, "chan_freq_hz is NULL");
   if (!(d->sample_rate_hz > 0)) return fail(PBK_ERR_INVALID, "sample_rate_hz must be > 0");
-  if (d->in_dtype != PBK_C64 && d->in_dtype != PBK_I8X2 && !(ramp && d->in_dtype == PBK_F32))
+  if (d->in_dtype != PBK_C64 && d->in_dtype != PBK_I8X2 && d->in_dtype != PBK_U4X2 &&
+      d->in_dtype != PBK_U2X2 && !(ramp && d->in_dtype == PBK_F32))
     return fail(PBK_ERR_INVALID, "unknown in_dtype %d", d->in_dtype);
+  if ((d->in_dtype == PBK_U4X2 || d->in_dtype == PBK_U2X2) && (d->nchan * d->npol) % 2)
+    return fail(PBK_ERR_INVALID, "packed input needs an even nchan * npol, got %lld",
+                (long long)(d->nchan * d->npol));
   if (d->out_kind < PBK_OUT_C64 || d->out_kind > PBK_OUT_STOKES_I)
     return fail(PBK_ERR_INVALID, "unknown out_kind %d", d->out_kind);
   if (d->out_kind == PBK_OUT_STOKES_I && d->npol != 2)
@@ -606,7 +620,7 @@ static int dedisp_plan_create_impl(const pbk_dedisp_desc* d, const RampSpec* ram
   pl->out_rows = d->downsample > 1 ? crop_rows / d->downsample : crop_rows;
   pl->row_elems = d->out_kind == PBK_OUT_STOKES_I ? C : I;
   pl->elem_bytes = d->out_kind == PBK_OUT_C64 ? 8 : 4;
-  pl->in_bytes = (size_t)N * I * (d->in_dtype == PBK_C64 ? 8 : d->in_dtype == PBK_F32 ? 4 : 2);
+  pl->in_bytes = ((size_t)N * I * load_bits(load_kind_of(d->in_dtype))) >> 3;
   pl->out_bytes = (size_t)pl->out_rows * pl->row_elems * pl->elem_bytes;
   pl->chirp_bytes = d->explicit_chirp ? (size_t)N * C * 8 : 0;
 
@@ -650,7 +664,7 @@ static int dedisp_plan_create_impl(const pbk_dedisp_desc* d, const RampSpec* ram
     ps.in_role = i == 0 ? ROLE_USER_IN : ROLE_SCRATCH;
     ps.out_role = ROLE_SCRATCH;
     if (i == 0)
-      ps.a.load_kind = d->in_dtype == PBK_I8X2 ? LOAD_I8X2 : d->in_dtype == PBK_F32 ? LOAD_F32 : LOAD_C64;
+      ps.a.load_kind = load_kind_of(d->in_dtype);
     ps.fast = fast_ok;
     ps.pair_ok = pair_ok;
     ts.ensure(l[i]);
@@ -682,7 +696,7 @@ static int dedisp_plan_create_impl(const pbk_dedisp_desc* d, const RampSpec* ram
     ps.in_role = m == 1 ? ROLE_USER_IN : ROLE_SCRATCH;
     ps.out_role = ROLE_SCRATCH;
     if (m == 1) {
-      ps.a.load_kind = d->in_dtype == PBK_I8X2 ? LOAD_I8X2 : d->in_dtype == PBK_F32 ? LOAD_F32 : LOAD_C64;
+      ps.a.load_kind = load_kind_of(d->in_dtype);
       final_epilogue(ps, 0);
     }
     ps.fast = fast_ok;
@@ -1188,14 +1202,14 @@ static int blue_dedisp_plan_create(const pbk_dedisp_desc* d, const RampSpec* ram
   pl->out_rows = d->downsample > 1 ? crop_rows / d->downsample : crop_rows;
   pl->row_elems = d->out_kind == PBK_OUT_STOKES_I ? C : I;
   pl->elem_bytes = d->out_kind == PBK_OUT_C64 ? 8 : 4;
-  pl->in_bytes = (size_t)N * I * (d->in_dtype == PBK_C64 ? 8 : d->in_dtype == PBK_F32 ? 4 : 2);
+  pl->in_bytes = ((size_t)N * I * load_bits(load_kind_of(d->in_dtype))) >> 3;
   pl->out_bytes = (size_t)pl->out_rows * pl->row_elems * pl->elem_bytes;
   pl->chirp_bytes = d->explicit_chirp ? (size_t)N * C * 8 : 0;
   auto cleanup = [&](int code) { pbk_plan_destroy(pl); return code; };
   int rc = blue_setup(b, d->device);
   if (rc != PBK_OK) return cleanup(rc);
   b->in = BlueIO{BlueMap{0, I, d->npol, 1}, 1, N, b->M, I, (int)d->npol,
-                 d->in_dtype == PBK_I8X2 ? LOAD_I8X2 : d->in_dtype == PBK_F32 ? LOAD_F32 : LOAD_C64,
+                 load_kind_of(d->in_dtype),
                  0, 0, 1.0f, 0, N};
   b->out = BlueIO{BlueMap{0, I, d->npol, 1}, 1, N, b->M, I, (int)d->npol, EPI_C64, 1, 0,
                   (float)(1.0 / (double)N), d->crop_start, std::max(d->crop_start, d->crop_stop)};
@@ -1619,6 +1633,54 @@ extern "C" int pbk_fold(const void* in, int64_t nsamp, int64_t row_elems, const 
   CUDA_TRY(cudaMemcpyAsync(profile, dp.p, pb, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(counts, dc.p, cb, cudaMemcpyDeviceToHost, st));
   if (bins_out) CUDA_TRY(cudaMemcpyAsync(bins_out, db.p, bb, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return PBK_OK;
+}
+
+extern "C" int pbk_phase_predict(const double* dt_s, int64_t n, double dt0_s,
+                                 double sample_rate_hz, int64_t n0, const double* coeffs,
+                                 int32_t ncoef, int64_t rphase, void* phase_int, void* phase_frac,
+                                 int32_t on_device, int32_t device, void* stream) {
+  if (!coeffs || !phase_int || !phase_frac) return fail(PBK_ERR_INVALID, "NULL pointer");
+  if (n <= 0) return fail(PBK_ERR_INVALID, "n must be positive");
+  if (ncoef < 1 || ncoef > kFoldMaxCoef)
+    return fail(PBK_ERR_INVALID, "ncoef must be in [1, %d]", kFoldMaxCoef);
+  if (!dt_s && !(sample_rate_hz > 0))
+    return fail(PBK_ERR_INVALID, "sample_rate_hz must be > 0 when times are generated");
+  CUDA_TRY(cudaSetDevice(device));
+  PredictArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  for (int i = 0; i < ncoef; ++i) pa.coef[i] = coeffs[i];
+  pa.ncoef = ncoef;
+  pa.dt0 = dt0_s;
+  pa.sample_rate = sample_rate_hz;
+  pa.n0 = n0;
+  pa.n = n;
+  pa.rphase = rphase;
+  if (on_device) {
+    pa.dt = dt_s;
+    pa.ph_int = reinterpret_cast<long long*>(phase_int);
+    pa.ph_frac = reinterpret_cast<double*>(phase_frac);
+    cudaError_t e = launch_phase_predict(pa, reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "predict launch: %s", cudaGetErrorString(e));
+    return PBK_OK;
+  }
+  DevBuf dd, di, df;
+  const size_t nb = (size_t)n * 8;
+  cudaStream_t st = cudaStreamPerThread;
+  if (dt_s) {
+    CUDA_TRY(cudaMalloc(&dd.p, nb));
+    CUDA_TRY(cudaMemcpyAsync(dd.p, dt_s, nb, cudaMemcpyHostToDevice, st));
+  }
+  CUDA_TRY(cudaMalloc(&di.p, nb));
+  CUDA_TRY(cudaMalloc(&df.p, nb));
+  pa.dt = reinterpret_cast<const double*>(dd.p);
+  pa.ph_int = reinterpret_cast<long long*>(di.p);
+  pa.ph_frac = reinterpret_cast<double*>(df.p);
+  cudaError_t e = launch_phase_predict(pa, st);
+  if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "predict launch: %s", cudaGetErrorString(e));
+  CUDA_TRY(cudaMemcpyAsync(phase_int, di.p, nb, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(phase_frac, df.p, nb, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   return PBK_OK;
 }

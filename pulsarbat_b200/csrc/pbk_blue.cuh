@@ -85,6 +85,8 @@ __global__ void __launch_bounds__(256) blue_pre_kernel(const void* __restrict__ 
       } else if (a.kind == LOAD_I8X2) {
         const char2 c = __ldg(reinterpret_cast<const char2*>(in) + e);
         v = make_float2((float)c.x, (float)c.y);
+      } else if (a.kind == LOAD_U4X2 || a.kind == LOAD_U2X2) {
+        v = ld_packed(in, e, a.kind);
       } else {
         v = make_float2(__ldg(reinterpret_cast<const float*>(in) + e), 0.f);
       }

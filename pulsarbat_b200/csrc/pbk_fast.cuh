@@ -154,7 +154,13 @@ constexpr int EPI_SCRATCH = 3;   // not a final pass: pair-planar complex64 to t
 // 128-bit access is exactly the packed register layout of c2 and needs no shuffling
 enum { LK_C64 = 0, LK_I8 = 1, LK_PLANAR = 2,
        LK_TRANSP = 3 /* user complex64 where every lane pair owns a contiguous run of rows
-                        (ISTFT input): transposed through shared memory */ };
+                        (ISTFT input): transposed through shared memory */,
+       LK_U4 = 4 /* packed 4+4-bit complex: two bytes per lane pair */,
+       LK_U2 = 5 /* packed 2+2-bit complex: one byte per lane pair */ };
+// bits per complex input element
+__host__ __device__ constexpr int lk_bits(int lk) {
+  return lk == LK_I8 ? 16 : lk == LK_U4 ? 8 : lk == LK_U2 ? 4 : 64;
+}
 
 // everything about a tile that is uniform across the CTA; computed by one thread (the address
 // arithmetic has 64-bit divisions) and broadcast through shared memory
@@ -168,7 +174,7 @@ struct TileInfo {
 
 template <class C, int EPI>
 __device__ __forceinline__ void fast_tile_info(const PassArgs& p, long long tile, TileInfo& ti,
-                                               int in_elem_bytes, int out_elem_bytes) {
+                                               int in_elem_bits, int out_elem_bytes) {
   const long long q0 = tile * C::W;              // first lane of the tile
   const long long o = q0 / p.RI;
   const long long r0 = q0 - o * p.RI;
@@ -177,7 +183,8 @@ __device__ __forceinline__ void fast_tile_info(const PassArgs& p, long long tile
   const long long o_orig = o >> p.log2Kprev;
   const long long kprev = o & ((1ll << p.log2Kprev) - 1);
   const long long klow = (kprev >> p.kl_sa) + ((kprev & p.kl_mb) << p.kl_sb);
-  ti.bi = map_base(p.min, o_orig, kprev, klow, nrest, col0, p.P) * in_elem_bytes;
+  // (lane pairs start at even elements, so packed sub-byte inputs land on whole bytes)
+  ti.bi = (map_base(p.min, o_orig, kprev, klow, nrest, col0, p.P) * in_elem_bits) >> 3;
   long long bo = map_base(p.mout, o_orig, kprev, klow, nrest, col0, p.P) * out_elem_bytes;
   ti.nrest = (unsigned)nrest;
   ti.klow = (unsigned)klow;
@@ -227,6 +234,14 @@ __device__ __forceinline__ c2 fast_load(const FastTile& T, unsigned row, unsigne
     const float4 t = ldg_stream_f4(a);
     v.re = make_float2(t.x, t.z);
     v.im = make_float2(t.y, t.w);
+  } else if (LOADK == LK_U4) {
+    const unsigned t = __ldcs(reinterpret_cast<const unsigned short*>(a));
+    v.re = make_float2(dec4(t), dec4(t >> 8));
+    v.im = make_float2(dec4(t >> 4), dec4(t >> 12));
+  } else if (LOADK == LK_U2) {
+    const unsigned t = __ldcs(reinterpret_cast<const unsigned char*>(a));
+    v.re = make_float2(dec2(t & 3u), dec2((t >> 4) & 3u));
+    v.im = make_float2(dec2((t >> 2) & 3u), dec2((t >> 6) & 3u));
   } else {
     const char4 t = __ldcs(reinterpret_cast<const char4*>(a));
     v.re = make_float2((float)t.x, (float)t.z);
@@ -581,9 +596,9 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
   const int tid = threadIdx.x;
   const int pr = tid & (C::PW - 1);
 
-  constexpr int in_eb = LOADK == LK_I8 ? 2 : 8;
+  constexpr int in_bits = lk_bits(LOADK);   // BITS per complex input element
   constexpr int out_eb = (EPI == EPI_INTENSITY || EPI == EPI_STOKES_I) ? 4 : 8;
-  const unsigned rb_in = (unsigned)(p.min.a_row * in_eb);
+  const unsigned rb_in = (unsigned)((p.min.a_row * in_bits) >> 3);
   const unsigned rb_out = (unsigned)(p.mout.a_row * out_eb);
 
   static_assert(!TSUM || (MODE == MODE_INV && !NARROW &&
@@ -605,7 +620,7 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
   const long long t_end = TSUM ? ts_total * (ts_r + 1) / ts_nr : ntiles;
   const long long t_step = TSUM ? 1 : gridDim.x;
   for (int i = tid; i < C::TW_TOTAL; i += C::NT) tws[i] = tables[i];
-  if (tid == 0 && t < t_end) fast_tile_info<C, EPI>(p, tile_at(t), *sinfo, in_eb, out_eb);
+  if (tid == 0 && t < t_end) fast_tile_info<C, EPI>(p, tile_at(t), *sinfo, in_bits, out_eb);
   __syncthreads();
 
   // Per-thread part of the addresses.  A tile is W adjacent lanes; a lane is (row jr, column) of
@@ -623,7 +638,7 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
   const long long row_in = LASTLEVEL ? p.min.a_kp : p.min.a_n;
   const long long row_out = LASTLEVEL ? p.mout.a_kp : p.mout.a_n;
   const long long off_in =
-      (jr * row_in + (long long)(colt / p.P) * p.min.a_c + (colt % p.P) * p.min.a_p) * in_eb;
+      ((jr * row_in + (long long)(colt / p.P) * p.min.a_c + (colt % p.P) * p.min.a_p) * in_bits) >> 3;
   const long long off_out =
       (jr * row_out + (long long)(colt / p.P) * p.mout.a_c + (colt % p.P) * p.mout.a_p) * out_eb;
   const int chant = colt / p.P;
@@ -696,7 +711,7 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
     // the next tile's record, which the end-of-tile barrier publishes
 #define PBK_NEXT_TILE_INFO()                                                        \
   if (tid == 0 && t + t_step < t_end)                                               \
-    fast_tile_info<C, EPI>(p, tile_at(t + t_step), *sinfo, in_eb, out_eb)
+    fast_tile_info<C, EPI>(p, tile_at(t + t_step), *sinfo, in_bits, out_eb)
     if (MODE == MODE_INV) PBK_NEXT_TILE_INFO();
 
     if (MODE == MODE_FWD) {

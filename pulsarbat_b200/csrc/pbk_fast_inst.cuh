@@ -87,6 +87,10 @@ static cudaError_t cfg_launch(int mode, const PassArgs& a, const float2* d_table
       }
       if (a.load_kind == LOAD_I8X2)
         return cfg_launch_mode<MODE_FWD, C, LK_I8, EPI_SCRATCH>(a, d_tables, ntiles, num_sms, st);
+      if (a.load_kind == LOAD_U4X2)
+        return cfg_launch_mode<MODE_FWD, C, LK_U4, EPI_SCRATCH>(a, d_tables, ntiles, num_sms, st);
+      if (a.load_kind == LOAD_U2X2)
+        return cfg_launch_mode<MODE_FWD, C, LK_U2, EPI_SCRATCH>(a, d_tables, ntiles, num_sms, st);
       if (a.load_kind == LOAD_PLANAR)
         return cfg_launch_mode<MODE_FWD, C, LK_PLANAR, EPI_SCRATCH>(a, d_tables, ntiles, num_sms,
                                                                     st);

@@ -34,7 +34,17 @@ namespace pbk {
 
 enum { MODE_FWD = 0, MODE_MID = 1, MODE_INV = 2 };
 enum { LOAD_C64 = 0, LOAD_I8X2 = 1, LOAD_PLANAR = 2, LOAD_F32 = 3 /* real input, im = 0 */,
-       LOAD_TRANSP = 4 /* fast kernels only: complex64 input transposed through shared memory */ };
+       LOAD_TRANSP = 4 /* fast kernels only: complex64 input transposed through shared memory */,
+       LOAD_U4X2 = 5 /* packed 4+4-bit complex */, LOAD_U2X2 = 6 /* packed 2+2-bit complex */ };
+
+// bits per complex input element of a load kind
+__host__ __device__ constexpr int load_bits(int kind) {
+  return kind == LOAD_I8X2 ? 16 : kind == LOAD_U4X2 ? 8 : kind == LOAD_U2X2 ? 4
+         : kind == LOAD_F32 ? 32 : 64;
+}
+__host__ __device__ constexpr bool load_is_raw(int kind) {
+  return kind == LOAD_I8X2 || kind == LOAD_U4X2 || kind == LOAD_U2X2;
+}
 enum { EPI_C64 = 0, EPI_INTENSITY = 1, EPI_STOKES_I = 2 };
 enum { CHIRP_NONE = 0, CHIRP_COMPUTED = 1, CHIRP_ARRAY = 2, CHIRP_RAMP = 3 };
 
@@ -295,6 +305,23 @@ __device__ __forceinline__ void st_lane(const PassArgs& p, long long e, float re
   }
 }
 
+// packed raw samples (include/pbk.h: PBK_U4X2, PBK_U2X2)
+__device__ __forceinline__ float dec4(unsigned c) { return (float)((int)(c & 15u) - 8); }
+__device__ __forceinline__ float dec2(unsigned c) {
+  const float mag = (((c ^ (c >> 1)) & 1u) == 0u) ? 3.3359f : 1.0f;   // codes 0 and 3 are the outer levels
+  return (c & 2u) ? mag : -mag;
+}
+// complex element e of a packed array
+__device__ __forceinline__ float2 ld_packed(const void* base, long long e, int kind) {
+  const unsigned char* b = reinterpret_cast<const unsigned char*>(base);
+  if (kind == LOAD_U4X2) {
+    const unsigned v = __ldg(b + e);
+    return make_float2(dec4(v), dec4(v >> 4));
+  }
+  const unsigned v = (unsigned)__ldg(b + (e >> 1)) >> ((e & 1) * 4);
+  return make_float2(dec2(v & 3u), dec2((v >> 2) & 3u));
+}
+
 template <bool FAST>
 __device__ __forceinline__ c2 load_row(const PassArgs& p, const LaneCtx& L, long long row) {
   c2 v;
@@ -331,6 +358,12 @@ __device__ __forceinline__ c2 load_row(const PassArgs& p, const LaneCtx& L, long
       v.re = make_float2(a.x, b.x);
       v.im = make_float2(a.y, b.y);
     }
+  } else if (p.load_kind == LOAD_U4X2 || p.load_kind == LOAD_U2X2) {
+    float2 a = make_float2(0.f, 0.f), b = a;
+    if (L.valid[0]) a = ld_packed(p.in, L.bin[0] + row * p.min.a_row, p.load_kind);
+    if (L.valid[1]) b = ld_packed(p.in, L.bin[1] + row * p.min.a_row, p.load_kind);
+    v.re = make_float2(a.x, b.x);
+    v.im = make_float2(a.y, b.y);
   } else {
     const char2* in = reinterpret_cast<const char2*>(p.in);
     if (FAST) {

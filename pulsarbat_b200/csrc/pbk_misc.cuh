@@ -342,6 +342,41 @@ __device__ __forceinline__ int fold_bin(const FoldArgs& a, long long n) {
   return (int)(b % a.nbin);
 }
 
+// Device-side PhasePredictor.__call__ (pulsar/predictor.py:121-147) for one polyco entry: the
+// phase polynomial at dt seconds from the entry's tmid, evaluated with numpy's Horner order in FP64
+// without FMA contraction (bit-equal to Polynomial.__call__), split as pulsar/phase.py:28-78 does
+// into integer cycles (reference phase + nearest integer) and a fraction in [-0.5, 0.5].
+// dt is either given per element or generated as dt0 + (n0 + i) / sample_rate.
+struct PredictArgs {
+  const double* dt;
+  double dt0, sample_rate;
+  long long n0, n;
+  double coef[kFoldMaxCoef];
+  int ncoef;
+  long long rphase;
+  long long* ph_int;
+  double* ph_frac;
+};
+
+__global__ void __launch_bounds__(256) phase_predict_kernel(const PredictArgs a) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double t = a.dt ? a.dt[i]
+                          : __dadd_rn(a.dt0, __ddiv_rn((double)(a.n0 + i), a.sample_rate));
+    double c0 = a.coef[a.ncoef - 1];
+    for (int j = a.ncoef - 2; j >= 0; --j) c0 = __dadd_rn(a.coef[j], __dmul_rn(c0, t));
+    const double whole = rint(c0);
+    a.ph_int[i] = a.rphase + (long long)whole;
+    a.ph_frac[i] = __dsub_rn(c0, whole);
+  }
+}
+
+static inline cudaError_t launch_phase_predict(const PredictArgs& a, cudaStream_t st) {
+  const long long blocks = std::min<long long>((a.n + 255) / 256, 148 * 8);
+  phase_predict_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
 // ---- wide rows (row_elems >= 32): one CTA owns SPAN consecutive samples x up to 256 elements.
 // Bins of a chunk of 64 samples are computed once into shared memory; every thread walks its
 // element down the chunk (coalesced row segments, 8 loads in flight) and keeps the running sum of

@@ -19,7 +19,8 @@ def _maps():
     if _NP2T is None:
         _NP2T = {np.dtype(np.complex64): torch.complex64, np.dtype(np.complex128): torch.complex128,
                  np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
-                 np.dtype(np.int8): torch.int8, np.dtype(np.int32): torch.int32,
+                 np.dtype(np.int8): torch.int8, np.dtype(np.uint8): torch.uint8,
+                 np.dtype(np.int32): torch.int32,
                  np.dtype(np.int64): torch.int64}
     return _NP2T
 

@@ -19,7 +19,8 @@ from . import _lib as L
 from .device import DeviceArray
 
 __all__ = ["default_device", "dedisperse", "chirp", "detect", "shift_channels", "phase_ramp", "mix", "analytic_decimate", "stokes", "pol_basis",
-           "downsample", "fft", "stft", "istft", "fold", "clear_plan_cache", "pinned_results"]
+           "downsample", "fft", "stft", "istft", "fold", "predict_phase", "clear_plan_cache",
+           "pinned_results"]
 
 
 def default_device():
@@ -130,32 +131,54 @@ def _real_of(cdtype):
 # --------------------------------------------------------------------------------------------
 # coherent dedispersion            reference: transforms/dedispersion.py:81-133
 # --------------------------------------------------------------------------------------------
+_RAW_KINDS = {"int8": (L.PBK_I8X2, np.int8), "u4": (L.PBK_U4X2, np.uint8),
+              "u2": (L.PBK_U2X2, np.uint8)}
+
+
 def dedisperse(data, *, dm, sample_rate_hz, chan_freq_hz, ref_freq_hz, crop=None,
-               out_kind=L.OUT_C64, downsample=1, chirp_array=None, int8=False, device=None):
+               out_kind=L.OUT_C64, downsample=1, chirp_array=None, int8=False, raw=None,
+               raw_shape=None, device=None):
     """ifft(fft(x, axis=0) * H, axis=0)[start:stop] (+ optional fused detection / time sum).
 
-    ``data`` is (nsamp, nchan, ...) complex, or with ``int8=True`` (nsamp, nchan, ..., 2) int8
-    (re, im) pairs.  ``crop`` is the (start, stop) computed by the caller as in
-    dedispersion.py:127-131; None keeps all rows.  Returns an array shaped (rows, nchan, ...)
-    (Stokes I drops the pol axis).
+    ``data`` is (nsamp, nchan, ...) complex, or raw baseband decoded inside the first pass:
+    ``raw="int8"`` (same as ``int8=True``): (nsamp, nchan, ..., 2) int8 (re, im) pairs;
+    ``raw="u4"``: (nsamp, nchan, ...) uint8, one byte per complex sample (low nibble re, high
+    nibble im, value = code - 8); ``raw="u2"``: uint8 with two complex samples per byte
+    (nsamp rows of nchan*npol/2 bytes; levels -3.3359, -1, 1, 3.3359) together with
+    ``raw_shape=(nchan, ...)``, the logical shape of a row.  ``crop`` is the (start, stop)
+    computed by the caller as in dedispersion.py:127-131; None keeps all rows.  Returns an array
+    shaped (rows, nchan, ...) (Stokes I drops the pol axis).
     """
+    if int8 and raw is None:
+        raw = "int8"
+    if raw is not None and raw not in _RAW_KINDS:
+        raise ValueError(f"raw must be one of {sorted(_RAW_KINDS)}, got {raw!r}")
+    int8 = raw is not None            # below: "the input is raw bytes"
     shape = tuple(data.shape)
-    body = shape[:-1] if int8 else shape
+    if raw == "u2":
+        if raw_shape is None:
+            raise ValueError('raw="u2" needs raw_shape=(nchan, ...)')
+        body = (shape[0],) + tuple(int(v) for v in raw_shape)
+        if int(np.prod(body[1:])) != 2 * int(np.prod(shape[1:])):
+            raise ValueError(f"raw_shape {raw_shape} does not match rows of {shape[1:]} bytes")
+    else:
+        body = shape[:-1] if raw == "int8" else shape
     nsamp, nchan = body[0], body[1]
     trailing = body[2:]
     npol = int(np.prod(trailing)) if trailing else 1
+    in_dtype, raw_np = _RAW_KINDS[raw] if raw is not None else (L.PBK_C64, None)
     start, stop = (0, nsamp) if crop is None else (int(crop[0]), int(crop[1]))
     if stop <= start:
         start, stop = 0, 0
     freqs = np.ascontiguousarray(chan_freq_hz, dtype=np.float64)
     dev = (data.device if _is_dev(data) else (default_device() if device is None else device))
-    key = ("dedisp", nsamp, nchan, npol, bool(int8), int(out_kind), float(dm),
+    key = ("dedisp", nsamp, nchan, npol, raw, int(out_kind), float(dm),
            float(sample_rate_hz), float(ref_freq_hz), freqs.tobytes(), start, stop,
            int(downsample), chirp_array is not None, dev)
     ent = _get_plan(key, lambda: L.DedispPlan(
         nsamp=nsamp, nchan=nchan, npol=npol, dm=dm, sample_rate_hz=sample_rate_hz,
         ref_freq_hz=ref_freq_hz, chan_freq_hz=freqs, crop=(start, stop),
-        in_dtype=L.PBK_I8X2 if int8 else L.PBK_C64, out_kind=out_kind, downsample=downsample,
+        in_dtype=in_dtype, out_kind=out_kind, downsample=downsample,
         explicit_chirp=chirp_array is not None, device=dev))
     plan = ent.plan
     out_trailing = (nchan,) if out_kind == L.OUT_STOKES_I else (nchan,) + trailing
@@ -177,7 +200,7 @@ def dedisperse(data, *, dm, sample_rate_hz, chan_freq_hz, ref_freq_hz, crop=None
         return out
 
     if int8:
-        x, odt = np.ascontiguousarray(data, dtype=np.int8), np.complex64
+        x, odt = np.ascontiguousarray(data, dtype=raw_np), np.complex64
     else:
         x, odt = _host_c64(data)
     out = _result(out_shape, np.complex64 if out_kind == L.OUT_C64 else np.float32)
@@ -527,3 +550,44 @@ def fold(data, coeffs, sample_rate_hz, nbin, n0=0, profile=None, counts=None, wa
     L.check(L.lib().pbk_fold(L.ptr(x), nsamp, relems, cp, len(c), float(sample_rate_hz), int(n0),
                              int(nbin), L.ptr(profile), L.ptr(counts), L.ptr(bins), 0, dev, None))
     return (profile, counts, bins) if want_bins else (profile, counts)
+
+
+def predict_phase(coeffs, rphase, *, dt_s=None, nsamp=None, dt0_s=0.0, sample_rate_hz=None, n0=0,
+                  on_device=False, device=None):
+    """Pulse phase from ONE polyco entry (reference pulsar/predictor.py:121-147): polyval at dt
+    seconds from the entry's tmid in numpy's Horner order (FP64, no FMA), returned as
+    (int64 cycles = rphase + nearest integer, FP64 fraction in [-0.5, 0.5]) like pulsar/phase.py.
+
+    Give the offsets ``dt_s`` (array, host or DeviceArray) or let the kernel generate them for
+    ``nsamp`` samples: dt = dt0_s + (n0 + i) / sample_rate_hz.  ``on_device`` keeps generated
+    results on the GPU as DeviceArrays."""
+    c = np.ascontiguousarray(coeffs, dtype=np.float64)
+    cp = c.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    if dt_s is None:
+        if nsamp is None or sample_rate_hz is None:
+            raise ValueError("give dt_s, or nsamp and sample_rate_hz")
+        n, shape = int(nsamp), (int(nsamp),)
+    else:
+        shape = tuple(dt_s.shape)
+        n = int(np.prod(shape))
+    sr = 0.0 if sample_rate_hz is None else float(sample_rate_hz)
+    if _is_dev(dt_s) or (dt_s is None and on_device):
+        dev = dt_s.device if _is_dev(dt_s) else (default_device() if device is None else device)
+        x = None
+        if dt_s is not None:
+            x = dt_s.contiguous()
+            if x.dtype != np.float64:
+                x = x.astype(np.float64)
+        pi = DeviceArray.empty(shape, np.int64, dev)
+        pf = DeviceArray.empty(shape, np.float64, dev)
+        L.check(L.lib().pbk_phase_predict(L.ptr(x.ptr) if x is not None else None, n,
+                                          float(dt0_s), sr, int(n0), cp, len(c), int(rphase),
+                                          L.ptr(pi.ptr), L.ptr(pf.ptr), 1, dev,
+                                          ctypes.c_void_p(_stream())))
+        return pi, pf
+    dev = default_device() if device is None else device
+    x = None if dt_s is None else np.ascontiguousarray(dt_s, dtype=np.float64)
+    pi, pf = np.empty(shape, np.int64), np.empty(shape, np.float64)
+    L.check(L.lib().pbk_phase_predict(L.ptr(x), n, float(dt0_s), sr, int(n0), cp, len(c),
+                                      int(rphase), L.ptr(pi), L.ptr(pf), 0, dev, None))
+    return pi, pf

@@ -99,6 +99,36 @@ class PhasePredictor:
         ints = (np.int64(e.rphase) + whole.astype(np.int64))
         return ints, val - whole
 
+    def sample_phases(self, start_time, nsamp, sample_rate, *, on_device=False, device=None):
+        """Phase of every sample of a block on the GPU: the reference's ``predictor(times)`` for
+        ``times = start_time + arange(nsamp) / sample_rate`` (predictor.py:121-147), entry by
+        entry as its ``np.unique(index)`` loop does.  Returns (int64 cycles, FP64 fraction);
+        raises the reference's ValueError when a sample lies outside the predictor's range."""
+        from .. import kernels
+        sr = float(u.to_value(sample_rate, u.Hz))
+        t0 = Time(start_time)
+        self._index_and_dt(t0 + ((nsamp - 1) / sr) * u.s)          # range check of the last sample
+        ends = [e.tmid + e.span / 2 for e in self.entries]
+        parts, first = [], 0
+        while first < nsamp:
+            t_first = t0 + (first / sr) * u.s
+            idx, dt = self._index_and_dt(t_first)
+            left = float((ends[idx] - t_first).to_value(u.s)) * sr
+            count = nsamp - first if idx == len(self.entries) - 1 else \
+                max(1, min(nsamp - first, int(np.floor(left + 1e-9)) + 1))
+            e = self.entries[idx]
+            parts.append(kernels.predict_phase(e.poly.coef, e.rphase, nsamp=count, dt0_s=dt,
+                                               sample_rate_hz=sr, on_device=on_device,
+                                               device=device))
+            first += count
+        if len(parts) == 1:
+            return parts[0]
+        if on_device:
+            import torch
+            from ..device import DeviceArray
+            return tuple(DeviceArray(torch.cat([p[k].tensor for p in parts])) for k in (0, 1))
+        return tuple(np.concatenate([p[k] for p in parts]) for k in (0, 1))
+
     def f0(self, t, n=0):
         """Spin frequency (n=0) or its derivatives, cycles / s^(n+1) (predictor.py:162-174)."""
         idx, dt = self._index_and_dt(t)

@@ -38,14 +38,16 @@ def _get_state(key, make):
 
 
 def dedisperse_blocks(blocks, *, dm, sample_rate_hz, chan_freq_hz, ref_freq_hz, crop=None,
-                      out_kind=L.OUT_C64, downsample=1, int8=False, device=None, pinned_out=False):
+                      out_kind=L.OUT_C64, downsample=1, int8=False, raw=None, raw_shape=None,
+                      device=None, pinned_out=False):
     """Generator: dedisperse every block of ``blocks`` (numpy arrays of one common shape, ideally
     in pinned memory) and yield the results in order as numpy arrays.
 
     Equivalent to ``[kernels.dedisperse(b, ...) for b in blocks]``; the copy of the next block
     overlaps the kernels of the current one.  With ``pinned_out=True`` each result is a view of
     one of two alternating pinned host buffers and is only valid until the next item is requested
-    (no extra host copy); by default a fresh array is returned.
+    (no extra host copy); by default a fresh array is returned.  ``raw`` / ``raw_shape`` select
+    packed raw input exactly as in :func:`kernels.dedisperse` (``int8=True`` is ``raw="int8"``).
     """
     import torch
     dev = kernels.default_device() if device is None else device
@@ -55,9 +57,21 @@ def dedisperse_blocks(blocks, *, dm, sample_rate_hz, chan_freq_hz, ref_freq_hz, 
         first = next(it)
     except StopIteration:
         return
-    first = np.ascontiguousarray(first, dtype=np.int8 if int8 else np.complex64)
+    if int8 and raw is None:
+        raw = "int8"
+    if raw is not None and raw not in kernels._RAW_KINDS:
+        raise ValueError(f"raw must be one of {sorted(kernels._RAW_KINDS)}, got {raw!r}")
+    in_dtype, raw_np = kernels._RAW_KINDS[raw] if raw is not None else (L.PBK_C64, np.complex64)
+    first = np.ascontiguousarray(first, dtype=raw_np)
     shape = first.shape
-    body = shape[:-1] if int8 else shape
+    if raw == "u2":
+        if raw_shape is None:
+            raise ValueError('raw="u2" needs raw_shape=(nchan, ...)')
+        body = (shape[0],) + tuple(int(v) for v in raw_shape)
+        if int(np.prod(body[1:])) != 2 * int(np.prod(shape[1:])):
+            raise ValueError(f"raw_shape {raw_shape} does not match rows of {shape[1:]} bytes")
+    else:
+        body = shape[:-1] if raw == "int8" else shape
     nsamp, nchan = body[0], body[1]
     trailing = body[2:]
     npol = int(np.prod(trailing)) if trailing else 1
@@ -65,14 +79,14 @@ def dedisperse_blocks(blocks, *, dm, sample_rate_hz, chan_freq_hz, ref_freq_hz, 
     if stop <= start:
         start, stop = 0, 0
     freqs = np.ascontiguousarray(chan_freq_hz, dtype=np.float64)
-    in_t = torch.int8 if int8 else torch.complex64
+    in_t = {None: torch.complex64, "int8": torch.int8}.get(raw, torch.uint8)
     out_t = torch.complex64 if out_kind == L.OUT_C64 else torch.float32
 
     def make():
         plan = L.DedispPlan(nsamp=nsamp, nchan=nchan, npol=npol, dm=dm,
                             sample_rate_hz=sample_rate_hz, ref_freq_hz=ref_freq_hz,
                             chan_freq_hz=freqs, crop=(start, stop),
-                            in_dtype=L.PBK_I8X2 if int8 else L.PBK_C64, out_kind=out_kind,
+                            in_dtype=in_dtype, out_kind=out_kind,
                             downsample=downsample, device=dev)
         out_trailing = (nchan,) if out_kind == L.OUT_STOKES_I else (nchan,) + tuple(trailing)
         out_shape = (plan.out_rows,) + out_trailing
@@ -84,7 +98,7 @@ def dedisperse_blocks(blocks, *, dm, sample_rate_hz, chan_freq_hz, ref_freq_hz, 
                     torch.cuda.Stream(tdev), torch.cuda.Stream(tdev), torch.cuda.Stream(tdev),
                     [torch.cuda.Event() for _ in range(6)])
 
-    key = (shape, bool(int8), float(dm), float(sample_rate_hz), float(ref_freq_hz),
+    key = (shape, raw, body, float(dm), float(sample_rate_hz), float(ref_freq_hz),
            freqs.tobytes(), start, stop, int(out_kind), int(downsample), dev)
     plan, d_in, d_out, h_out, s_copy, s_comp, s_down, ev = _get_state(key, make)
     copied, consumed, done = ev[0:2], ev[2:4], ev[4:6]   # per slot: H2D done / kernels done / D2H done

@@ -345,3 +345,83 @@ def test_pinned_result_arrays():
     keep = pinned[5:7].copy()
     del pinned
     assert np.isfinite(keep).all()
+
+
+def test_device_phase_prediction_bit_exact():
+    """pbk_phase_predict = PhasePredictor.__call__ (reference pulsar/predictor.py:121-147) for the
+    samples of a block: bit-equal to numpy's polyval of the entry polynomial and to the int/frac
+    split of pulsar/phase.py, for given offsets and for generated sample times, on host arrays and
+    device arrays; across polyco entries it follows the entry the reference selects."""
+    import pulsarbat_b200 as pb
+    u = pb.units
+    here = os.path.dirname(os.path.abspath(__file__))
+    path = os.path.join(here, "golden", "timing.dat")
+    pred = pb.PhasePredictor.from_polyco(path)
+    with open(path) as f:
+        entries = orc.parse_polyco(f.read())
+    e = pred.entries[3]
+    rng = np.random.default_rng(23)
+    dt = rng.uniform(-2700.0, 2700.0, 100_001)
+    want = orc.polyval_numpy(dt, e.poly.coef)
+    pi, pf = pb.kernels.predict_phase(e.poly.coef, e.rphase, dt_s=dt)
+    assert pi.dtype == np.int64 and pf.dtype == np.float64
+    assert np.array_equal(pi, e.rphase + np.rint(want).astype(np.int64))
+    assert np.array_equal(pf, want - np.rint(want))
+    assert np.all(np.abs(pf) <= 0.5)
+    di, df = pb.kernels.predict_phase(e.poly.coef, e.rphase, dt_s=pb.DeviceArray.from_numpy(dt))
+    assert np.array_equal(np.asarray(di), pi) and np.array_equal(np.asarray(df), pf)
+    # generated sample times: dt0 + (n0 + i) / sample_rate
+    sr, n0, n = 1234.5, 77, 50_000
+    gi, gf = pb.kernels.predict_phase(e.poly.coef, e.rphase, nsamp=n, dt0_s=-100.25,
+                                      sample_rate_hz=sr, n0=n0)
+    w2 = orc.polyval_numpy(-100.25 + (n0 + np.arange(n)) / sr, e.poly.coef)
+    assert np.array_equal(gi, e.rphase + np.rint(w2).astype(np.int64))
+    assert np.array_equal(gf, w2 - np.rint(w2))
+    # a block spanning four entries, against the oracle's predictor stretch by stretch
+    t0 = pb.Time(pred.entries[0].tmid.mjd + 0.02)
+    sr, nsamp = 500.0, 6_000_000
+    si, sf = pred.sample_phases(t0, nsamp, sr * u.Hz)
+    from pulsarbat_b200.pulsar.folding import fold_segments
+    z0 = pb.Signal(np.zeros((nsamp, 1), np.float32), sample_rate=sr * u.Hz, start_time=t0)
+    segs = fold_segments(z0, pred)
+    assert len(segs) == 4
+    for first, count, _ in segs:
+        tf = t0 + (first / sr) * u.s
+        oi, of = orc.predict_phase(entries, (tf.jd1, tf.jd2), np.arange(count) / sr)
+        assert np.array_equal(si[first:first + count], oi)
+        # the kernel adds the sample offset to dt before the polynomial exactly as the oracle does
+        assert np.array_equal(sf[first:first + count], of)
+    with pytest.raises(ValueError):
+        pred.sample_phases(pb.Time(pred.entries[-1].tmid.mjd + 1.0), 10, sr * u.Hz)
+    ddi, ddf = pred.sample_phases(t0, 100_000, sr * u.Hz, on_device=True)
+    assert np.array_equal(np.asarray(ddi), si[:100_000]) and np.array_equal(np.asarray(ddf), sf[:100_000])
+
+
+def test_raw_packed_blocks_through_the_api():
+    """kernels.dedisperse / streaming.dedisperse_blocks with raw="u4" / "u2" / "int8" blocks give
+    what the complex64 path gives on the decoded samples (fused Stokes I + time sum included)."""
+    import pulsarbat_b200 as pb
+    from pulsarbat_b200 import _lib as L
+    rng = np.random.default_rng(31)
+    N, C = 2 ** 14, 16
+    sr, fcen, dm = 1e6, 600e6, 0.3
+    kw = dict(dm=dm, sample_rate_hz=sr, chan_freq_hz=orc.channel_freqs(fcen, sr, C),
+              ref_freq_hz=fcen, crop=(128, N - 256), out_kind=L.OUT_STOKES_I, downsample=8)
+    raw4 = [rng.integers(0, 256, size=(N, C, 2), dtype=np.uint8) for _ in range(3)]
+    raw2 = [rng.integers(0, 256, size=(N, C), dtype=np.uint8) for _ in range(3)]
+    for blocks, kind, dec, extra in [
+            (raw4, "u4", orc.unpack_u4, {}),
+            (raw2, "u2", lambda r: orc.unpack_u2(r).reshape(N, C, 2), {"raw_shape": (C, 2)})]:
+        want = [pb.kernels.dedisperse(dec(b), **kw) for b in blocks]
+        one = pb.kernels.dedisperse(blocks[0], raw=kind, **extra, **kw)
+        assert one.shape == want[0].shape and np.array_equal(one, want[0])
+        got = list(pb.streaming.dedisperse_blocks(iter(blocks), raw=kind, **extra, **kw))
+        assert len(got) == 3
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w)
+        dev = pb.kernels.dedisperse(pb.DeviceArray.from_numpy(blocks[1]), raw=kind, **extra, **kw)
+        assert np.array_equal(np.asarray(dev), want[1])
+    with pytest.raises(ValueError):
+        pb.kernels.dedisperse(raw2[0], raw="u2", **kw)               # raw_shape missing
+    with pytest.raises(ValueError):
+        pb.kernels.dedisperse(raw2[0], raw="u3", **kw)

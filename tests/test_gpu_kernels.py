@@ -775,3 +775,63 @@ def test_dedisp_fused_time_sum(N, C, M, crop, out_kind):
             del os.environ["PBK_NO_FUSED_SUM"]
         assert "timesum" not in desc2
         assert relerr(got, plain) < 2e-6
+
+
+def _pack_u4(rng, shape):
+    """random 4+4-bit complex samples: uint8 array of `shape`."""
+    return rng.integers(0, 256, size=shape, dtype=np.uint8)
+
+
+@pytest.mark.parametrize("N, C, P", [
+    (2 ** 16, 64, 2),     # fast kernels, wide tiles
+    (2 ** 18, 4, 2),      # fast kernels, narrow tiles
+    (2 ** 14, 16, 1),     # single polarisation
+    (4096, 3, 2),         # generic kernels (odd channel count)
+    (4233, 2, 2),         # arbitrary length (Bluestein)
+    (2 ** 10, 2, 2),      # single-level plan
+])
+@pytest.mark.parametrize("kind", ["u4", "u2"])
+def test_dedisp_packed_raw_input(N, C, P, kind):
+    """Packed 4-bit / 2-bit complex baseband (include/pbk.h PBK_U4X2 / PBK_U2X2) decoded in the
+    load of the first pass == oracle unpack followed by the complex64 path (row U: exact decode,
+    then the usual 1e-5 tolerance of the transform)."""
+    L = _lib()
+    rng = np.random.default_rng(N + C + P)
+    sr, fcen, dm = 1e6, 800e6, 1.0
+    I = C * P
+    if kind == "u4":
+        raw = _pack_u4(rng, (N, I))
+        x = orc.unpack_u4(raw).reshape(N, C, P)
+        in_dtype = L.PBK_U4X2
+    else:
+        raw = rng.integers(0, 256, size=(N, I // 2), dtype=np.uint8)
+        x = orc.unpack_u2(raw).reshape(N, C, P)
+        in_dtype = L.PBK_U2X2
+    assert set(np.unique(x.real)) <= (set(range(-8, 8)) if kind == "u4" else
+                                      set(np.float32([-3.3359, -1, 1, 3.3359]).tolist()))
+    freqs = orc.channel_freqs(fcen, sr, C, "center")
+    want, s0, s1 = orc.coherent_dedispersion(x, dm, sample_rate=sr, center_freq=fcen, crop=False)
+    plan = L.DedispPlan(nsamp=N, nchan=C, npol=P, dm=dm, sample_rate_hz=sr, ref_freq_hz=fcen,
+                        chan_freq_hz=freqs, crop=(0, N), in_dtype=in_dtype)
+    got = plan.exec_host(raw, plan.out_array())
+    desc = plan.describe()
+    plan.destroy()
+    assert relerr(got.reshape(want.shape), want) < 1e-5, desc
+    # the decode itself is exact: the same plan on the unpacked complex64 gives the same bits
+    plan = L.DedispPlan(nsamp=N, nchan=C, npol=P, dm=dm, sample_rate_hz=sr, ref_freq_hz=fcen,
+                        chan_freq_hz=freqs, crop=(0, N))
+    got64 = plan.exec_host(np.ascontiguousarray(x), plan.out_array())
+    desc64 = plan.describe()
+    plan.destroy()
+    if desc64 == desc:      # (a single-level plan reads raw input through the generic kernel)
+        assert np.array_equal(got, got64), desc
+    else:
+        assert relerr(got, got64) < 2e-6, (desc, desc64)
+
+
+def test_packed_input_needs_even_row():
+    L = _lib()
+    with pytest.raises(L.PbkError):
+        L.DedispPlan(nsamp=1024, nchan=3, npol=1, dm=1.0, sample_rate_hz=1e6, ref_freq_hz=8e8,
+                     chan_freq_hz=orc.channel_freqs(8e8, 1e6, 3, "center"), crop=(0, 1024),
+                     in_dtype=L.PBK_U2X2)

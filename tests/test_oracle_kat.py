@@ -337,3 +337,16 @@ def test_real_to_complex_theoretical():
     with pytest.raises(ValueError):
         orc.real_to_complex(np.ones((8, 2), complex))
     assert orc.real_to_complex(np.ones(32, np.float32)).dtype == np.complex64
+
+
+def test_packed_sample_decoders():
+    """Builder-defined raw formats (include/pbk.h PBK_U4X2 / PBK_U2X2): offset-binary 4-bit and the
+    four-level 2-bit code, first sample in the least significant bits."""
+    b = np.array([[0x00, 0xF8, 0x7F, 0x19]], dtype=np.uint8)
+    assert np.array_equal(orc.unpack_u4(b), np.array([[-8 - 8j, 0 + 7j, 7 - 1j, 1 - 7j]],
+                                                     dtype=np.complex64))
+    hi = np.float32(3.3359)
+    # byte 0b11_10_01_00: sample 0 = (code 0, code 1), sample 1 = (code 2, code 3)
+    got = orc.unpack_u2(np.array([[0b11100100]], dtype=np.uint8))
+    assert got.shape == (1, 2)
+    assert np.array_equal(got, np.array([[-hi - 1j, 1 + 1j * hi]], dtype=np.complex64))
