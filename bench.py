@@ -48,6 +48,17 @@ WORKLOADS = {
     "cfg3_shard": dict(N=2 ** 22, C=128, P=2, dm=100.0, sr=390625.0, fcen=600e6, stokes=None,
                        ds=1, int8=True, Call=1024,
                        text="one GPU's shard of cfg3: int8 complex 2^22 x 128 chan x 2 pol -> c64"),
+    # cfg2's geometry and output fed with raw baseband (what a recorder delivers): the decode is
+    # fused into the first pass, so the end-to-end path moves 4x / 8x / 16x fewer PCIe bytes
+    "cfg2_int8": dict(N=2 ** 22, C=64, P=2, dm=100.0, sr=6.25e6, fcen=600e6, stokes=True, ds=64,
+                      int8=True, raw="int8",
+                      text="cfg2 geometry from int8 complex baseband -> Stokes I x64 time sum"),
+    "cfg2_u4": dict(N=2 ** 22, C=64, P=2, dm=100.0, sr=6.25e6, fcen=600e6, stokes=True, ds=64,
+                    int8=True, raw="u4",
+                    text="cfg2 geometry from packed 4-bit complex baseband -> Stokes I x64 time sum"),
+    "cfg2_u2": dict(N=2 ** 22, C=64, P=2, dm=100.0, sr=6.25e6, fcen=600e6, stokes=True, ds=64,
+                    int8=True, raw="u2",
+                    text="cfg2 geometry from packed 2-bit complex baseband -> Stokes I x64 time sum"),
     "cfg5_shard": dict(N=2 ** 26, C=32, P=2, dm=1000.0, sr=400e6 / 256, fcen=600e6, stokes=False,
                        ds=1, int8=False, Call=256,
                        text="one GPU's shard of cfg5: 2^26 x 32 chan (of 256) x 2 pol c64, DM=1000, "
@@ -250,9 +261,14 @@ def run_b200(args, w):
     freqs = chan_freqs(w)
     out_kind = L.OUT_C64 if w["stokes"] is None else (L.OUT_STOKES_I if w["stokes"] else
                                                       L.OUT_INTENSITY)
+    raw = w.get("raw", "int8" if w["int8"] else None)
+    in_dtype = {None: L.PBK_C64, "int8": L.PBK_I8X2, "u4": L.PBK_U4X2, "u2": L.PBK_U2X2}[raw]
+    # host/device shape of one raw block and the extra arguments the API needs for it
+    raw_block = {"int8": (N, C, P, 2), "u4": (N, C, P), "u2": (N, C * P // 2)}.get(raw)
+    raw_kw = {"raw": raw, **({"raw_shape": (C, P)} if raw == "u2" else {})} if raw else {}
     plan = L.DedispPlan(nsamp=N, nchan=C, npol=P, dm=w["dm"], sample_rate_hz=w["sr"],
                         ref_freq_hz=w["fcen"], chan_freq_hz=freqs, crop=(0, N),
-                        in_dtype=L.PBK_I8X2 if w["int8"] else L.PBK_C64, out_kind=out_kind,
+                        in_dtype=in_dtype, out_kind=out_kind,
                         downsample=w["ds"], device=local)
     info = plan.info()
     # the time sum is a separate launch unless the plan fused it into the last pass (":timesum")
@@ -264,8 +280,10 @@ def run_b200(args, w):
     # ---- device-resident run -----------------------------------------------------------
     g = torch.Generator(device=dev)
     g.manual_seed(8 + rank)          # rank r holds time block r of the stream
-    if w["int8"]:
-        x = torch.randint(-127, 128, (N, C, P, 2), device=dev, dtype=torch.int8, generator=g)
+    if raw == "int8":
+        x = torch.randint(-127, 128, raw_block, device=dev, dtype=torch.int8, generator=g)
+    elif raw:
+        x = torch.randint(0, 256, raw_block, device=dev, dtype=torch.uint8, generator=g)
     else:
         x = torch.empty((N, C, P, 2), device=dev, dtype=torch.float32)
         for i in range(0, N, 2 ** 22):
@@ -347,15 +365,17 @@ def run_b200(args, w):
     del x
     torch.cuda.empty_cache()
     e2e = None
-    if not args.no_e2e and w["int8"]:
-        hx = torch.empty((N, C, P, 2), dtype=torch.int8, pin_memory=True)
-        hx.random_(-127, 128, generator=torch.Generator().manual_seed(8 + rank))
+    if not args.no_e2e and raw:
+        hx = torch.empty(raw_block, dtype=torch.int8 if raw == "int8" else torch.uint8,
+                         pin_memory=True)
+        hx.random_(*((-127, 128) if raw == "int8" else (0, 256)),
+                   generator=torch.Generator().manual_seed(8 + rank))
         hraw = hx.numpy()
 
         def call8():
             return pb.kernels.dedisperse(hraw, dm=w["dm"], sample_rate_hz=w["sr"],
                                          chan_freq_hz=freqs, ref_freq_hz=w["fcen"], crop=None,
-                                         int8=True)
+                                         out_kind=out_kind, downsample=w["ds"], **raw_kw)
         ke = max(1, min(K, args.e2e_steps))
         r = call8()
         barrier()
@@ -365,7 +385,7 @@ def run_b200(args, w):
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - t0)
         single = {"value": world * nsamp * ke / dt / 1e9, "ms_per_step": dt / ke * 1e3,
-                  "api": "pulsarbat_b200.kernels.dedisperse(int8 numpy, pinned) -- one synchronous "
+                  "api": f"pulsarbat_b200.kernels.dedisperse({raw} numpy, pinned) -- one synchronous "
                          "call per block, result in fresh pageable memory"}
         single["pinned_results"] = time_pinned_results(call8, ke, world, nsamp, max_over_ranks)
 
@@ -373,8 +393,8 @@ def run_b200(args, w):
             tot = 0.0
             for y in pb.streaming.dedisperse_blocks(
                     (hraw for _ in range(nblk)), dm=w["dm"], sample_rate_hz=w["sr"],
-                    chan_freq_hz=freqs, ref_freq_hz=w["fcen"], crop=None, int8=True,
-                    device=local, pinned_out=True):
+                    chan_freq_hz=freqs, ref_freq_hz=w["fcen"], crop=None, out_kind=out_kind,
+                    downsample=w["ds"], device=local, pinned_out=True, **raw_kw):
                 tot += float(y.ravel()[0].real)
             return tot
         stream8(2)
@@ -386,7 +406,7 @@ def run_b200(args, w):
         e2e = {"value": world * nsamp * ke / dts / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": int(hraw.nbytes), "d2h_bytes_per_step": int(r.nbytes),
                "steps": ke, "ms_per_step": dts / ke * 1e3,
-               "api": "pulsarbat_b200.streaming.dedisperse_blocks(pinned int8 blocks): upload of "
+               "api": f"pulsarbat_b200.streaming.dedisperse_blocks(pinned {raw} blocks): upload of "
                       "block i+1, kernels of block i and download of block i-1 overlap",
                "single_call": single}
         del hx, hraw, r
