@@ -209,14 +209,19 @@ def overlap_save_dedispersion(z, DM, block_len, /, *, ref_freq=None):
     valid = stop - start
     if valid <= 0:
         raise ValueError("block length does not exceed the dispersion sweep")
-    pieces = []
-    b = 0
-    while b + block_len <= len(z):
-        blk = z[b:b + block_len]
-        y = kernels.dedisperse(blk.data, dm=DM.dm, sample_rate_hz=z.sample_rate_hz,
-                               chan_freq_hz=z.channel_freqs_hz, ref_freq_hz=_hz(ref_freq),
-                               crop=(start, stop))
-        pieces.append(np.asarray(y))
-        b += valid
-    data = np.concatenate(pieces, axis=0)
+    starts = list(range(0, len(z) - block_len + 1, valid))
+    kw = dict(dm=DM.dm, sample_rate_hz=z.sample_rate_hz, chan_freq_hz=z.channel_freqs_hz,
+              ref_freq_hz=_hz(ref_freq), crop=(start, stop))
+    if isinstance(z.data, kernels.DeviceArray) or np.asarray(z.data).dtype != np.complex64:
+        pieces = [np.asarray(kernels.dedisperse(z[b:b + block_len].data, **kw)) for b in starts]
+        data = np.concatenate(pieces, axis=0)
+    else:
+        # host complex64 stream: the blocks go through the three-stream pipeline (upload of block
+        # i+1, kernels of block i and download of block i-1 overlap) straight into the result
+        from .. import streaming
+        src = np.asarray(z.data)
+        data = np.empty((len(starts) * valid,) + src.shape[1:], np.complex64)
+        blocks = (src[b:b + block_len] for b in starts)
+        for i, y in enumerate(streaming.dedisperse_blocks(blocks, pinned_out=True, **kw)):
+            data[i * valid:(i + 1) * valid] = y
     return _cropped_like(type(z), z, data, start)
