@@ -745,14 +745,14 @@ static int dedisp_plan_create_impl(const pbk_dedisp_desc* d, const RampSpec* ram
                           cudaGetErrorString(e)));
   }
   // Time sum fused into the last inverse pass (fast_pass_kernel TSUM): power-of-two factor that
-  // divides the inner extent of the outermost level, groups aligned with the inner time offset
-  // (crop_start a multiple of the factor), wide tiles on the compile-time-shaped kernels.
+  // divides half the inner extent of the outermost level, wide tiles on the compile-time-shaped
+  // kernels.
   if (d->downsample > 1 && pl->out_rows > 0 && m > 1 && !getenv("PBK_NO_FUSED_SUM")) {
     Pass& last = pl->passes.back();
     const int lm = ilog2_exact(d->downsample);
     const long long W = 2ll << last.finfo.log2pw;
-    if (last.family >= 0 && last.mode == MODE_INV && lm > 0 && lm <= last.a.log2nmul &&
-        d->crop_start % d->downsample == 0 && I % W == 0 && W % P == 0 &&
+    if (last.family >= 0 && last.mode == MODE_INV && lm > 0 && lm < last.a.log2nmul &&
+        I % W == 0 && W % P == 0 &&
         last.finfo.tsum_ok) {
       last.a.tsum_log2 = lm;
       const long long ncg = I / W;   // column groups per row; q of them are read side by side

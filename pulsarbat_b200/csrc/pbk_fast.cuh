@@ -551,8 +551,9 @@ __device__ __forceinline__ void inv_last_sum(const FastTile& T, float4* tile, co
 // adds the running sums of a finished (or interrupted) group of 2^tsum_log2 time rows to the output.
 // `colbase` points at this thread's column(s) in output row 0; tile row r at inner offset nrest is
 // time n = (r << log2nmul) + nrest and lands in output row (n - crop_start) >> tsum_log2.  A group
-// receives at most two contributions (a CTA's run of tiles is at least one group long), so the
-// float atomics give the same result in either order.
+// receives at most two contributions (a CTA's run of tiles is at least two groups long and run
+// boundaries avoid the groups that straddle the wrap of the inner offset), so the float atomics
+// give the same result in either order.
 template <class C, int EPI>
 __device__ __forceinline__ void tsum_flush(const PassArgs& p, TsumAcc<C, EPI>& acc, char* colbase,
                                            unsigned nrest, int tid, long long out_row_bytes) {
@@ -616,8 +617,21 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
   };
   const long long ts_total = TSUM ? ntiles / tq : 0;              // runs are split over grid / q
   const long long ts_r = TSUM ? blockIdx.x / tq : 0, ts_nr = TSUM ? gridDim.x / tq : 1;
-  long long t = TSUM ? ts_total * ts_r / ts_nr : p.tile0 + blockIdx.x;
-  const long long t_end = TSUM ? ts_total * (ts_r + 1) / ts_nr : ntiles;
+  // Groups of summed rows start where (inner offset - crop_start) is a multiple of M.  When
+  // crop_start is not, the first and last group of a walk over the inner offsets are the two
+  // halves of groups that straddle the wrap; a run boundary inside them would give such a group
+  // a third contribution, so it is moved to the edge of the partial group.
+  const unsigned ts_off = TSUM ? (unsigned)(p.crop_start & ((1ll << p.tsum_log2) - 1)) : 0u;
+  auto ts_snap = [&](long long u) -> long long {
+    if (!TSUM || ts_off == 0) return u;
+    const long long nr = u & ((1ll << p.log2nmul) - 1);
+    const long long tail = (1ll << p.log2nmul) - ((1ll << p.tsum_log2) - ts_off);
+    if (nr > 0 && nr < ts_off) return u - nr + ts_off;
+    if (nr > tail) return u - nr + tail;
+    return u;
+  };
+  long long t = TSUM ? ts_snap(ts_total * ts_r / ts_nr) : p.tile0 + blockIdx.x;
+  const long long t_end = TSUM ? ts_snap(ts_total * (ts_r + 1) / ts_nr) : ntiles;
   const long long t_step = TSUM ? 1 : gridDim.x;
   for (int i = tid; i < C::TW_TOTAL; i += C::NT) tws[i] = tables[i];
   if (tid == 0 && t < t_end) fast_tile_info<C, EPI>(p, tile_at(t), *sinfo, in_bits, out_eb);
@@ -665,7 +679,7 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
         // ti.bo = (nrest - crop_start) rows + the column offset; keep the column part only
         char* colbase = T.gout - ((long long)ti.nrest - p.crop_start) * ts_rowbytes;
         if (ts_colbase != nullptr &&
-            (colbase != ts_colbase || (ti.nrest & ((1u << p.tsum_log2) - 1)) == 0))
+            (colbase != ts_colbase || ((ti.nrest - ts_off) & ((1u << p.tsum_log2) - 1)) == 0))
           tsum_flush<C, EPI>(p, tacc, ts_colbase, ts_nrest, tid, ts_rowbytes);
         ts_colbase = colbase;
         ts_nrest = ti.nrest;

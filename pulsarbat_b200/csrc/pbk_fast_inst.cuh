@@ -34,11 +34,11 @@ static cudaError_t cfg_launch_variant(const PassArgs& a, const float2* d_tables,
   }
   const long long resident = (long long)num_sms * C::MINB;
   unsigned grid = (unsigned)std::min<long long>(ntiles - a.tile0, resident);
-  // a TSUM CTA's contiguous run of tiles must span at least one whole group of summed rows
+  // a TSUM CTA's contiguous run of tiles must span at least two whole groups of summed rows
   if (TSUM) {
     const long long q = a.tsum_q;
     grid = (unsigned)(q * std::max<long long>(1, std::min<long long>(resident / q,
-                                                                      (ntiles / q) >> a.tsum_log2)));
+                                                                      (ntiles / q) >> (a.tsum_log2 + 1))));
   }
   kern<<<grid, C::NT, smem, st>>>(a, d_tables, ntiles);
   return cudaGetLastError();

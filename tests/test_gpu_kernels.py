@@ -732,9 +732,11 @@ def test_dedisp_fast_kernels_single_pol(N, C):
 @pytest.mark.parametrize("N, C, M, crop", [
     (2 ** 16, 16, 64, (0, 2 ** 16)),                 # whole block, groups aligned: fused
     (2 ** 16, 16, 64, (4096, 2 ** 16 - 1000)),       # aligned start, ragged stop: fused, tail dropped
-    (2 ** 16, 16, 64, (4100, 2 ** 16 - 1000)),       # start not a multiple of M: two-kernel path
+    (2 ** 16, 16, 64, (4100, 2 ** 16 - 1000)),       # start not a multiple of M: groups straddle the wrap
+    (2 ** 16, 64, 128, (4100 + 63, 2 ** 16 - 3)),
+    (2 ** 20, 64, 32, (77777, 2 ** 20 - 11)),
     (2 ** 18, 32, 16, (1024, 2 ** 18 - 7)),
-    (2 ** 18, 64, 256, (256 * 11, 2 ** 18)),
+    (2 ** 18, 64, 128, (128 * 11, 2 ** 18)),
     (2 ** 20, 64, 4, (0, 2 ** 20)),
     (2 ** 16, 64, 1024, (0, 2 ** 16)),               # factor larger than the inner extent: not fused
 ])
@@ -764,7 +766,7 @@ def test_dedisp_fused_time_sum(N, C, M, crop, out_kind):
     assert got.shape == ref.shape
     assert relerr(got, ref) < 1e-5, desc
     fused = "timesum" in desc
-    assert fused == (crop[0] % M == 0 and M <= 2 ** 8), desc   # N = L1 * inner: inner >= 2^8 here
+    assert fused == (M < 2 ** 8), desc   # N = L1 * inner with inner >= 2^8 here; M must divide inner / 2
     if fused:
         again, _ = run()
         assert np.array_equal(got, again)
