@@ -837,3 +837,84 @@ def test_packed_input_needs_even_row():
         L.DedispPlan(nsamp=1024, nchan=3, npol=1, dm=1.0, sample_rate_hz=1e6, ref_freq_hz=8e8,
                      chan_freq_hz=orc.channel_freqs(8e8, 1e6, 3, "center"), crop=(0, 1024),
                      in_dtype=L.PBK_U2X2)
+
+
+def test_cfg3_shard_full_size_int8_device_resident():
+    """One GPU's shard of BASELINE configs[2] at full size: int8 complex 2^22 x 128 chan (of 1024)
+    x 2 pol, DM=100, 400-800 MHz band, GLOBAL reference frequency and crop (shards must
+    crop identically).  Data generated on the device; checks: crop integers against the oracle,
+    sampled channels against the float64 oracle on the cropped rows, and linearity (the transform
+    of 2x the input is exactly 2x the output: the int8 decode has no offset or scale)."""
+    import torch
+    L = _lib()
+    N, Call, C, P = 2 ** 22, 1024, 128, 2
+    sr, fcen, dm = 400e6 / Call, 600e6, 100.0
+    start, stop = orc.crop_range(dm, N, fcen, sr, Call, fcen)
+    assert (start, stop) == (196979, 3631508)            # SURVEY 8d, cfg 3
+    shard = 5                                            # channels 640..767 of the band
+    freqs = orc.channel_freqs(fcen, sr, Call)[shard * C:(shard + 1) * C]
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev)
+    g.manual_seed(15)
+    x = torch.randint(-60, 61, (N, C, P, 2), device=dev, dtype=torch.int8, generator=g)
+    rows = stop - start
+    y = torch.empty((rows, C, P, 2), device=dev, dtype=torch.float32)
+    st = torch.cuda.current_stream().cuda_stream
+    plan = L.DedispPlan(nsamp=N, nchan=C, npol=P, dm=dm, sample_rate_hz=sr, ref_freq_hz=fcen,
+                        chan_freq_hz=freqs, crop=(start, stop), in_dtype=L.PBK_I8X2)
+    assert plan.out_rows == rows
+    plan.exec_device(x.data_ptr(), y.data_ptr(), None, st)
+    torch.cuda.synchronize()
+    for c in (0, 77, 127):
+        xc = orc.unpack_int8(x[:, c].cpu().numpy()).reshape(N, 1, P)
+        yc = y[:, c].cpu().numpy().view(np.complex64).reshape(rows, P)
+        chirp = orc.transfer_function(dm, N, sr, freqs[c], fcen)[:, None]
+        want, _, _ = orc.coherent_dedispersion(xc, dm, sample_rate=sr, center_freq=freqs[c],
+                                               ref_freq=fcen, chirp=chirp, crop=False)
+        assert relerr(yc, want[start:stop, 0]) < 1e-5, c
+    y2 = torch.empty_like(y)
+    x2 = x * 2
+    plan.exec_device(x2.data_ptr(), y2.data_ptr(), None, st)
+    torch.cuda.synchronize()
+    plan.destroy()
+    assert torch.equal(y2, 2 * y)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_fused_time_sum_random_shapes(seed):
+    """Fused time sum against the two-kernel path (itself checked against the oracle above) on
+    random lengths, channel counts (1-6 column groups per row), factors and crops -- exercises
+    the run boundaries, the groups that straddle the inner-offset wrap and ragged tails."""
+    L = _lib()
+    rng = np.random.default_rng(1000 + seed)
+    N = 2 ** int(rng.integers(14, 19))
+    C = int(rng.choice([16, 32, 48, 64, 96]))
+    M = 2 ** int(rng.integers(1, 8))
+    out_kind = int(rng.integers(1, 3))
+    start = int(rng.integers(0, N // 4))
+    stop = int(rng.integers(N - N // 4, N + 1))
+    sr, fcen, dm = 6.25e6, 625e6, 0.5
+    x = crandn(rng, (N, C, 2))
+    freqs = orc.channel_freqs(fcen, sr, C, "center")
+
+    def run():
+        plan = L.DedispPlan(nsamp=N, nchan=C, npol=2, dm=dm, sample_rate_hz=sr, ref_freq_hz=fcen,
+                            chan_freq_hz=freqs, crop=(start, stop), out_kind=out_kind,
+                            downsample=M)
+        out = plan.exec_host(x, plan.out_array())
+        desc = plan.describe()
+        plan.destroy()
+        return out, desc
+
+    got, desc = run()
+    os.environ["PBK_NO_FUSED_SUM"] = "1"
+    try:
+        plain, desc2 = run()
+    finally:
+        del os.environ["PBK_NO_FUSED_SUM"]
+    assert "timesum" not in desc2
+    assert got.shape == plain.shape == ((stop - start) // M, C) + ((2,) if out_kind == 1 else ())
+    assert relerr(got, plain) < 2e-6, (desc, N, C, M, start, stop)
+    if "timesum" in desc:
+        again, _ = run()
+        assert np.array_equal(got, again)
