@@ -149,6 +149,11 @@ int pbk_fft_plan_create(int64_t outer, int64_t n, int64_t inner, int32_t inverse
  */
 int pbk_stft_plan_create(int64_t nseg, int64_t nperseg, int64_t nchan, int64_t npol,
                          int32_t inverse, int32_t device, pbk_plan** plan);
+/* the channelizer fed with raw baseband (PBK_I8X2 / PBK_U4X2 / PBK_U2X2, decoded in the load of the
+ * first pass; forward transform only): what readers/_baseband_readers.py:139-153 + misc.py:17-55
+ * do in two steps on the host */
+int pbk_stft_plan_create_raw(int64_t nseg, int64_t nperseg, int64_t nchan, int64_t npol,
+                             int32_t in_dtype, int32_t device, pbk_plan** plan);
 
 /* execution for FFT and STFT plans */
 int pbk_fft_exec_host(pbk_plan* plan, const void* in, void* out);

@@ -17,7 +17,7 @@ EXPORTS = [
     "pbk_version", "pbk_last_error", "pbk_status_string", "pbk_device_count",
     "pbk_device_pci_bus_id", "pbk_phase_predict",
     "pbk_dedisp_plan_create", "pbk_dedisp_out_shape", "pbk_dedisp_exec_host",
-    "pbk_dedisp_exec_device", "pbk_fft_plan_create", "pbk_stft_plan_create",
+    "pbk_dedisp_exec_device", "pbk_fft_plan_create", "pbk_stft_plan_create", "pbk_stft_plan_create_raw",
     "pbk_fft_exec_host", "pbk_fft_exec_device", "pbk_detect", "pbk_detect_scrunch", "pbk_shift_channels", "pbk_downsample", "pbk_fold",
     "pbk_stokes", "pbk_pol_basis", "pbk_chirp", "pbk_ramp_plan_create", "pbk_mix", "pbk_decimate2",
     "pbk_plan_destroy", "pbk_plan_info", "pbk_plan_describe", "pbk_plan_profile",
@@ -82,6 +82,7 @@ def lib():
         L.pbk_dedisp_exec_device.argtypes = [vp, vp, vp, vp, vp]
         L.pbk_fft_plan_create.argtypes = [i64, i64, i64, i32, i32, ctypes.POINTER(vp)]
         L.pbk_stft_plan_create.argtypes = [i64, i64, i64, i64, i32, i32, ctypes.POINTER(vp)]
+        L.pbk_stft_plan_create_raw.argtypes = [i64, i64, i64, i64, i32, i32, ctypes.POINTER(vp)]
         L.pbk_fft_exec_host.argtypes = [vp, vp, vp]
         L.pbk_fft_exec_device.argtypes = [vp, vp, vp, vp]
         L.pbk_detect.argtypes = [vp, vp, i64, i64, i64, i32, i64, i32, i32, vp]
@@ -285,8 +286,12 @@ class FFTPlan(Plan):
 
 
 class STFTPlan(FFTPlan):
-    def __init__(self, nseg, nperseg, nchan, npol, inverse=False, device=0):
+    def __init__(self, nseg, nperseg, nchan, npol, inverse=False, device=0, in_dtype=PBK_C64):
         h = ctypes.c_void_p(0)
-        check(lib().pbk_stft_plan_create(nseg, nperseg, nchan, npol, int(bool(inverse)), device,
-                                         ctypes.byref(h)))
+        if in_dtype != PBK_C64:
+            check(lib().pbk_stft_plan_create_raw(nseg, nperseg, nchan, npol, int(in_dtype),
+                                                 device, ctypes.byref(h)))
+        else:
+            check(lib().pbk_stft_plan_create(nseg, nperseg, nchan, npol, int(bool(inverse)),
+                                             device, ctypes.byref(h)))
         Plan.__init__(self, h)

@@ -401,6 +401,7 @@ static int setup_fast(pbk_plan* pl) {
     ps.family = -1;
     if (fam < 0 || !ps.pair_ok) continue;
     if (ps.signinv && (ps.mode != MODE_FWD || pl->kind != PLAN_FFT)) continue;
+    if (ps.signinv && load_is_raw(ps.a.load_kind)) continue;
     // the fast kernels are specialised to the dedispersion passes (see pbk_fast.cuh) plus the
     // last pass of a forward FFT / STFT plan (FWD-last: no level twiddle, scale, fftshift)
     const bool fwd_last = ps.mode == MODE_FWD && ps.a.log2M == 0 && ps.out_role == ROLE_USER_OUT &&
@@ -968,18 +969,19 @@ struct ExtMap {  // external array addressing: o*eo + idx*ei + c*ec + p*ep
 };
 static int blue_fft_plan_create(long long O, long long n, long long C, long long P, bool inverse,
                                 ExtMap in, ExtMap outm, float scale, bool shift_out, bool shift_in,
-                                int device, pbk_plan** out);
+                                int device, pbk_plan** out, int in_kind);
 
+// in_kind: load kind of the user's input (LOAD_C64, or raw baseband decoded in the first pass)
 static int build_fft_plan(long long O, long long n, long long C, long long P, bool inverse,
                           ExtMap in, ExtMap outm, float scale, bool shift_out, bool shift_in,
-                          int device, pbk_plan** out) {
+                          int device, pbk_plan** out, int in_kind = LOAD_C64) {
   *out = nullptr;
   const int ln = ilog2_exact(n);
   if (ln < 1) {
     if (n < 2) return fail(PBK_ERR_UNSUPPORTED, "transform length %lld is too short", (long long)n);
     // not a power of two: Bluestein on top of the power-of-two passes (pbk_blue.cuh)
     return blue_fft_plan_create(O, n, C, P, inverse, in, outm, scale, shift_out, shift_in, device,
-                                out);
+                                out, in_kind);
   }
   int l[3] = {0, 0, 0};
   const int m = choose_levels(ln, C * P, l, false);
@@ -997,8 +999,8 @@ static int build_fft_plan(long long O, long long n, long long C, long long P, bo
   pl->device = device;
   pl->nlevels = m;
   for (int i = 0; i < m; ++i) pl->level_log2[i] = l[i];
-  pl->in_bytes = (size_t)O * n * I * 8;
-  pl->out_bytes = pl->in_bytes;
+  pl->in_bytes = ((size_t)O * n * I * load_bits(in_kind)) >> 3;
+  pl->out_bytes = (size_t)O * n * I * 8;
   TableSet ts;
   long long Kprev[3], R[3];
   {
@@ -1023,6 +1025,7 @@ static int build_fft_plan(long long O, long long n, long long C, long long P, bo
       AddrMap& a = ps.a.min;
       a.a_o = in.eo; a.a_kp = 0; a.a_kl = 0; a.a_n = in.ei; a.a_c = in.ec; a.a_p = in.ep;
       a.a_row = R[0] * in.ei;
+      ps.a.load_kind = in_kind;
       if (shift_in) ps.a.fxor = 1 << (l[0] - 1);
     }
     if (i == m - 1) {
@@ -1249,7 +1252,7 @@ static int blue_dedisp_plan_create(const pbk_dedisp_desc* d, const RampSpec* ram
 // plain / STFT transform of a length that is not a power of two
 static int blue_fft_plan_create(long long O, long long n, long long C, long long P, bool inverse,
                                 ExtMap in, ExtMap outm, float scale, bool shift_out, bool shift_in,
-                                int device, pbk_plan** out) {
+                                int device, pbk_plan** out, int in_kind) {
   int ndev = 0;
   CUDA_TRY(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev)
@@ -1262,11 +1265,11 @@ static int blue_fft_plan_create(long long O, long long n, long long C, long long
   pl->device = device;
   b->O = O; b->n = n; b->I = C * P; b->P = (int)P;
   b->inverse = inverse;
-  pl->in_bytes = (size_t)O * n * C * P * 8;
-  pl->out_bytes = pl->in_bytes;
+  pl->in_bytes = ((size_t)O * n * C * P * load_bits(in_kind)) >> 3;
+  pl->out_bytes = (size_t)O * n * C * P * 8;
   int rc = blue_setup(b, device);
   if (rc != PBK_OK) { pbk_plan_destroy(pl); return rc; }
-  b->in = BlueIO{BlueMap{in.eo, in.ei, in.ec, in.ep}, O, n, b->M, C * P, (int)P, LOAD_C64,
+  b->in = BlueIO{BlueMap{in.eo, in.ei, in.ec, in.ep}, O, n, b->M, C * P, (int)P, in_kind,
                  inverse ? 1 : 0, shift_in ? n / 2 : 0, 1.0f, 0, n};
   b->out = BlueIO{BlueMap{outm.eo, outm.ei, outm.ec, outm.ep}, O, n, b->M, C * P, (int)P, EPI_C64,
                   inverse ? 1 : 0, shift_out ? n / 2 : 0, scale, 0, n};
@@ -1287,23 +1290,41 @@ extern "C" int pbk_fft_plan_create(int64_t outer, int64_t n, int64_t inner, int3
                         plan);
 }
 
-extern "C" int pbk_stft_plan_create(int64_t nseg, int64_t nperseg, int64_t nchan, int64_t npol,
-                                    int32_t inverse, int32_t device, pbk_plan** plan) {
+static int stft_plan_create(int64_t nseg, int64_t nperseg, int64_t nchan, int64_t npol,
+                            int32_t inverse, int32_t in_dtype, int32_t device, pbk_plan** plan) {
   if (!plan) return fail(PBK_ERR_INVALID, "plan is NULL");
   if (nseg <= 0 || nperseg <= 0 || nchan <= 0 || npol <= 0)
     return fail(PBK_ERR_INVALID, "shape must be positive");
+  if (in_dtype != PBK_C64 && in_dtype != PBK_I8X2 && in_dtype != PBK_U4X2 && in_dtype != PBK_U2X2)
+    return fail(PBK_ERR_INVALID, "unknown in_dtype %d", in_dtype);
+  if (in_dtype != PBK_C64 && inverse)
+    return fail(PBK_ERR_INVALID, "raw input applies to the forward transform only");
+  if ((in_dtype == PBK_U4X2 || in_dtype == PBK_U2X2) && (nchan * npol) % 2)
+    return fail(PBK_ERR_INVALID, "packed input needs an even nchan * npol, got %lld",
+                (long long)(nchan * npol));
   const long long n = nperseg, C = nchan, P = npol;
   if (!inverse) {
     // in[(s*n + t), c, p] ; out[s, c*n + shift(k), p] ; scale 1/n   (misc.py:41-52)
     ExtMap in{n * C * P, C * P, P, 1};
     ExtMap om{C * n * P, P, n * P, 1};
     return build_fft_plan(nseg, n, C, P, false, in, om, (float)(1.0 / (double)n), true, false,
-                          device, plan);
+                          device, plan, load_kind_of(in_dtype));
   }
   // in[s, c*n + k', p] with ifftshift ; out[(s*n + t), c, p] ; (x*n) then ifft => unit scale
   ExtMap in{C * n * P, P, n * P, 1};
   ExtMap om{n * C * P, C * P, P, 1};
   return build_fft_plan(nseg, n, C, P, true, in, om, 1.0f, false, true, device, plan);
+}
+
+extern "C" int pbk_stft_plan_create(int64_t nseg, int64_t nperseg, int64_t nchan, int64_t npol,
+                                    int32_t inverse, int32_t device, pbk_plan** plan) {
+  return stft_plan_create(nseg, nperseg, nchan, npol, inverse, PBK_C64, device, plan);
+}
+
+extern "C" int pbk_stft_plan_create_raw(int64_t nseg, int64_t nperseg, int64_t nchan,
+                                        int64_t npol, int32_t in_dtype, int32_t device,
+                                        pbk_plan** plan) {
+  return stft_plan_create(nseg, nperseg, nchan, npol, 0, in_dtype, device, plan);
 }
 
 extern "C" int pbk_fft_exec_device(pbk_plan* pl, const void* d_in, void* d_out, void* stream) {

@@ -452,17 +452,20 @@ def downsample(data, factor, device=None):
 # --------------------------------------------------------------------------------------------
 # FFT / channelize                 reference: fft.py:30-48, contrib/misc.py:17-93
 # --------------------------------------------------------------------------------------------
-def _run_fft_plan(key, factory, data, out_shape):
+def _run_fft_plan(key, factory, data, out_shape, raw_np=None):
     ent = _get_plan(key, factory)
     if _is_dev(data):
         x = data.contiguous()
-        if x.dtype != np.complex64:
+        if raw_np is None and x.dtype != np.complex64:
             x = x.astype(np.complex64)
         out = DeviceArray.empty(out_shape, np.complex64, x.device)
         with ent.lock:
             ent.plan.exec_device(x.ptr, out.ptr, _stream())
         return out
-    x, odt = _host_c64(data)
+    if raw_np is not None:
+        x, odt = np.ascontiguousarray(data, dtype=raw_np), np.complex64
+    else:
+        x, odt = _host_c64(data)
     out = _result(out_shape, np.complex64)
     with ent.lock:
         ent.plan.exec_host(x, out)
@@ -482,17 +485,32 @@ def fft(data, axis=0, inverse=False, device=None):
                          data, shape)
 
 
-def stft(data, nperseg, device=None):
+def stft(data, nperseg, device=None, raw=None, raw_shape=None):
     """(nseg*n, nchan, ...) -> (nseg, nchan*n, ...), fftshift-ed and scaled by 1/n
-    (misc.py:41-52).  ``data`` must already be trimmed to a multiple of nperseg."""
+    (misc.py:41-52).  ``data`` must already be trimmed to a multiple of nperseg.  ``raw`` /
+    ``raw_shape`` feed the channelizer with raw baseband as in :func:`dedisperse` ("int8": a
+    trailing (re, im) axis; "u4": one byte per sample; "u2": rows of nchan*npol/2 bytes plus
+    ``raw_shape=(nchan, ...)``)."""
+    if raw is not None and raw not in _RAW_KINDS:
+        raise ValueError(f"raw must be one of {sorted(_RAW_KINDS)}, got {raw!r}")
     shape = tuple(data.shape)
+    if raw == "u2":
+        if raw_shape is None:
+            raise ValueError('raw="u2" needs raw_shape=(nchan, ...)')
+        shape = (shape[0],) + tuple(int(v) for v in raw_shape)
+        if int(np.prod(shape[1:])) != 2 * int(np.prod(tuple(data.shape)[1:])):
+            raise ValueError(f"raw_shape {raw_shape} does not match rows of {data.shape[1:]} bytes")
+    elif raw == "int8":
+        shape = shape[:-1]
     n = int(nperseg)
     nseg, nchan = shape[0] // n, shape[1]
     npol = int(np.prod(shape[2:])) if len(shape) > 2 else 1
+    in_dtype, raw_np = _RAW_KINDS[raw] if raw is not None else (L.PBK_C64, None)
     dev = data.device if _is_dev(data) else (default_device() if device is None else device)
-    key = ("stft", nseg, n, nchan, npol, False, dev)
-    return _run_fft_plan(key, lambda: L.STFTPlan(nseg, n, nchan, npol, inverse=False, device=dev),
-                         data, (nseg, nchan * n) + shape[2:])
+    key = ("stft", nseg, n, nchan, npol, False, raw, dev)
+    return _run_fft_plan(key, lambda: L.STFTPlan(nseg, n, nchan, npol, inverse=False, device=dev,
+                                                 in_dtype=in_dtype),
+                         data, (nseg, nchan * n) + shape[2:], raw_np=raw_np)
 
 
 def istft(data, nperseg, device=None):

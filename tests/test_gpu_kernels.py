@@ -918,3 +918,29 @@ def test_fused_time_sum_random_shapes(seed):
     if "timesum" in desc:
         again, _ = run()
         assert np.array_equal(got, again)
+
+
+@pytest.mark.parametrize("shape, nperseg", [((2 ** 18, 1, 2), 2 ** 12), ((2 ** 20, 1, 2), 2 ** 16),
+                                            ((2 ** 16, 16, 2), 64), ((2 ** 16, 4, 1), 2 ** 13),
+                                            ((4224, 3, 2), 33)])
+@pytest.mark.parametrize("kind", ["int8", "u4", "u2"])
+def test_stft_raw_input(shape, nperseg, kind):
+    """The channelizer fed with raw baseband (pbk_stft_plan_create_raw): equal to the complex64
+    channelizer on the decoded samples (reference contrib/misc.py:17-55 after the reader's decode)."""
+    import pulsarbat_b200 as pb
+    rng = np.random.default_rng(shape[0] + nperseg)
+    N, I = shape[0], int(np.prod(shape[1:]))
+    if kind == "int8":
+        raw = rng.integers(-127, 128, size=shape + (2,), dtype=np.int8)
+        x, extra = orc.unpack_int8(raw), {}
+    elif kind == "u4":
+        raw = rng.integers(0, 256, size=shape, dtype=np.uint8)
+        x, extra = orc.unpack_u4(raw), {}
+    else:
+        raw = rng.integers(0, 256, size=(N, I // 2), dtype=np.uint8)
+        x, extra = orc.unpack_u2(raw).reshape(shape), {"raw_shape": shape[1:]}
+    want = orc.stft(x.astype(np.complex128), nperseg)
+    got = pb.kernels.stft(raw, nperseg, raw=kind, **extra)
+    assert got.shape == want.shape and got.dtype == np.complex64
+    assert relerr(got, want) < 1e-5
+    assert relerr(got, pb.kernels.stft(x, nperseg)) < 2e-6
