@@ -446,6 +446,19 @@ def run_b200(args, w):
                          " -- one synchronous call per block"}
         if rbytes > 2 ** 26:
             single["pinned_results"] = time_pinned_results(call, ke, world, nsamp, max_over_ranks)
+        # the same call on an ordinary (pageable) numpy block: the library moves it through its
+        # multi-threaded bounce pipeline (csrc/pbk_hostcopy.h)
+        zp = cls(np.array(z.data, copy=True), **kw)
+        z, z_pinned = zp, z
+        call()
+        t0 = time.perf_counter()
+        for _ in range(max(1, ke // 2)):
+            r = call()
+        torch.cuda.synchronize()
+        dtp = max_over_ranks(time.perf_counter() - t0) / max(1, ke // 2)
+        single["pageable_input"] = {"value": world * nsamp / dtp / 1e9, "ms_per_step": dtp * 1e3}
+        z = z_pinned
+        del zp
         # the same blocks as a stream: H2D of block i+1 overlaps the kernels of block i
         out_kind_s = L.OUT_C64 if w["stokes"] is None else (L.OUT_STOKES_I if w["stokes"] else
                                                             L.OUT_INTENSITY)

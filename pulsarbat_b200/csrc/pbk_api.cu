@@ -24,6 +24,7 @@
 #include "pbk_fast_launch.h"
 #include "pbk_blue.cuh"
 #include "pbk_fft.cuh"
+#include "pbk_hostcopy.h"
 #include "pbk_misc.cuh"
 
 using namespace pbk;
@@ -951,13 +952,12 @@ extern "C" int pbk_dedisp_exec_host(pbk_plan* pl, const void* in, void* out, con
   if ((rc = ensure_buf(&pl->h_dout, pl->out_bytes)) != PBK_OK) return rc;
   if ((rc = ensure_buf(&pl->h_dchirp, pl->chirp_bytes)) != PBK_OK) return rc;
   cudaStream_t st = cudaStreamPerThread;
-  CUDA_TRY(cudaMemcpyAsync(pl->h_din, in, pl->in_bytes, cudaMemcpyHostToDevice, st));
-  if (pl->chirp_bytes)
-    CUDA_TRY(cudaMemcpyAsync(pl->h_dchirp, chirp, pl->chirp_bytes, cudaMemcpyHostToDevice, st));
+  // pageable blocks go through the multi-threaded bounce pipeline (pbk_hostcopy.h)
+  CUDA_TRY(host_to_device(pl->h_din, in, pl->in_bytes, st));
+  if (pl->chirp_bytes) CUDA_TRY(host_to_device(pl->h_dchirp, chirp, pl->chirp_bytes, st));
   rc = pbk_dedisp_exec_device(pl, pl->h_din, pl->h_dout, pl->h_dchirp, st);
   if (rc != PBK_OK) return rc;
-  CUDA_TRY(cudaMemcpyAsync(out, pl->h_dout, pl->out_bytes, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(device_to_host(out, pl->h_dout, pl->out_bytes, st));
   return PBK_OK;
 }
 
@@ -1346,11 +1346,10 @@ extern "C" int pbk_fft_exec_host(pbk_plan* pl, const void* in, void* out) {
   if ((rc = ensure_buf(&pl->h_din, pl->in_bytes)) != PBK_OK) return rc;
   if ((rc = ensure_buf(&pl->h_dout, pl->out_bytes)) != PBK_OK) return rc;
   cudaStream_t st = cudaStreamPerThread;
-  CUDA_TRY(cudaMemcpyAsync(pl->h_din, in, pl->in_bytes, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(host_to_device(pl->h_din, in, pl->in_bytes, st));
   rc = pbk_fft_exec_device(pl, pl->h_din, pl->h_dout, st);
   if (rc != PBK_OK) return rc;
-  CUDA_TRY(cudaMemcpyAsync(out, pl->h_dout, pl->out_bytes, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(device_to_host(out, pl->h_dout, pl->out_bytes, st));
   return PBK_OK;
 }
 
@@ -1721,11 +1720,10 @@ static int run_elementwise(const void* in, void* out, size_t in_bytes, size_t ou
   CUDA_TRY(cudaMalloc(&di.p, in_bytes ? in_bytes : 16));
   CUDA_TRY(cudaMalloc(&dout.p, out_bytes ? out_bytes : 16));
   cudaStream_t st = cudaStreamPerThread;
-  CUDA_TRY(cudaMemcpyAsync(di.p, in, in_bytes, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(host_to_device(di.p, in, in_bytes, st));
   cudaError_t e = launch(di.p, dout.p, st);
   if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
-  CUDA_TRY(cudaMemcpyAsync(out, dout.p, out_bytes, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(device_to_host(out, dout.p, out_bytes, st));
   return PBK_OK;
 }
 
