@@ -1855,8 +1855,11 @@ extern "C" int pbk_memcpy_d2h(void* dst, const void* src, size_t bytes, int32_t 
 extern "C" int pbk_memcpy_async(void* dst, const void* src, size_t bytes, int32_t to_device,
                                 int32_t device, void* stream) {
   CUDA_TRY(cudaSetDevice(device));
-  CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost,
-                           reinterpret_cast<cudaStream_t>(stream)));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (to_device)   // large pageable sources go through the bounce pipeline (returns once src is read)
+    CUDA_TRY(host_to_device(dst, src, bytes, st));
+  else
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
   return PBK_OK;
 }
 extern "C" int pbk_device_sync(int32_t device) {

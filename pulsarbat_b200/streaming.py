@@ -141,9 +141,11 @@ def dedisperse_blocks(blocks, *, dm, sample_rate_hz, chan_freq_hz, ref_freq_hz, 
         nxt = next(it, None)
         while True:
             slot = i & 1
+            # kernels of block i are queued before block i+1 is uploaded: a pageable block is
+            # copied by host threads inside upload() (csrc/pbk_hostcopy.h), which then overlaps them
+            compute(slot, i >= 2)
             if nxt is not None:
                 keep[slot ^ 1] = upload(nxt, slot ^ 1, i >= 1)
-            compute(slot, i >= 2)
             if i >= 1:
                 yield result(slot ^ 1)
             if nxt is None:

@@ -248,6 +248,13 @@ def test_block_stream_matches_single_calls():
             assert np.array_equal(g, np.asarray(pb.kernels.dedisperse(b, **kw)))
     assert list(pb.streaming.dedisperse_blocks(iter([]), dm=dm, sample_rate_hz=sr,
                                                chan_freq_hz=freqs, ref_freq_hz=fcen)) == []
+    # blocks large enough (64 MiB) for the pageable bounce pipeline of the upload
+    big = [crandn(rng, (2 ** 18, C, 2)) for _ in range(3)]
+    kwb = dict(dm=dm, sample_rate_hz=sr, chan_freq_hz=freqs, ref_freq_hz=fcen,
+               crop=(1000, 2 ** 18 - 3000), out_kind=L.OUT_STOKES_I, downsample=8)
+    gotb = list(pb.streaming.dedisperse_blocks(iter(big), **kwb))
+    for g, b in zip(gotb, big):
+        assert np.array_equal(g, pb.kernels.dedisperse(b, **kwb))
     one = list(pb.streaming.dedisperse_blocks([blocks[0]], dm=dm, sample_rate_hz=sr,
                                               chan_freq_hz=freqs, ref_freq_hz=fcen))
     assert len(one) == 1 and one[0].shape == (N, C, 2)
