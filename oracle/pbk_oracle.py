@@ -14,7 +14,16 @@ here 1.18.1) and numpy ufuncs -- which ARE available, so the oracle calls exactl
 the reference's argument order.  astropy's contribution to the numbers on this path reduces
 to the constant 1/2.41e-4, powers of ten between Hz and MHz, and cycle->rad = 2*pi.
 
-Pinning (see tests/test_oracle_*.py): every known-answer test the reference holds for the
+Pinning, part 1 (tests/test_ref_golden.py): OUTPUTS OF THE REFERENCE ITSELF.  The hot-path source
+files of /root/reference are executed here, unmodified and where they lie, by oracle/ref_run.py
+(unit bookkeeping on the stand-ins of oracle/ref_shim, since astropy/dask cannot be installed);
+oracle/make_ref_golden.py froze their outputs for seeded inputs into tests/golden/ref_golden.npz
+(coherent dedispersion in seven geometries, the chirp at BASELINE sizes, the crops of configs
+1/2/3/5, stft/istft, intensity/Stokes/pol basis, time_shift, freq_shift, incoherent
+dedispersion, real_to_complex).  This oracle reproduces all of them, and the live re-run is
+compared with the frozen file bit for bit whenever /root/reference is present.
+
+Pinning, part 2 (tests/test_oracle_*.py): every known-answer test the reference holds for the
 path is reproduced against this oracle --
   tests/test_dedispersion.py:12-32   (delay constants)
   tests/test_dedispersion.py:73-98   (+DM / -DM reversibility, atol 3e-8)
@@ -171,7 +180,8 @@ def incoherent_dedispersion(x, dm, *, sample_rate, center_freq, chan_bw, freq_al
 # ----------------------------------------------------------------------------------------
 def time_shift(x, shift):
     """transforms.py:248-286 for an array x (time axis 0) and per-sample-shape shifts (samples):
-    ifft(fft(x) * exp(-2j pi shift fftfreq(N, 1))) with the wrapped-around samples zeroed.
+    ifft(fft(x) * exp(-2j pi shift fftfreq(N, 1))) with the wrapped-around samples zeroed
+    (where the reference zeroes them, see the note at the loop).
     Returns (shifted, start, stop) where [start : N + stop] is the crop of ``crop=True``."""
     x = np.asarray(x)
     shift = np.array(shift, dtype=np.float64)
@@ -184,8 +194,10 @@ def time_shift(x, shift):
     shifted = scipy.fft.ifft(scipy.fft.fft(x, axis=0) * ph, axis=0)
     shifted = shifted if np.iscomplexobj(x) else shifted.real
     start, stop = 0, 0
-    it = np.nditer(np.broadcast_to(shift, x.shape[1:]) if shift.ndim else shift,
-                   flags=["multi_index"])
+    # transforms.py:274 iterates the UN-broadcast shift (trailing axes of length 1): with one
+    # shift per channel of a (time, chan, pol) signal only pol 0 is zeroed.  Verified by running
+    # the reference (tests/golden/ref_golden.npz, tshift_perchan); reproduced, not corrected.
+    it = np.nditer(shift, flags=["multi_index"])
     for a in it:
         if a < 0:
             a = int(np.floor(a))
@@ -210,7 +222,8 @@ def freq_shift(x, ft):
     nix = tuple(slice(None) if j == 0 else None for j in range(x.ndim))
     ph = np.exp(2j * np.pi * ft * n[nix]).astype(x.dtype)
     X = np.fft.fftshift(scipy.fft.fft(x * ph, axis=0), axes=(0,))
-    it = np.nditer(np.broadcast_to(ft, x.shape[1:]) * x.shape[0], flags=["multi_index"])
+    # same iteration quirk as time_shift (transforms.py:349): un-broadcast ft
+    it = np.nditer(ft * x.shape[0], flags=["multi_index"])
     for a in it:
         if a < 0:
             a = int(np.floor(a))

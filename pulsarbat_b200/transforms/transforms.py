@@ -15,7 +15,13 @@ __all__ = ["time_shift", "freq_shift"]
 
 def _per_column(values, z, what):
     """Broadcast ``values`` (scalar or array matching leading sample axes, transforms.py:255-266)
-    to one value per column of ``z``; returns (flat array, array shaped like z.sample_shape)."""
+    to one value per column of ``z``; returns (flat array, the UN-broadcast array with trailing
+    axes of length 1).  The reference applies the phase to every column by broadcasting but walks
+    the un-broadcast array when it zeroes the shifted-out part (``np.nditer`` at
+    transforms.py:274 and :349), so e.g. one shift per channel of a (time, chan, pol) signal
+    zeroes pol 0 only, and a scalar ``freq_shift`` zeroes column (0, 0) only -- observed by
+    running the reference (tests/golden/ref_golden.npz) and reproduced here, since a drop-in
+    must return what the reference returns."""
     values = np.array(values, dtype=np.float64)
     if values.ndim >= z.ndim:
         raise ValueError(f"{what} has too many dimensions. Expected <= {z.ndim - 1} dimensions, "
@@ -27,7 +33,7 @@ def _per_column(values, z, what):
         full = np.broadcast_to(values, z.sample_shape)
     except ValueError as e:
         raise ValueError(f"{what} shape does not match the signal: {e}") from None
-    return np.ascontiguousarray(full).reshape(-1), full
+    return np.ascontiguousarray(full).reshape(-1), values
 
 
 def _as_2d(z):
@@ -45,7 +51,7 @@ def time_shift(z, /, shift, crop=False):
         raise TypeError("z must be a Signal.")
     if isinstance(shift, u.Quantity):
         shift = np.asarray((shift * z.sample_rate).to_value(u.one))
-    flat, full = _per_column(shift, z, "shift")
+    flat, walked = _per_column(shift, z, "shift")
     if np.allclose(flat, 0):
         return z
     real_in = not np.iscomplexobj(np.empty(0, dtype=z.dtype))
@@ -58,7 +64,7 @@ def time_shift(z, /, shift, crop=False):
         y = y.real.astype(z.dtype)
     y = np.ascontiguousarray(y).reshape(z.shape)
     start, stop = 0, 0
-    it = np.nditer(full, flags=["multi_index"])
+    it = np.nditer(walked, flags=["multi_index"])
     for a in it:
         if a < 0:
             a = int(math.floor(a))
@@ -85,17 +91,20 @@ def freq_shift(z, /, shift):
         raise ValueError("shift must be a Quantity with units of frequency.") from None
     if shift_hz.ndim == 0:
         shift_hz = shift_hz[None]
-    ft_flat, ft_full = _per_column(shift_hz / z.sample_rate_hz, z, "shift")
+    ft_flat, walked = _per_column(shift_hz / z.sample_rate_hz, z, "shift")
     n = len(z)
     x2 = _as_2d(z)
     mixed = kernels.mix(x2, ft_flat)
-    lo = np.zeros(ft_flat.shape, np.int64)
-    hi = np.zeros(ft_flat.shape, np.int64)
-    for i, a in enumerate(ft_flat * n):
+    # band mask [lo, hi) per column; only the columns the reference's nditer visits get one
+    lo = np.zeros(z.sample_shape, np.int64)
+    hi = np.zeros(z.sample_shape, np.int64)
+    it = np.nditer(walked * n, flags=["multi_index"])
+    for a in it:
         if a < 0:                                    # x[floor(a):] = 0   (transforms.py:352-354)
-            lo[i], hi[i] = max(n + int(math.floor(a)), 0), n
+            lo[it.multi_index], hi[it.multi_index] = max(n + int(math.floor(a)), 0), n
         else:                                        # x[:ceil(a)] = 0    (transforms.py:355-357)
-            lo[i], hi[i] = 0, min(int(math.ceil(a)), n)
+            lo[it.multi_index], hi[it.multi_index] = 0, min(int(math.ceil(a)), n)
+    lo, hi = lo.reshape(-1), hi.reshape(-1)
     y = kernels.phase_ramp(mixed, zero_lo=lo, zero_hi=hi)
     y = y.reshape(z.shape) if hasattr(y, "reshape") else y
     return type(z).like(z, y)

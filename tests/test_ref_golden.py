@@ -1,0 +1,254 @@
+"""Parity against OUTPUTS OF THE REFERENCE ITSELF.
+
+tests/golden/ref_golden.npz holds what the reference's own, unmodified hot-path source files
+(/root/reference/pulsarbat/{core,fft,utils}.py, transforms/*.py, contrib/misc.py) return for small
+seeded inputs; oracle/make_ref_golden.py wrote it by executing those files where they lie through
+oracle/ref_run.py (astropy/dask are absent from the image, so unit bookkeeping runs on the
+stand-ins of oracle/ref_shim).  Here
+
+* CPU: the oracle restatement must reproduce the reference's outputs, and -- when /root/reference
+  is present (build container; never on the GPU box) -- re-running the reference live must
+  reproduce the frozen file bit for bit;
+* GPU: the CUDA path, through the public API, must match the reference's outputs: relative RMS
+  error <= 1e-5 for voltages and intensities (the north star's tolerance; the reference's own
+  complex64 arithmetic is ~2e-7 from exact), identical shapes, crops, start times and metadata,
+  bit-exact for the integer gather of incoherent dedispersion.
+"""
+
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pbk_oracle as orc
+from oracle import ref_run
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = np.load(os.path.join(HERE, "golden", "ref_golden.npz"))
+META = json.loads(str(G["meta_json"]))
+DEDISP = sorted(META["dedisp"])
+TOL = 1e-5            # BASELINE.json north_star: relative RMS error, complex64 vs reference
+
+
+def relerr(a, b):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    wide = np.complex128 if np.iscomplexobj(a) or np.iscomplexobj(b) else np.float64
+    a, b = a.astype(wide), b.astype(wide)
+    den = np.linalg.norm(b.ravel())
+    return np.linalg.norm((a - b).ravel()) / (den if den else 1.0)
+
+
+# ------------------------------------------------------------------------------------------
+# CPU: oracle restatement vs the reference's outputs
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", DEDISP)
+def test_oracle_dedispersion_matches_reference(name):
+    m = META["dedisp"][name]
+    x, want = G[name + "_x"], G[name + "_y"]
+    y, s0, s1 = orc.coherent_dedispersion(
+        x.astype(np.complex128), m["dm"], sample_rate=m["sample_rate_hz"],
+        center_freq=m["center_freq_hz"], freq_align=m["freq_align"], ref_freq=m["ref_freq_hz"])
+    assert y.shape == want.shape and s1 - s0 == m["nout"]
+    assert s0 == round(m["start_shift_s"] * m["sample_rate_hz"])
+    # the reference transforms complex64 input in complex64 (scipy keeps the dtype)
+    assert relerr(y, want) < (5e-7 if want.dtype == np.complex64 else 1e-8)
+
+
+def test_oracle_chirp_and_crops_match_reference():
+    freqs = orc.channel_freqs(600e6, 6.25e6, 64)
+    assert np.array_equal(freqs, G["chan_freqs_cfg2_hz"])
+    idx = G["chirp_cfg2_idx"]
+    for j, c in enumerate(G["chirp_cfg2_chan"]):
+        h = orc.transfer_function(100.0, 2 ** 22, 6.25e6, freqs[c], 600e6)[idx]
+        # phases reach 1.15e8 cycles = 7e8 rad, where 1 ulp of float64 is 1.2e-7 rad: two
+        # orderings of the same formula differ by a few ulp (measured 6e-7)
+        assert np.max(np.abs(h - G["chirp_cfg2_val"][:, j])) < 2e-6
+    h1 = orc.transfer_function(71.0, 2 ** 20, 16e6, 400e6, 400e6)[G["chirp_cfg1_idx"]]
+    assert np.max(np.abs(h1 - G["chirp_cfg1_val"])) < 2e-7
+    geom = {"cfg1": (2 ** 20, 1, 16e6, 71.0, 400e6), "cfg2": (2 ** 22, 64, 6.25e6, 100.0, 600e6),
+            "cfg3": (2 ** 22, 1024, 0.390625e6, 100.0, 600e6),
+            "cfg5": (2 ** 26, 256, 1.5625e6, 1000.0, 600e6)}
+    for tag, (n, c, sr, dm, fc) in geom.items():
+        assert orc.crop_range(dm, n, fc, sr, c, fc) == (META["crops"][tag]["start"],
+                                                        META["crops"][tag]["stop"]), tag
+
+
+def test_oracle_stft_istft_match_reference():
+    x = G["stft_x"].astype(np.complex128)
+    for n in (32, 33, 1056):
+        assert relerr(orc.stft(x, n), G[f"stft_y{n}"]) < 5e-7
+        assert relerr(orc.istft(G[f"stft_y{n}"].astype(np.complex128), n), G[f"istft_y{n}"]) < 5e-7
+        assert relerr(G[f"istft_y{n}"], x) < 5e-7          # perfect reconstruction
+
+
+def test_oracle_detection_matches_reference():
+    x = G["pol_x"].astype(np.complex128)
+    for pt in ("linear", "circular"):
+        assert relerr(orc.to_intensity(x), G[f"pol_{pt}_intensity"]) < 2e-7
+        assert relerr(orc.to_stokes(x, pt), G[f"pol_{pt}_stokes"]) < 5e-7
+        assert relerr(orc.stokes_I(x), G[f"pol_{pt}_stokes"][..., 0]) < 5e-7
+        assert relerr(orc.to_linear(x, pt), G[f"pol_{pt}_to_linear"]) < 2e-7
+        assert relerr(orc.to_circular(x, pt), G[f"pol_{pt}_to_circular"]) < 2e-7
+
+
+def test_oracle_shifts_match_reference():
+    x = G["shift_x"].astype(np.complex128)
+    for tag, m in META["time_shift"].items():
+        y, start, stop = orc.time_shift(x, m["shift"])
+        assert relerr(y, G[f"tshift_{tag}"]) < 5e-7
+        assert len(x) + stop - start == m["ncrop"]
+        assert start == round(m["crop_shift_s"] * 1e6)
+    for tag, m in META["freq_shift"].items():
+        ft = np.array(m["shift_hz"]) / 1e6
+        assert relerr(orc.freq_shift(x, ft), G[f"fshift_{tag}"]) < 5e-7
+
+
+def test_oracle_incoherent_and_real_to_complex_match_reference():
+    for tag, m in META["incoh"].items():
+        y, crop_before, _ = orc.incoherent_dedispersion(
+            G["incoh_x"], m["dm"], sample_rate=1e3, center_freq=600e6, chan_bw=10e6,
+            ref_freq=m["ref_freq_hz"])
+        assert np.array_equal(y, G[f"incoh_{tag}"])
+        assert crop_before == round(m["start_shift_s"] * 1e3)
+    assert relerr(orc.real_to_complex(G["r2c_x32"]), G["r2c_y32"]) < 5e-7
+    assert relerr(orc.real_to_complex(G["r2c_x64"]), G["r2c_y64"]) < 1e-14
+
+
+@pytest.mark.skipif(not ref_run.available(), reason="/root/reference is not on this machine")
+def test_live_reference_reproduces_frozen_vectors(tmp_path, monkeypatch):
+    """Re-run the reference's own source now and compare with the committed file, bit for bit."""
+    from oracle import make_ref_golden as mk
+    monkeypatch.setattr(mk, "OUT", str(tmp_path / "live.npz"))
+    mk.main()
+    live = np.load(str(tmp_path / "live.npz"))
+    assert sorted(live.files) == sorted(G.files)
+    for k in G.files:
+        if k == "meta_json":
+            assert json.loads(str(live[k])) == META
+        else:
+            assert live[k].dtype == G[k].dtype and np.array_equal(live[k], G[k]), k
+
+
+# ------------------------------------------------------------------------------------------
+# GPU: the CUDA path (public API over the C ABI) vs the reference's outputs
+# ------------------------------------------------------------------------------------------
+def _signal(pb, kind, x, m):
+    u = pb.units
+    kw = dict(sample_rate=m["sample_rate_hz"] * u.Hz, center_freq=m["center_freq_hz"] * u.Hz,
+              freq_align=m["freq_align"], start_time=pb.Time(*META["T0"]))
+    if kind == "DualPolarizationSignal":
+        kw["pol_type"] = "linear"
+    return getattr(pb, kind)(x, **kw)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", DEDISP)
+def test_cuda_dedispersion_matches_reference(name):
+    import pulsarbat_b200 as pb
+    u = pb.units
+    m = META["dedisp"][name]
+    z = _signal(pb, m["kind"], G[name + "_x"], m)
+    rf = None if m["ref_freq_hz"] is None else m["ref_freq_hz"] * u.Hz
+    y = pb.coherent_dedispersion(z, pb.DM(m["dm"]), ref_freq=rf)
+    want = G[name + "_y"]
+    assert type(y) is type(z) and y.shape == want.shape
+    assert relerr(np.asarray(y.data), want) < TOL
+    shift = float((y.start_time - z.start_time).to_value(u.s))
+    assert abs(shift - m["start_shift_s"]) < 1e-9
+    assert float(y.sample_rate.to_value(u.Hz)) == m["out_sample_rate_hz"]
+    assert float(y.center_freq.to_value(u.Hz)) == m["out_center_freq_hz"]
+    assert y.freq_align == z.freq_align
+
+
+@pytest.mark.gpu
+def test_cuda_explicit_chirp_and_chirp_values_match_reference():
+    import pulsarbat_b200 as pb
+    m = META["dedisp"]["dd_dualpol"]
+    z = _signal(pb, m["kind"], G["dd_dualpol_x"], m)
+    y = pb.coherent_dedispersion(z, pb.DM(m["dm"]), chirp=G["dd_dualpol_chirp"][:, :, 0])
+    assert relerr(np.asarray(y.data), G["dd_dualpol_y"]) < TOL
+    own = np.asarray(pb.DM(m["dm"]).chirp_from_signal(z))
+    assert own.shape == G["dd_dualpol_chirp"].shape
+    assert np.max(np.abs(own - G["dd_dualpol_chirp"])) < 2e-6
+    freqs = G["chan_freqs_cfg2_hz"]
+    assert np.array_equal(pb.BasebandSignal(
+        np.zeros((8, 64), np.complex64), sample_rate=6.25e6 * pb.units.Hz,
+        center_freq=600e6 * pb.units.Hz).channel_freqs_hz, freqs)
+    chans = G["chirp_cfg2_chan"]
+    h = pb.kernels.chirp(2 ** 22, len(chans), dm=100.0, sample_rate_hz=6.25e6, ref_freq_hz=600e6,
+                         chan_freq_hz=freqs[chans])
+    assert np.max(np.abs(np.asarray(h)[G["chirp_cfg2_idx"]] - G["chirp_cfg2_val"])) < 2e-6
+
+
+@pytest.mark.gpu
+def test_cuda_stft_istft_match_reference():
+    import pulsarbat_b200 as pb
+    u = pb.units
+    m = dict(sample_rate_hz=1e6, center_freq_hz=600e6, freq_align="center")
+    for n in (32, 33, 1056):
+        mm = META["stft"][str(n)]
+        z = _signal(pb, "DualPolarizationSignal", G["stft_x"], m)
+        y = pb.contrib.stft(z, nperseg=n)
+        assert relerr(np.asarray(y.data), G[f"stft_y{n}"]) < TOL
+        assert y.nchan == mm["nchan"] and y.freq_align == mm["freq_align"]
+        assert math.isclose(float(y.sample_rate.to_value(u.Hz)), mm["sample_rate_hz"], rel_tol=1e-15)
+        assert float(y.center_freq.to_value(u.Hz)) == mm["center_freq_hz"]
+        yin = type(y).like(y, G[f"stft_y{n}"].copy())
+        zi = pb.contrib.istft(yin, nperseg=n)
+        assert relerr(np.asarray(zi.data), G[f"istft_y{n}"]) < TOL
+        assert zi.nchan == mm["inv_nchan"] and zi.freq_align == mm["inv_freq_align"]
+        assert math.isclose(float(zi.sample_rate.to_value(u.Hz)), mm["inv_sample_rate_hz"],
+                            rel_tol=1e-15)
+
+
+@pytest.mark.gpu
+def test_cuda_detection_matches_reference():
+    import pulsarbat_b200 as pb
+    u = pb.units
+    for pt in ("linear", "circular"):
+        z = pb.DualPolarizationSignal(G["pol_x"], sample_rate=1e6 * u.Hz,
+                                      center_freq=600e6 * u.Hz, pol_type=pt)
+        assert relerr(np.asarray(z.to_intensity().data), G[f"pol_{pt}_intensity"]) < TOL
+        assert relerr(np.asarray(z.to_stokes().data), G[f"pol_{pt}_stokes"]) < TOL
+        assert relerr(np.asarray(z.to_stokes_I().data), G[f"pol_{pt}_stokes"][..., 0]) < TOL
+        assert relerr(np.asarray(z.to_linear().data), G[f"pol_{pt}_to_linear"]) < TOL
+        assert relerr(np.asarray(z.to_circular().data), G[f"pol_{pt}_to_circular"]) < TOL
+
+
+@pytest.mark.gpu
+def test_cuda_shifts_match_reference():
+    import pulsarbat_b200 as pb
+    u = pb.units
+    m = dict(sample_rate_hz=1e6, center_freq_hz=600e6, freq_align="center")
+    z = _signal(pb, "DualPolarizationSignal", G["shift_x"], m)
+    for tag, mm in META["time_shift"].items():
+        y = pb.time_shift(z, mm["shift"])
+        assert relerr(np.asarray(y.data), G[f"tshift_{tag}"]) < TOL
+        yc = pb.time_shift(z, mm["shift"], crop=True)
+        assert len(yc) == mm["ncrop"]
+        assert abs(float((yc.start_time - z.start_time).to_value(u.s)) - mm["crop_shift_s"]) < 1e-9
+    for tag, mm in META["freq_shift"].items():
+        y = pb.freq_shift(z, np.array(mm["shift_hz"]) * u.Hz)
+        assert relerr(np.asarray(y.data), G[f"fshift_{tag}"]) < TOL
+
+
+@pytest.mark.gpu
+def test_cuda_incoherent_and_real_to_complex_match_reference():
+    import pulsarbat_b200 as pb
+    u = pb.units
+    for tag, m in META["incoh"].items():
+        z = pb.IntensitySignal(G["incoh_x"], sample_rate=1e3 * u.Hz, center_freq=600e6 * u.Hz,
+                               chan_bw=10e6 * u.Hz, freq_align="center",
+                               start_time=pb.Time(*META["T0"]))
+        rf = None if m["ref_freq_hz"] is None else m["ref_freq_hz"] * u.Hz
+        y = pb.incoherent_dedispersion(z, pb.DM(m["dm"]), ref_freq=rf)
+        assert np.array_equal(np.asarray(y.data), G[f"incoh_{tag}"])
+        assert abs(float((y.start_time - z.start_time).to_value(u.s)) - m["start_shift_s"]) < 1e-9
+    y32 = pb.utils.real_to_complex(G["r2c_x32"], axis=0)
+    assert y32.dtype == np.complex64 and relerr(y32, G["r2c_y32"]) < TOL
+    y64 = pb.utils.real_to_complex(G["r2c_x64"])
+    assert relerr(y64, G["r2c_y64"]) < TOL
