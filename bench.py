@@ -16,8 +16,11 @@ with CUDA events, max over ranks; `e2e` = the same metric through the public API
 (pinned) numpy input, H2D and D2H inside the timed region; `roofline` = the dominant kernel's
 read+write bytes / its CUDA-event duration against MEASURED_PEAKS.json; `cpu_baseline` = the
 oracle (scipy.fft restatement of the reference) on this box's host cores on a bounded sample.
-`--impl reference` times that CPU restatement alone (the reference is pure Python on scipy and
-cannot be imported in this image: astropy/dask are absent).
+`--impl reference` times the UNMODIFIED reference through its own `pb.coherent_dedispersion`
+(package loaded by oracle/ref_run.py from /root/reference or the pip install under baseline/_ref,
+with the astropy/dask stand-ins of oracle/ref_shim -- those packages are not installable here),
+per channel chunk on a thread pool; if no copy of the reference is present it times the oracle
+port and says so (`cpu_baseline.kind`).
 """
 
 import argparse
@@ -114,6 +117,44 @@ def cpu_step(x, w, freqs, threads):
         return list(ex.map(one, range(c)))
 
 
+def reference_step(x, w, freqs, threads):
+    """The UNMODIFIED reference through its own public API (oracle/ref_run.py loads the package
+    from /root/reference or the pip install under baseline/_ref): one
+    ``pb.coherent_dedispersion(Signal(chunk), DM, ref_freq=band centre)`` per channel chunk,
+    followed by ``to_stokes()`` / ``to_intensity()`` and the time sum, chunks spread over a
+    thread pool the way dask's threaded scheduler applies a chunk function
+    (transforms/transforms.py:49-50).  The reference always crops (dedispersion.py:127-133); at
+    cfg2's DM the crop is empty, so detection and the time sum see an empty signal and the
+    time is that of chirp generation + fft * chirp + ifft -- an under-count in the reference's
+    favour."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import ref_run
+    pb, u, _ = ref_run.load()
+    c = x.shape[1]
+    cls = pb.DualPolarizationSignal if w["P"] == 2 else pb.BasebandSignal
+    kw = {"pol_type": "linear"} if w["P"] == 2 else {}
+    dm, ref = pb.DM(w["dm"]), w["fcen"] * u.Hz
+
+    def one(i):
+        blk = x[:, i:i + 1] if w["P"] == 2 else x[:, i:i + 1].reshape(x.shape[0], 1)
+        z = cls(blk, sample_rate=w["sr"] * u.Hz, center_freq=freqs[i] * u.Hz, **kw)
+        y = pb.coherent_dedispersion(z, dm, ref_freq=ref)
+        if w["stokes"] is True:
+            d = np.asarray(y.to_stokes().data)[:, :, 0]
+        elif w["stokes"] is False:
+            d = np.asarray(y.to_intensity().data)
+        else:
+            d = np.asarray(y.data)
+        if w["ds"] > 1:
+            n = d.shape[0] // w["ds"] * w["ds"]
+            d = d[:n].reshape((n // w["ds"], w["ds"]) + d.shape[1:]).sum(axis=1)
+        return d
+
+    with ThreadPoolExecutor(max_workers=min(threads, c)) as ex:
+        return list(ex.map(one, range(c)))
+
+
 def cpu_block(w, nchan, seed=8):
     rng = np.random.default_rng(seed)
     shape = (w["N"], nchan, w["P"])
@@ -123,7 +164,7 @@ def cpu_block(w, nchan, seed=8):
     return x
 
 
-def cpu_calibrate(w, freqs, threads, target_s):
+def cpu_calibrate(w, freqs, threads, target_s, cpu_step=cpu_step):
     """Pick how many channels one CPU step processes so that it takes about target_s."""
     x1 = cpu_block(w, 1)
     t0 = time.perf_counter()
@@ -143,25 +184,36 @@ def run_reference(args, w):
         return
     threads = os.cpu_count() or 1
     freqs = chan_freqs(w)
-    nch = cpu_calibrate(w, freqs, threads, target_s=4.0)
+    from oracle import ref_run
+    # the reference's own code when its package is on this machine (/root/reference in the
+    # build container, the unmodified pip install under baseline/_ref on the GPU box) and the
+    # workload is one its API expresses (complex input); otherwise the oracle port
+    real = ref_run.available() and not w.get("int8")
+    step, kind = (reference_step, "reference") if real else (cpu_step, "port")
+    nch = cpu_calibrate(w, freqs, threads, target_s=4.0, cpu_step=step)
     x = cpu_block(w, nch)
     for _ in range(args.warmup):
-        cpu_step(x, w, freqs[:nch], threads)
+        step(x, w, freqs[:nch], threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_step(x, w, freqs[:nch], threads)
+        step(x, w, freqs[:nch], threads)
     dt = time.perf_counter() - t0
     nsamp = w["N"] * nch * w["P"]
     val = nsamp * args.steps / dt / 1e9
     sample = (f"{nch} of {w['C']} channels x {w['P']} pol x 2^{int(np.log2(w['N']))} samples per "
-              f"step, chirp generation included, scipy.fft + thread pool")
+              f"step, chirp generation included, ")
+    sample += (f"unmodified pulsarbat from {os.path.relpath(ref_run.REF_ROOT, ROOT)} through "
+               "pb.coherent_dedispersion per channel chunk on a thread pool (astropy/dask "
+               "stand-ins of oracle/ref_shim for unit bookkeeping; the reference's crop is empty "
+               "at this DM, so detection and the time sum are not in its time)"
+               if real else "scipy.fft restatement (oracle port) + thread pool")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c64",
         "data": "synthetic",
         "config": {"workload": w["text"], "name": args.workload, "sample": sample},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind,
                          "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -22,12 +22,25 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("PBK_REFERENCE_ROOT", "/root/reference")
-_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_shim")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SHIM = os.path.join(_HERE, "ref_shim")
+
+
+def _has_ref(root):
+    return bool(root) and os.path.isfile(
+        os.path.join(root, "pulsarbat", "transforms", "dedispersion.py"))
+
+
+# where the reference's package directory lives: the read-only checkout in the build container,
+# else the unmodified pip install under baseline/_ref (git-ignored; it travels to the GPU box,
+# where /root/reference does not exist -- __graft_entry__.build() creates it)
+REF_ROOT = next((r for r in (os.environ.get("PBK_REFERENCE_ROOT"), "/root/reference",
+                             os.path.join(os.path.dirname(_HERE), "baseline", "_ref"))
+                 if _has_ref(r)), "/root/reference")
 
 
 def available():
-    return os.path.isfile(os.path.join(REF_ROOT, "pulsarbat", "transforms", "dedispersion.py"))
+    return _has_ref(REF_ROOT)
 
 
 def load():

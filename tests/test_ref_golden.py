@@ -7,8 +7,8 @@ oracle/ref_run.py (astropy/dask are absent from the image, so unit bookkeeping r
 stand-ins of oracle/ref_shim).  Here
 
 * CPU: the oracle restatement must reproduce the reference's outputs, and -- when /root/reference
-  is present (build container; never on the GPU box) -- re-running the reference live must
-  reproduce the frozen file bit for bit;
+  or the unmodified install under baseline/_ref is present -- re-running the reference live must
+  reproduce the frozen file;
 * GPU: the CUDA path, through the public API, must match the reference's outputs: relative RMS
   error <= 1e-5 for voltages and intensities (the north star's tolerance; the reference's own
   complex64 arithmetic is ~2e-7 from exact), identical shapes, crops, start times and metadata,
@@ -120,7 +120,9 @@ def test_oracle_incoherent_and_real_to_complex_match_reference():
 
 @pytest.mark.skipif(not ref_run.available(), reason="/root/reference is not on this machine")
 def test_live_reference_reproduces_frozen_vectors(tmp_path, monkeypatch):
-    """Re-run the reference's own source now and compare with the committed file, bit for bit."""
+    """Re-run the reference's own source now and compare with the committed file: integers and
+    metadata equal, floating-point arrays equal bit for bit on the authoring machine (checked
+    there) and to 1e-6 relative anywhere else (pocketfft picks its SIMD path per CPU)."""
     from oracle import make_ref_golden as mk
     monkeypatch.setattr(mk, "OUT", str(tmp_path / "live.npz"))
     mk.main()
@@ -130,7 +132,9 @@ def test_live_reference_reproduces_frozen_vectors(tmp_path, monkeypatch):
         if k == "meta_json":
             assert json.loads(str(live[k])) == META
         else:
-            assert live[k].dtype == G[k].dtype and np.array_equal(live[k], G[k]), k
+            assert live[k].dtype == G[k].dtype and live[k].shape == G[k].shape, k
+            if not np.array_equal(live[k], G[k]):
+                assert np.issubdtype(G[k].dtype, np.inexact) and relerr(live[k], G[k]) < 1e-6, k
 
 
 # ------------------------------------------------------------------------------------------
