@@ -944,3 +944,59 @@ def test_stft_raw_input(shape, nperseg, kind):
     assert got.shape == want.shape and got.dtype == np.complex64
     assert relerr(got, want) < 1e-5
     assert relerr(got, pb.kernels.stft(x, nperseg)) < 2e-6
+
+
+# ------------------------------------------------------------------ memory safety (guard bands)
+# compute-sanitizer is closed on the GPU pool, so out-of-bounds stores are looked for directly:
+# the user's input and output live in the middle of device buffers filled with a canary; after
+# the plan has run the canaries on both sides must be intact, the input unchanged, and every
+# output element written (the output starts as NaN).
+@pytest.mark.parametrize("N, C, P, in_kind, out_kind, ds, crop, levels", [
+    (2 ** 18, 32, 2, "c64", 0, 1, (5, 2 ** 18 - 7), "6,6,6"),      # fast kernels, 3 levels
+    (2 ** 18, 32, 2, "c64", 2, 8, (0, 2 ** 18), "6,6,6"),          # fused time sum
+    (2 ** 18, 32, 2, "c64", 2, 8, (37, 2 ** 18 - 11), "6,6,6"),    # ... with a ragged crop
+    (2 ** 16, 64, 2, "c64", 1, 4, (3, 2 ** 16 - 1), None),         # per-pol intensity + sum
+    (2 ** 16, 64, 2, "int8", 0, 1, (0, 2 ** 16), None),            # raw int8 in
+    (2 ** 16, 64, 2, "u4", 2, 1, (1, 2 ** 16 - 2), None),          # packed 4-bit in
+    (2 ** 16, 4, 2, "c64", 0, 1, (9, 2 ** 16 - 9), None),          # narrow tiles
+    (2 ** 16, 16, 1, "c64", 1, 1, (0, 2 ** 16), None),             # single pol (two chans / pair)
+    (2 ** 12, 3, 1, "c64", 0, 1, (2, 2 ** 12 - 3), None),          # generic kernels, odd lanes
+    (4233, 3, 2, "c64", 0, 1, (4, 4200), None),                    # Bluestein length
+])
+def test_guard_bands_intact(N, C, P, in_kind, out_kind, ds, crop, levels, monkeypatch):
+    import torch
+    L = _lib()
+    if levels:
+        monkeypatch.setenv("PBK_LEVELS", levels)
+    else:
+        monkeypatch.delenv("PBK_LEVELS", raising=False)
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev)
+    g.manual_seed(N + C)
+    in_dtype = {"c64": L.PBK_C64, "int8": L.PBK_I8X2, "u4": L.PBK_U4X2}[in_kind]
+    freqs = 600e6 + 1e6 * (np.arange(C) + 0.5 - C / 2)
+    plan = L.DedispPlan(nsamp=N, nchan=C, npol=P, dm=1.0, sample_rate_hz=1e6, ref_freq_hz=600e6,
+                        chan_freq_hz=freqs, crop=crop, in_dtype=in_dtype, out_kind=out_kind,
+                        downsample=ds, device=0)
+    in_bytes = N * C * P * {"c64": 8, "int8": 2, "u4": 1}[in_kind]
+    out_bytes = plan.out_rows * plan.row_elems * plan.elem_bytes
+    G = 1 << 20                                                     # 1 MiB of canary on each side
+    ibuf = torch.full((G + in_bytes + G,), 0x5A, device=dev, dtype=torch.uint8)
+    obuf = torch.full((G + out_bytes + G,), 0xA5, device=dev, dtype=torch.uint8)
+    body = ibuf[G:G + in_bytes]
+    if in_kind == "c64":
+        body.view(torch.float32).normal_(generator=g)
+    else:
+        body.copy_(torch.randint(0, 256, (in_bytes,), device=dev, dtype=torch.uint8, generator=g))
+    before = body.clone()
+    obuf[G:G + out_bytes].view(torch.float32).fill_(float("nan"))
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(2):                                              # plan reuse included
+        plan.exec_device(ibuf.data_ptr() + G, obuf.data_ptr() + G, None, st)
+    torch.cuda.synchronize()
+    assert bool((ibuf[:G] == 0x5A).all()) and bool((ibuf[G + in_bytes:] == 0x5A).all())
+    assert bool((obuf[:G] == 0xA5).all()) and bool((obuf[G + out_bytes:] == 0xA5).all())
+    assert torch.equal(body, before)                                # input is read-only
+    res = obuf[G:G + out_bytes].view(torch.float32)
+    assert bool(torch.isfinite(res).all())                          # every output element written
+    plan.destroy()
