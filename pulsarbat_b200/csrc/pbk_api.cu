@@ -213,6 +213,15 @@ static void set_geometry(Pass& ps, int log2L, long long Q, long long RI, int I, 
   int lpw = std::min(7, std::max(0, 12 - log2L));
   const long long pairs = (Q + 1) / 2;
   while (lpw > 0 && (1ll << (lpw - 1)) >= pairs) --lpw;
+  // small problems: prefer narrower tiles until every SM has a few CTAs to overlap (a 2^20-point
+  // single column gives 128 tiles of 64 KiB otherwise, fewer than the 148 SMs)
+  {
+    static const long long min_grid = [] {
+      const char* e = getenv("PBK_GENERIC_MINGRID");
+      return e ? atoll(e) : 0ll;
+    }();
+    while (lpw > 1 && (Q + (2ll << lpw) - 1) / (2ll << lpw) < min_grid) --lpw;
+  }
   a.log2pw = lpw;
   a.log2Kprev = log2Kprev;
   // tile (multi-stage tiles only) + per-tile level-twiddle table [lanes][16]

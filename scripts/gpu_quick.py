@@ -38,8 +38,12 @@ def time_plan(name, N, C, P, dm, sr, fcen, out_kind=0, downsample=1, in_dtype=0,
     torch.cuda.synchronize()
     plan.profile(iters)
     ts = []
+    flush = (torch.empty(256 << 20, device=dev, dtype=torch.uint8)
+             if os.environ.get("PBK_QUICK_FLUSH") else None)     # cold-L2 timing of small plans
     for _ in range(iters):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if flush is not None:
+            flush.zero_()
         e0.record()
         plan.exec_device(x.data_ptr(), out.data_ptr(), None, st)
         e1.record()
