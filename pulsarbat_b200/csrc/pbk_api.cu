@@ -122,6 +122,9 @@ struct pbk_plan {
   void* d_tmpf = nullptr;       // pre-downsample float buffer
   size_t tmpf_bytes = 0;
   bool fused_tsum = false;      // the time sum runs in the epilogue of the last pass (no d_tmpf)
+  bool split_column = false;    // single column run as its even / odd samples (see plan creation)
+  bool split_ragged = false;    // ... with an odd crop edge: passes write d_tmpf, then a D2D copy
+  size_t split_skip = 0;
   // lazily allocated staging buffers for *_host execution
   void* h_din = nullptr;
   void* h_dout = nullptr;
@@ -597,6 +600,58 @@ static int dedisp_plan_create_impl(const pbk_dedisp_desc* d, const RampSpec* ram
     return fail(PBK_ERR_INVALID, "crop [%lld, %lld) outside [0, %lld]", (long long)d->crop_start,
                 (long long)d->crop_stop, (long long)d->nsamp);
   const int n = ilog2_exact(d->nsamp);
+  // ONE complex64 column (a BasebandSignal with a single channel, BASELINE config 1) has no lane
+  // pairs for the compile-time-shaped kernels.  Its even and odd samples do: the (N/2, 2) view of
+  // the same memory is a two-"channel" single-pol array, transformed at half length by the fast
+  // kernels, with the radix-2 recombination, the chirp at bins k and k - N/2 and the inverse
+  // split done in registers by the middle pass (pbk_fast.cuh: fast_chirp, p.split).
+  if (!ramp && n >= 13 && d->nchan == 1 && d->npol == 1 && d->in_dtype == PBK_C64 &&
+      !d->explicit_chirp && d->downsample == 1 && d->out_kind != PBK_OUT_STOKES_I &&
+      d->crop_stop >= d->crop_start &&
+      std::fabs(d->chan_freq_hz[0]) >= 8.0 * d->sample_rate_hz && !getenv("PBK_NO_SPLIT")) {
+    pbk_dedisp_desc h = *d;
+    const double f2[2] = {d->chan_freq_hz[0], d->chan_freq_hz[0]};
+    h.nsamp = d->nsamp / 2;
+    h.nchan = 2;
+    h.sample_rate_hz = d->sample_rate_hz / 2;   // same bin width: df = (SR/2) / (N/2)
+    h.chan_freq_hz = f2;
+    h.crop_start = d->crop_start / 2;           // whole (even, odd) rows covering the crop
+    h.crop_stop = (d->crop_stop + 1) / 2;
+    pbk_plan* pl = nullptr;
+    const int rc = dedisp_plan_create_impl(&h, nullptr, &pl);
+    if (rc == PBK_OK) {
+      bool all_fast = true;
+      for (auto& ps : pl->passes) all_fast = all_fast && ps.family >= 0;
+      if (all_fast) {
+        for (auto& ps : pl->passes)
+          if (ps.mode == MODE_MID) { ps.a.split = 1; ps.a.scale *= 0.5f; }
+        pl->desc = *d;                          // report the caller's geometry
+        pl->desc.chan_freq_hz = nullptr;
+        const bool ragged = (d->crop_start | d->crop_stop) & 1;
+        const size_t rows_bytes = pl->out_bytes;   // whole rows of the half-length view
+        pl->out_rows = pl->full_rows = d->crop_stop - d->crop_start;
+        pl->row_elems = 1;
+        pl->out_bytes = (size_t)pl->out_rows * pl->elem_bytes;
+        pl->split_column = true;
+        if (ragged && pl->out_rows > 0) {
+          // a crop edge inside a row: the passes write whole rows to a plan-owned buffer and the
+          // requested samples are copied out (device to device, at most 8 bytes skipped)
+          pl->split_skip = (size_t)(d->crop_start & 1) * pl->elem_bytes;
+          pl->tmpf_bytes = rows_bytes;
+          cudaError_t e = cudaMalloc(&pl->d_tmpf, pl->tmpf_bytes);
+          if (e != cudaSuccess) {
+            pbk_plan_destroy(pl);
+            return fail(PBK_ERR_NOMEM, "split buffer (%zu bytes): %s", rows_bytes,
+                        cudaGetErrorString(e));
+          }
+          pl->split_ragged = true;
+        }
+        *out = pl;
+        return PBK_OK;
+      }
+      pbk_plan_destroy(pl);                     // no fast coverage for this shape: generic path
+    }
+  }
   if (n < 4) {
     // not a power of two (or shorter than 16): Bluestein on top of the power-of-two passes
     if (d->nsamp < 2)
@@ -930,8 +985,11 @@ extern "C" int pbk_dedisp_exec_device(pbk_plan* pl, const void* d_in, void* d_ou
   if (pl->blue) return blue_exec(pl, d_in, d_out, d_chirp, st);
   if (pl->fused_tsum)   // the last pass adds its group sums to the output
     CUDA_TRY(cudaMemsetAsync(d_out, 0, pl->out_bytes, st));
-  int rc = run_passes(pl, d_in, d_out, d_chirp, st);
+  int rc = run_passes(pl, d_in, pl->split_ragged ? pl->d_tmpf : d_out, d_chirp, st);
   if (rc != PBK_OK) return rc;
+  if (pl->split_ragged)
+    CUDA_TRY(cudaMemcpyAsync(d_out, static_cast<const char*>(pl->d_tmpf) + pl->split_skip,
+                             pl->out_bytes, cudaMemcpyDeviceToDevice, st));
   if (pl->desc.downsample > 1 && !pl->fused_tsum) {
     cudaError_t e = launch_downsample(reinterpret_cast<const float*>(pl->d_tmpf),
                                       reinterpret_cast<float*>(d_out), pl->out_rows,
@@ -1444,10 +1502,10 @@ extern "C" int pbk_plan_describe(const pbk_plan* pl, char* buf, size_t n) {
     const bool blocked = pl->l2_chunks > 0;
     const char* sep = i == 0 ? "" : (blocked && (i == 2 || i == 3)) ? "+" : ";";
     if (ps.family >= 0)
-      w = snprintf(buf + off, n - off, "%s%s:L=2^%d:%s:W=%d:tiles=%lld:threads=%d%s", sep,
+      w = snprintf(buf + off, n - off, "%s%s:L=2^%d:%s:W=%d:tiles=%lld:threads=%d%s%s", sep,
                    mode, ps.a.log2L, "fast-r16",
                    2 << ps.finfo.log2pw, ps.ntiles, ps.finfo.threads,
-                   ps.a.tsum_log2 > 0 ? ":timesum" : "");
+                   ps.a.tsum_log2 > 0 ? ":timesum" : "", ps.a.split ? ":evenodd" : "");
     else
       w = snprintf(buf + off, n - off, "%s%s:L=2^%d:%s:W=%d:tiles=%u:threads=%d", sep,
                    mode, ps.a.log2L, ps.fast ? "generic-vec" : "generic", 2 << ps.a.log2pw,

@@ -340,6 +340,32 @@ __device__ __forceinline__ void fast_chirp(const PassArgs& p, const FastTile& T,
     cc0[i] = p.chan_const[3 * T.chan + i];
     cc1[i] = TWOCH ? p.chan_const[3 * (T.chan + 1) + i] : 0.0;
   }
+  if (TWOCH && p.split) {
+    // ONE column of length 2N whose even / odd samples are the two lanes (radix-2 decimation in
+    // time done by the memory layout: row j of the (N, 2) view holds x[2j], x[2j+1]).  Register m
+    // holds E[k], O[k] of the two half-length transforms at the natural index k = k0 + m N/R:
+    //   X[k] = E + w O,  X[k+N] = E - w O,  w = exp(-i pi k / N)      (full-length spectrum)
+    //   Y[k] = X[k] H(k),  Y[k+N] = X[k+N] H(k - N)                   (fftfreq: k+N >= 2N/2)
+    //   E' = (Y[k] + Y[k+N]) / 2,  O' = conj(w) (Y[k] - Y[k+N]) / 2   (the 1/2 is in p.scale)
+    const long long k0i = (long long)T.klow + ((long long)klo << p.log2Kmul);
+    const int log2N2 = 64 - __clzll((unsigned long long)p.N);          // log2(2N)
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+      const double kn = fma((double)m / R, Nd, k0);
+      const float2 h0 = fast_chirp_value(p, cc0, kn);
+      const float2 h1 = fast_chirp_value(p, cc0, kn - Nd);
+      const float2 w = unit_root((unsigned long long)(k0i + m * (p.N / R)), log2N2);
+      const float er = v[m].re.x, ei = v[m].im.x, orr = v[m].re.y, oi = v[m].im.y;
+      const float tr = w.x * orr - w.y * oi, ti = w.x * oi + w.y * orr;
+      const float x0r = er + tr, x0i = ei + ti, x1r = er - tr, x1i = ei - ti;
+      const float y0r = x0r * h0.x - x0i * h0.y, y0i = x0r * h0.y + x0i * h0.x;
+      const float y1r = x1r * h1.x - x1i * h1.y, y1i = x1r * h1.y + x1i * h1.x;
+      const float dr = y0r - y1r, di = y0i - y1i;
+      v[m].re = make_float2(y0r + y1r, w.x * dr + w.y * di);
+      v[m].im = make_float2(y0i + y1i, w.x * di - w.y * dr);
+    }
+    return;
+  }
 #pragma unroll
   for (int m = 0; m < R; ++m) {
     const double cm = (double)m / R - (m >= R / 2 ? 1.0 : 0.0);

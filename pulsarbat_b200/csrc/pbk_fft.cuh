@@ -101,6 +101,8 @@ struct PassArgs {
   int tsum_log2;      // fast final INV pass: > 0 = sum 2^tsum_log2 consecutive time rows of the
                       // detected output in the epilogue (row R fused; see fast_pass_kernel TSUM)
   int tsum_q;         // ... with groups of tsum_q adjacent CTAs covering adjacent column groups
+  int split;          // fast MID pass, P == 1: the lane pair is the even / odd samples of ONE column
+                      // of length 2N (see fast_chirp); N, df and the tables are the half length's
 };
 
 // ------------------------------------------------------------------------------------------

@@ -1000,3 +1000,41 @@ def test_guard_bands_intact(N, C, P, in_kind, out_kind, ds, crop, levels, monkey
     res = obuf[G:G + out_bytes].view(torch.float32)
     assert bool(torch.isfinite(res).all())                          # every output element written
     plan.destroy()
+
+
+# ------------------------------------------------------ single column as even / odd samples
+@pytest.mark.parametrize("N", [2 ** 13, 2 ** 16, 2 ** 20])
+@pytest.mark.parametrize("out_kind, crop_odd", [(0, False), (1, False), (0, True), (1, True)])
+def test_single_column_even_odd_split(N, out_kind, crop_odd, monkeypatch):
+    """BASELINE config 1's shape (one channel, one pol): the (N/2, 2) even/odd view runs on the
+    compile-time-shaped kernels with the radix-2 recombination inside the chirp step.  Parity
+    against the oracle, agreement with the generic kernels, crop edges inside an (even, odd) row."""
+    L = _lib()
+    rng = np.random.default_rng(N + out_kind)
+    sr, fc, dm = 16e6, 400e6, 71.0 * N / 2 ** 20 / 8          # sweep shorter than the block
+    x = crandn(rng, (N, 1))
+    start, stop = orc.crop_range(dm, N, fc, sr, 1, fc)
+    assert 0 <= start < stop <= N
+    start += (start % 2) ^ int(crop_odd)                       # even or odd edges, as asked
+    stop -= (stop % 2) ^ int(crop_odd)
+    want = orc.coherent_dedispersion(x.astype(np.complex128), dm, sample_rate=sr, center_freq=fc,
+                                     crop=False)[0][start:stop]
+    if out_kind == 1:
+        want = orc.to_intensity(want)
+    kw = dict(nsamp=N, nchan=1, npol=1, dm=dm, sample_rate_hz=sr, ref_freq_hz=fc,
+              chan_freq_hz=np.array([fc]), crop=(start, stop), out_kind=out_kind)
+    monkeypatch.delenv("PBK_NO_SPLIT", raising=False)
+    plan = L.DedispPlan(**kw)
+    if N >= 2 ** 16:                                          # (tiny plans may lack fast coverage)
+        assert ":evenodd" in plan.describe(), plan.describe()
+    assert (plan.out_rows, plan.row_elems) == (stop - start, 1)
+    got = plan.exec_host(x, plan.out_array()).copy()
+    plan.destroy()
+    assert got.shape[0] == stop - start
+    assert relerr(got, want) < 1e-5
+    monkeypatch.setenv("PBK_NO_SPLIT", "1")
+    plan = L.DedispPlan(**kw)
+    assert ":evenodd" not in plan.describe()
+    ref = plan.exec_host(x, plan.out_array()).copy()
+    plan.destroy()
+    assert relerr(got, ref) < 3e-6
