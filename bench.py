@@ -68,6 +68,12 @@ WORKLOADS = {
                             "per-pol intensity out"),
     "cfg1": dict(N=2 ** 20, C=1, P=1, dm=71.0, sr=16e6, fcen=400e6, stokes=None, ds=1, int8=False,
                  text="BasebandSignal 2^20 x 1 chan c64, 400 MHz, 16 MHz, DM=71"),
+    # config 1 is launch/latency-bound on a GPU, so also a batch of 256 such signals
+    # (as the 256 channels of one BasebandSignal; 256 x 16 MHz does not fit around 400 MHz, so
+    # the band is centred on 6 GHz)
+    "cfg1x256": dict(N=2 ** 20, C=256, P=1, dm=71.0, sr=16e6, fcen=6e9, stokes=None, ds=1,
+                     int8=False, text="batch of 256 config-1 signals: BasebandSignal 2^20 x 256 "
+                                      "chan c64, 16 MHz channels, 3952-8048 MHz, DM=71"),
     "small": dict(N=2 ** 16, C=16, P=2, dm=3.0, sr=6.25e6, fcen=600e6, stokes=True, ds=64,
                   int8=False, text="CI-sized smoke workload"),
 }
