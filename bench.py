@@ -37,6 +37,25 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# stdout carries exactly ONE JSON line: native libraries write there too (NCCL prints its version
+# banner on communicator creation), so file descriptor 1 is pointed at stderr for the whole run and
+# the line goes to a private duplicate of the original stdout.
+_JSON_OUT = None
+
+
+def claim_stdout():
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    print(json.dumps(line), file=out, flush=True)
+
+
 METRIC = "dedispersed complex Gsamples/s"
 UNIT = "Gsamples/s"
 
@@ -224,7 +243,7 @@ def run_reference(args, w):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -592,7 +611,7 @@ def run_b200(args, w):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(K * info["launches"]),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     plan.destroy()
     if world > 1:
         dist.destroy_process_group()
@@ -628,6 +647,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
