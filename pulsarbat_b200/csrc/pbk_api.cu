@@ -111,6 +111,7 @@ struct pbk_plan {
   // device resources owned by the plan
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
+  void* scratch2 = nullptr;     // second scratch array: intermediate passes run out of place
   float2* d_tw = nullptr;
   double* d_chanfreq = nullptr;
   double* d_chanconst = nullptr;   // per-channel constants of the fast MID chirp
@@ -864,6 +865,22 @@ static int dedisp_plan_create_impl(const pbk_dedisp_desc* d, const RampSpec* ram
                                          : (d->sample_rate_hz / (double)N) / d->ref_freq_hz;
   }
   if (m == 3) setup_l2_blocking(pl, (N >> l[0]) * I * 8, 1 << l[0]);
+  // Out-of-place intermediate passes: a pass that reads and writes the same scratch array is
+  // 2-3 % slower than one that writes another array (cfg2: 1.505 -> 1.463 ms and 1.476 -> 1.426 ms,
+  // profiles/r01_pingpong_scratch.log), so when the scratch is small against the device memory
+  // (<= 1/8 of it, and 4x its size still free) a second one is allocated and pass i reads
+  // buffer (i-1)&1 and writes buffer i&1.  PBK_NO_PINGPONG=1 keeps the passes in place.
+  if (pl->scratch && pl->l2_chunks == 0 && !getenv("PBK_NO_PINGPONG")) {
+    bool any = false;
+    for (const auto& ps : pl->passes)
+      any = any || (ps.in_role == ROLE_SCRATCH && ps.out_role == ROLE_SCRATCH);
+    size_t free_b = 0, total_b = 0;
+    if (any && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess &&
+        pl->scratch_bytes <= total_b / 8 && free_b >= 4 * pl->scratch_bytes &&
+        cudaMalloc(&pl->scratch2, pl->scratch_bytes) != cudaSuccess)
+      pl->scratch2 = nullptr;
+    cudaGetLastError();
+  }
   const int ds = (d->downsample > 1 && !pl->fused_tsum) ? 1 : 0;
   if (pl->l2_chunks > 0) {
     pl->launches = 2 + 3 * pl->l2_chunks + ds;
@@ -895,10 +912,16 @@ static void* role_ptr(const pbk_plan* pl, int role, const void* uin, void* uout)
 }
 
 static int launch_one(pbk_plan* pl, const Pass& ps, const void* d_in, void* d_out,
-                      const void* d_chirp, long long tile0, long long tile_end, cudaStream_t st) {
+                      const void* d_chirp, long long tile0, long long tile_end, cudaStream_t st,
+                      int idx = 0) {
   Pass p = ps;
   p.a.in = role_ptr(pl, ps.in_role, d_in, d_out);
   p.a.out = role_ptr(pl, ps.out_role, d_in, d_out);
+  if (pl->scratch2) {   // pass idx reads buffer (idx-1)&1 and writes buffer idx&1
+    void* buf[2] = {pl->scratch, pl->scratch2};
+    if (ps.in_role == ROLE_SCRATCH) p.a.in = buf[(idx + 1) & 1];
+    if (ps.out_role == ROLE_SCRATCH) p.a.out = buf[idx & 1];
+  }
   p.a.chirp_arr = reinterpret_cast<const float2*>(d_chirp);
   p.a.tile0 = tile0;
   const bool aligned = (((uintptr_t)p.a.in | (uintptr_t)p.a.out) & 15) == 0;
@@ -944,7 +967,8 @@ static int run_passes(pbk_plan* pl, const void* d_in, void* d_out, const void* d
   }
   for (size_t i = 0; i < np; ++i) {
     prof_mark(pl, seg++, st);
-    if ((rc = launch_one(pl, pl->passes[i], d_in, d_out, d_chirp, 0, -1, st)) != PBK_OK) return rc;
+    if ((rc = launch_one(pl, pl->passes[i], d_in, d_out, d_chirp, 0, -1, st, (int)i)) != PBK_OK)
+      return rc;
   }
   prof_mark(pl, seg, st);
   return PBK_OK;
@@ -1461,6 +1485,7 @@ extern "C" void pbk_plan_destroy(pbk_plan* pl) {
   prof_free(pl);
   blue_free(pl->blue);
   cudaFree(pl->scratch);
+  cudaFree(pl->scratch2);
   cudaFree(pl->d_tw);
   cudaFree(pl->d_ftab);
   cudaFree(pl->d_chanfreq);
@@ -1478,7 +1503,8 @@ extern "C" int pbk_plan_info(const pbk_plan* pl, int32_t* launches, int64_t* wor
                              int32_t* levels, int32_t* level_log2) {
   if (!pl) return fail(PBK_ERR_INVALID, "plan is NULL");
   if (launches) *launches = pl->launches;
-  if (workspace_bytes) *workspace_bytes = (int64_t)(pl->scratch_bytes + pl->tmpf_bytes);
+  if (workspace_bytes) *workspace_bytes =
+      (int64_t)(pl->scratch_bytes * (pl->scratch2 ? 2 : 1) + pl->tmpf_bytes);
   if (levels) *levels = pl->nlevels;
   if (level_log2)
     for (int i = 0; i < 3; ++i) level_log2[i] = pl->level_log2[i];
