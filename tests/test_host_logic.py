@@ -179,3 +179,22 @@ def test_phase_predictor_host_side():
     import io
     with pytest.raises(ValueError):
         pb.PhasePredictor.from_polyco(io.StringIO("this is not a polyco"))
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    # bench contract: rank 0 prints ONE JSON line on stdout; everything else (library banners,
+    # warnings) goes to stderr.  The reference arm needs no GPU, so it runs here.
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference",
+                        "--workload", "small", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "Gsamples/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port")
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
