@@ -70,6 +70,9 @@ int pbk_device_count(int* count);
 /* PCI bus id of a CUDA device ("0000:1b:00.0"), for binding the host process to the GPU's NUMA
  * node (one process per GPU); no reference counterpart */
 int pbk_device_pci_bus_id(int device, char* buf, int n);
+/* free / total bytes of device memory (the host mirror caps its plan cache by workspace bytes);
+ * no reference counterpart */
+int pbk_device_mem_info(int device, size_t* free_bytes, size_t* total_bytes);
 
 /* ---- coherent dedispersion ---------------------------------------------------------------
  * Replaces transforms/dedispersion.py:81-133 `coherent_dedispersion` for numpy/dask blocks and

@@ -137,6 +137,25 @@ def main():
         meta["stft"][str(n)].update(inv_sample_rate_hz=float(zi.sample_rate.to_value(u.Hz)),
                                     inv_freq_align=zi.freq_align, inv_nchan=zi.nchan)
 
+    # freq_align 'bottom' / 'top' with an EVEN number of channels: misc.py:41 slices both axes, and
+    # the frequency slice re-centres center_freq (core.py:479-484) before `like` sets freq_align,
+    # so the output's center_freq moves by half a coarse channel -- frozen here as metadata
+    xa = cnoise(np.random.default_rng(201), (256, 4))
+    out["stft_align_x"] = xa
+    meta["stft_align"] = {}
+    for align in ("bottom", "top", "center"):
+        for n in (32, 33):
+            za = make_signal(pb, u, Time, "BasebandSignal", xa.copy(), 1.0, 400.0, align)
+            ya = pb.contrib.stft(za, nperseg=n)
+            tag = f"{align}_{n}"
+            out[f"stft_align_{tag}_freqs_hz"] = ya.channel_freqs.to_value(u.Hz)
+            if align == "bottom" and n == 32:
+                out["stft_align_y"] = np.asarray(ya.data).copy()
+            meta["stft_align"][tag] = dict(
+                in_align=align, nperseg=n, freq_align=ya.freq_align, nchan=ya.nchan,
+                center_freq_hz=float(ya.center_freq.to_value(u.Hz)),
+                sample_rate_hz=float(ya.sample_rate.to_value(u.Hz)))
+
     # ---- detection (core.py:766-774, 882-966) ----------------------------------------------
     xp = cnoise(np.random.default_rng(300), (256, 3, 2))
     out["pol_x"] = xp

@@ -15,7 +15,7 @@ OUT_C64, OUT_INTENSITY, OUT_STOKES_I = 0, 1, 2
 
 EXPORTS = [
     "pbk_version", "pbk_last_error", "pbk_status_string", "pbk_device_count",
-    "pbk_device_pci_bus_id", "pbk_phase_predict",
+    "pbk_device_pci_bus_id", "pbk_device_mem_info", "pbk_phase_predict",
     "pbk_dedisp_plan_create", "pbk_dedisp_out_shape", "pbk_dedisp_exec_host",
     "pbk_dedisp_exec_device", "pbk_fft_plan_create", "pbk_stft_plan_create", "pbk_stft_plan_create_raw",
     "pbk_fft_exec_host", "pbk_fft_exec_device", "pbk_detect", "pbk_detect_scrunch", "pbk_shift_channels", "pbk_downsample", "pbk_fold",
@@ -74,6 +74,8 @@ def lib():
         L.pbk_status_string.argtypes = [ctypes.c_int]
         L.pbk_device_count.argtypes = [ctypes.POINTER(ctypes.c_int)]
         L.pbk_device_pci_bus_id.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
+        L.pbk_device_mem_info.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_size_t),
+                                          ctypes.POINTER(ctypes.c_size_t)]
         L.pbk_phase_predict.argtypes = [vp, i64, dbl, dbl, i64, ctypes.POINTER(dbl), i32, i64, vp,
                                         vp, i32, i32, vp]
         L.pbk_dedisp_plan_create.argtypes = [ctypes.POINTER(DedispDesc), ctypes.POINTER(vp)]
@@ -130,6 +132,13 @@ def device_count():
     n = ctypes.c_int(0)
     check(lib().pbk_device_count(ctypes.byref(n)))
     return n.value
+
+
+def device_mem_info(device=0):
+    """(free, total) bytes of device memory."""
+    f, t = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    check(lib().pbk_device_mem_info(int(device), ctypes.byref(f), ctypes.byref(t)))
+    return f.value, t.value
 
 
 def ptr(a):

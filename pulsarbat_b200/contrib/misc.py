@@ -1,7 +1,9 @@
 """Critically-sampled STFT / inverse ("channelize / unchannelize"), GPU-backed mirror of the
 reference's ``contrib/misc.py``."""
 
-from .. import kernels
+import numpy as np
+
+from .. import _dask, kernels
 from ..core import BasebandSignal
 
 __all__ = ["stft", "istft"]
@@ -19,8 +21,17 @@ def stft(z, /, window="boxcar", nperseg=256, noverlap=0, nfft=None):
     if not isinstance(z, BasebandSignal):
         raise ValueError("z must be a BasebandSignal.")
     n = int(nperseg)
-    z = z[: len(z) - len(z) % n]
-    x = kernels.stft(z.data, n)
+    # the reference slices BOTH axes (misc.py:41): the frequency slice re-centres center_freq on
+    # the mean of the channel centres and sets freq_align='center' (core.py:479-484) before
+    # ``like`` applies the new freq_align, so for 'bottom'/'top' inputs with an even number of
+    # channels the output's center_freq is shifted by half a coarse channel exactly as there
+    z = z[: len(z) - len(z) % n, :]
+    if _dask.is_dask(z.data):      # per time chunk (whole segments), lazily
+        x = _dask.map_time_chunks(z.data, lambda b: np.asarray(kernels.stft(np.asarray(b), n)),
+                                  multiple=n, rows_out=lambda m: m // n, cols_out=z.nchan * n,
+                                  out_dtype=z.dtype)
+    else:
+        x = kernels.stft(z.data, n)
     falign = "center" if n % 2 else "bottom"
     return type(z).like(z, x, sample_rate=z.sample_rate / n, freq_align=falign)
 
@@ -33,5 +44,10 @@ def istft(z, /, window="boxcar", nperseg=256, noverlap=0, nfft=None):
     if not isinstance(z, BasebandSignal):
         raise ValueError("z must be a BasebandSignal.")
     n = int(nperseg)
-    x = kernels.istft(z.data, n)
+    if _dask.is_dask(z.data):
+        x = _dask.map_time_chunks(z.data, lambda b: np.asarray(kernels.istft(np.asarray(b), n)),
+                                  multiple=1, rows_out=lambda m: m * n, cols_out=z.nchan // n,
+                                  out_dtype=z.dtype)
+    else:
+        x = kernels.istft(z.data, n)
     return type(z).like(z, x, sample_rate=z.sample_rate * n, freq_align="center")

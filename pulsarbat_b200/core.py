@@ -402,7 +402,11 @@ class BasebandSignal(RadioSignal):
 
     def to_intensity(self):
         """re**2 + im**2 per element (core.py:766-774), computed on the GPU."""
-        from . import kernels
+        from . import _dask, kernels
+        if _dask.is_dask(self.data):
+            return IntensitySignal.like(self, _dask.map_elementwise(
+                self.data, lambda b: np.asarray(kernels.detect(np.asarray(b), stokes=False)),
+                out_dtype=_dask.real_dtype_of(self.dtype)))
         return IntensitySignal.like(self, kernels.detect(self.data, stokes=False))
 
 
@@ -450,10 +454,20 @@ class DualPolarizationSignal(BasebandSignal):
 
     def to_stokes(self):
         """IQUV in the PSR/IEEE convention (core.py:930-966), computed on the GPU."""
-        from . import kernels
+        from . import _dask, kernels
+        if _dask.is_dask(self.data):
+            x, pt = self.data.rechunk({2: -1}), self.pol_type
+            return FullStokesSignal.like(self, _dask.map_elementwise(
+                x, lambda b: np.asarray(kernels.stokes(np.asarray(b), pt)),
+                out_dtype=_dask.real_dtype_of(self.dtype), chunks=x.chunks[:2] + ((4,),)))
         return FullStokesSignal.like(self, kernels.stokes(self.data, self.pol_type))
 
     def to_stokes_I(self):
         """Stokes I only (AA + BB, identical in both bases, core.py:948/960)."""
-        from . import kernels
+        from . import _dask, kernels
+        if _dask.is_dask(self.data):
+            x = self.data.rechunk({2: -1})
+            return IntensitySignal.like(self, _dask.map_elementwise(
+                x, lambda b: np.asarray(kernels.detect(np.asarray(b), stokes=True)),
+                out_dtype=_dask.real_dtype_of(self.dtype), chunks=x.chunks[:2], drop_axis=2))
         return IntensitySignal.like(self, kernels.detect(self.data, stokes=True))

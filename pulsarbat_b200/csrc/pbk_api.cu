@@ -75,6 +75,15 @@ extern "C" int pbk_device_pci_bus_id(int device, char* buf, int n) {
   return PBK_OK;
 }
 
+extern "C" int pbk_device_mem_info(int device, size_t* free_bytes, size_t* total_bytes) {
+  CUDA_TRY(cudaSetDevice(device));
+  size_t f = 0, t = 0;
+  CUDA_TRY(cudaMemGetInfo(&f, &t));
+  if (free_bytes) *free_bytes = f;
+  if (total_bytes) *total_bytes = t;
+  return PBK_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------
@@ -1706,7 +1715,11 @@ extern "C" int pbk_fold(const void* in, int64_t nsamp, int64_t row_elems, const 
   if (nsamp <= 0 || row_elems <= 0 || nbin <= 0) return fail(PBK_ERR_INVALID, "bad shape");
   if (ncoef < 1 || ncoef > kFoldMaxCoef)
     return fail(PBK_ERR_INVALID, "ncoef must be in [1, %d]", kFoldMaxCoef);
-  if (!(sample_rate_hz > 0)) return fail(PBK_ERR_INVALID, "sample_rate_hz must be > 0");
+  if (!(sample_rate_hz > 0) || !std::isfinite(sample_rate_hz))
+    return fail(PBK_ERR_INVALID, "sample_rate_hz must be finite and > 0");
+  for (int i = 0; i < ncoef; ++i)
+    if (!std::isfinite(coeffs[i]))
+      return fail(PBK_ERR_INVALID, "phase coefficient %d is not finite", i);
   CUDA_TRY(cudaSetDevice(device));
   FoldArgs fa;
   memset(&fa, 0, sizeof(fa));
@@ -1949,7 +1962,10 @@ extern "C" int pbk_memcpy_async(void* dst, const void* src, size_t bytes, int32_
                                 int32_t device, void* stream) {
   CUDA_TRY(cudaSetDevice(device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (to_device)   // large pageable sources go through the bounce pipeline (returns once src is read)
+  // large PAGEABLE sources go through the bounce pipeline, which has read src when it returns; a
+  // page-locked source (and any copy under 32 MiB) is one plain cudaMemcpyAsync, so the caller
+  // must keep src valid until the stream has reached the copy
+  if (to_device)
     CUDA_TRY(host_to_device(dst, src, bytes, st));
   else
     CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));

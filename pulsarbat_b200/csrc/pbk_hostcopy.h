@@ -109,8 +109,10 @@ inline int bounce_threads() {
   return (int)std::max(1u, std::min<unsigned>(8, hw / 2));   // half the cores, at most 8, by default
 }
 
-// host -> device.  On return every byte of h_src has been read (the caller may reuse it) and all
-// later work on `st` is ordered after the copy; the DMA itself may still be in flight.
+// host -> device; all later work on `st` is ordered after the copy.  A large PAGEABLE source takes
+// the bounce pipeline: on return every byte of h_src has been read (the caller may reuse it) while
+// the DMA may still be in flight.  A page-locked source, or any copy under 32 MiB, is one plain
+// cudaMemcpyAsync: h_src must then stay valid until the stream has reached the copy.
 inline cudaError_t host_to_device(void* d_dst, const void* h_src, size_t bytes, cudaStream_t st) {
   if (!bounce_wanted(h_src, bytes))
     return cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st);

@@ -338,8 +338,12 @@ __device__ __forceinline__ int fold_bin(const FoldArgs& a, long long n) {
   double c0 = a.coef[a.ncoef - 1];
   for (int i = a.ncoef - 2; i >= 0; --i) c0 = __dadd_rn(a.coef[i], __dmul_rn(c0, t));
   const double fr = __dsub_rn(c0, floor(c0));
-  const long long b = (long long)floor(__dmul_rn(fr, (double)a.nbin));
-  return (int)(b % a.nbin);
+  long long b = (long long)floor(__dmul_rn(fr, (double)a.nbin));
+  // fr*nbin can round up to nbin (-> bin 0, like the oracle's `% nbin`); a phase that is not
+  // finite (overflowing polynomial) must not index outside the histogram either
+  b = b == a.nbin ? 0 : b;
+  if (!(b >= 0 && b < a.nbin)) b = 0;
+  return (int)b;
 }
 
 // Device-side PhasePredictor.__call__ (pulsar/predictor.py:121-147) for one polyco entry: the

@@ -6,9 +6,15 @@ The storage is a torch CUDA tensor (PyTorch is the device-memory and stream plum
 the compute); complex data is kept as torch.complex64.
 """
 
+import os
+import warnings
+
 import numpy as np
 
 __all__ = ["DeviceArray"]
+
+#: implicit device -> host copies (np.asarray(device_array)) above this size warn once per call site
+_D2H_WARN_BYTES = int(float(os.environ.get("PBK_D2H_WARN_BYTES", 256 << 20)))
 
 _NP2T = None
 
@@ -91,8 +97,19 @@ class DeviceArray:
     def __len__(self):
         return self.tensor.shape[0]
 
+    def numpy(self):
+        """Explicit device -> host copy (never warns)."""
+        return self.tensor.detach().cpu().numpy()
+
     def __array__(self, dtype=None, copy=None):
-        a = self.tensor.detach().cpu().numpy()
+        # np.asarray(signal) on a resident array is a full device -> host copy: harmless for a
+        # profile, a hidden multi-gigabyte PCIe transfer for a voltage block -- say so
+        nbytes = self.tensor.numel() * self.tensor.element_size()
+        if nbytes > _D2H_WARN_BYTES:
+            warnings.warn(f"implicit device->host copy of {nbytes / 2**20:.0f} MiB from a "
+                          "DeviceArray (np.asarray / __array__); call .numpy() to make it explicit "
+                          "or raise $PBK_D2H_WARN_BYTES", ResourceWarning, stacklevel=2)
+        a = self.numpy()
         return a if dtype is None else a.astype(dtype)
 
     def __dlpack__(self, stream=None):

@@ -33,49 +33,147 @@ def default_device():
 
 
 # --------------------------------------------------------------------------------------------
-# plan cache: plans own their scratch (gigabytes for the large configs), so the cache is small
+# plan cache: plans own their scratch (gigabytes for the large configs), so the cache is bounded
+# by BYTES of device workspace as well as by count, entries are pinned while a call uses them and
+# new plans are built outside the global lock
 # --------------------------------------------------------------------------------------------
 _MAX_PLANS = int(os.environ.get("PBK_PLAN_CACHE", "6"))
 _cache = collections.OrderedDict()
 _cache_lock = threading.Lock()
 
 
+def _max_cache_bytes():
+    """Cap on the summed workspace of IDLE + in-use cached plans: $PBK_PLAN_CACHE_BYTES, else 40 %
+    of the device memory (a dask thread pool with varied chunk shapes must not fill the GPU with
+    scratch arrays); the plan a call is about to use is always admitted."""
+    v = os.environ.get("PBK_PLAN_CACHE_BYTES")
+    if v:
+        return int(float(v))
+    global _mem_total
+    if _mem_total is None:
+        try:
+            _mem_total = L.device_mem_info(default_device())[1]
+        except Exception:
+            _mem_total = 0
+    return int(0.4 * _mem_total) if _mem_total else 64 << 30
+
+
+_mem_total = None
+
+
 class _Entry:
-    __slots__ = ("plan", "lock")
+    __slots__ = ("plan", "lock", "refs", "bytes", "ready", "error", "doomed")
 
-    def __init__(self, plan):
-        self.plan = plan
-        self.lock = threading.Lock()
+    def __init__(self):
+        self.plan = None
+        self.lock = threading.Lock()      # serialises executions of this plan
+        self.refs = 0                     # calls currently holding the entry (never evicted)
+        self.bytes = 0
+        self.ready = threading.Event()    # set once the creator has built (or failed to build) it
+        self.error = None
+        self.doomed = False               # removed from the cache while in use: destroy on release
 
 
-def _get_plan(key, factory):
-    with _cache_lock:
-        ent = _cache.get(key)
-        if ent is not None:
-            _cache.move_to_end(key)
-            return ent
-        ent = _Entry(factory())
-        _cache[key] = ent
-        while len(_cache) > _MAX_PLANS:
-            for k, old in _cache.items():
-                if old is not ent and old.lock.acquire(blocking=False):
-                    try:
-                        old.plan.destroy()
-                    finally:
-                        old.lock.release()
-                    del _cache[k]
-                    break
-            else:
+def _evict_locked(keep):
+    """Pop idle least-recently-used entries until the cache is within its limits (lock held);
+    returns the plans to destroy once the lock is released."""
+    victims = []
+    cap = _max_cache_bytes()
+
+    def over():
+        return (len(_cache) > max(_MAX_PLANS, 1) or
+                sum(e.bytes for e in _cache.values()) > cap)
+    while over():
+        for k, e in _cache.items():
+            if e is not keep and e.refs == 0 and e.ready.is_set():
+                victims.append(e)
+                del _cache[k]
                 break
+        else:
+            break                          # everything left is in use
+    return victims
+
+
+def _acquire(key, factory):
+    """Pinned cache entry for ``key`` (refs + 1); the plan is built by exactly one thread, outside
+    the global lock, while others asking for the same key wait for it."""
+    while True:
+        with _cache_lock:
+            ent = _cache.get(key)
+            creator = ent is None
+            if creator:
+                ent = _cache[key] = _Entry()
+            else:
+                _cache.move_to_end(key)
+            ent.refs += 1
+        if not creator:
+            ent.ready.wait()
+            if ent.error is None:
+                return ent
+            with _cache_lock:
+                ent.refs -= 1
+            continue                       # the creator failed: try to build it ourselves
+        try:
+            ent.plan = factory()
+            try:
+                ent.bytes = int(ent.plan.info()["workspace_bytes"])
+            except Exception:
+                ent.bytes = 0
+        except BaseException as exc:
+            with _cache_lock:
+                ent.error = exc
+                ent.refs -= 1
+                if _cache.get(key) is ent:
+                    del _cache[key]
+            ent.ready.set()
+            raise
+        with _cache_lock:
+            victims = _evict_locked(ent)
+        ent.ready.set()
+        for v in victims:
+            v.plan.destroy()
         return ent
 
 
-def clear_plan_cache():
+def _release(ent):
     with _cache_lock:
-        for ent in _cache.values():
-            with ent.lock:
-                ent.plan.destroy()
+        ent.refs -= 1
+        kill = ent.doomed and ent.refs == 0
+    if kill:
+        ent.plan.destroy()
+
+
+class _use_plan:
+    """``with _use_plan(key, factory) as plan:`` -- the entry stays pinned for the whole block;
+    take ``self.lock`` (``with ctx.lock:``) around the execution itself."""
+
+    def __init__(self, key, factory):
+        self.key, self.factory, self.ent = key, factory, None
+
+    def __enter__(self):
+        self.ent = _acquire(self.key, self.factory)
+        self.lock = self.ent.lock
+        return self.ent.plan
+
+    def __exit__(self, *exc):
+        _release(self.ent)
+        return False
+
+
+def clear_plan_cache():
+    """Destroy every cached plan; plans a running call still holds are destroyed when it ends."""
+    with _cache_lock:
+        ents = list(_cache.values())
         _cache.clear()
+        idle = []
+        for e in ents:
+            if e.refs == 0 and e.ready.is_set():
+                idle.append(e)
+            else:
+                e.doomed = True
+    for e in idle:
+        if e.plan is not None:
+            e.plan.destroy()
 
 
 def _stream():
@@ -175,12 +273,18 @@ def dedisperse(data, *, dm, sample_rate_hz, chan_freq_hz, ref_freq_hz, crop=None
     key = ("dedisp", nsamp, nchan, npol, raw, int(out_kind), float(dm),
            float(sample_rate_hz), float(ref_freq_hz), freqs.tobytes(), start, stop,
            int(downsample), chirp_array is not None, dev)
-    ent = _get_plan(key, lambda: L.DedispPlan(
+    ctx = _use_plan(key, lambda: L.DedispPlan(
         nsamp=nsamp, nchan=nchan, npol=npol, dm=dm, sample_rate_hz=sample_rate_hz,
         ref_freq_hz=ref_freq_hz, chan_freq_hz=freqs, crop=(start, stop),
         in_dtype=in_dtype, out_kind=out_kind, downsample=downsample,
         explicit_chirp=chirp_array is not None, device=dev))
-    plan = ent.plan
+    with ctx as plan:
+        return _dedisperse_with(ctx, plan, data, nsamp, nchan, trailing, out_kind, chirp_array,
+                                int8, raw_np, dev)
+
+
+def _dedisperse_with(ent, plan, data, nsamp, nchan, trailing, out_kind, chirp_array, int8, raw_np,
+                     dev):
     out_trailing = (nchan,) if out_kind == L.OUT_STOKES_I else (nchan,) + trailing
     out_shape = (plan.out_rows,) + out_trailing
 
@@ -312,20 +416,21 @@ def phase_ramp(data, shift_samples=None, zero_lo=None, zero_hi=None, device=None
         return None if a is None else np.ascontiguousarray(a, dtype=dt).tobytes()
     key = ("ramp", nsamp, ncols, key_of(shift_samples, np.float64), key_of(zero_lo, np.int64),
            key_of(zero_hi, np.int64), dev)
-    ent = _get_plan(key, lambda: L.RampPlan(nsamp, ncols, shift_samples, zero_lo, zero_hi,
+    ctx = _use_plan(key, lambda: L.RampPlan(nsamp, ncols, shift_samples, zero_lo, zero_hi,
                                             device=dev))
-    if _is_dev(data):
-        x = data.contiguous()
-        if x.dtype != np.complex64:
-            x = x.astype(np.complex64)
-        out = DeviceArray.empty(shape, np.complex64, dev)
-        with ent.lock:
-            ent.plan.exec_device(x.ptr, out.ptr, _stream())
-        return out
-    x, odt = _host_c64(data)
-    out = _result(shape, np.complex64)
-    with ent.lock:
-        ent.plan.exec_host(x, out)
+    with ctx as plan:
+        if _is_dev(data):
+            x = data.contiguous()
+            if x.dtype != np.complex64:
+                x = x.astype(np.complex64)
+            out = DeviceArray.empty(shape, np.complex64, dev)
+            with ctx.lock:
+                plan.exec_device(x.ptr, out.ptr, _stream())
+            return out
+        x, odt = _host_c64(data)
+        out = _result(shape, np.complex64)
+        with ctx.lock:
+            plan.exec_host(x, out)
     return out if odt == np.complex64 else out.astype(odt)
 
 
@@ -339,25 +444,26 @@ def analytic_decimate(data, device=None):
     rows_out = (nsamp + 1) // 2
     dev = data.device if _is_dev(data) else (default_device() if device is None else device)
     key = ("hilbert", nsamp, ncols, dev)
-    ent = _get_plan(key, lambda: L.RampPlan(nsamp, ncols,
+    ctx = _use_plan(key, lambda: L.RampPlan(nsamp, ncols,
                                             flags=L.RampPlan.HILBERT | L.RampPlan.REAL_INPUT,
                                             device=dev))
-    if _is_dev(data):
-        x = data.contiguous()
-        if x.dtype != np.float32:
-            x = x.astype(np.float32)
-        tmp = DeviceArray.empty(shape, np.complex64, dev)
-        out = DeviceArray.empty((rows_out, ncols), np.complex64, dev)
-        st = _stream()
-        with ent.lock:
-            ent.plan.exec_device(x.ptr, tmp.ptr, st)
-        L.check(L.lib().pbk_decimate2(L.ptr(tmp.ptr), L.ptr(out.ptr), nsamp, ncols, 1, dev,
-                                      ctypes.c_void_p(st)))
-        return out
-    x = np.ascontiguousarray(data, dtype=np.float32)
-    tmp = np.empty(shape, np.complex64)
-    with ent.lock:
-        ent.plan.exec_host(x, tmp)
+    with ctx as plan:
+        if _is_dev(data):
+            x = data.contiguous()
+            if x.dtype != np.float32:
+                x = x.astype(np.float32)
+            tmp = DeviceArray.empty(shape, np.complex64, dev)
+            out = DeviceArray.empty((rows_out, ncols), np.complex64, dev)
+            st = _stream()
+            with ctx.lock:
+                plan.exec_device(x.ptr, tmp.ptr, st)
+            L.check(L.lib().pbk_decimate2(L.ptr(tmp.ptr), L.ptr(out.ptr), nsamp, ncols, 1, dev,
+                                          ctypes.c_void_p(st)))
+            return out
+        x = np.ascontiguousarray(data, dtype=np.float32)
+        tmp = np.empty(shape, np.complex64)
+        with ctx.lock:
+            plan.exec_host(x, tmp)
     out = _result((rows_out, ncols), np.complex64)
     L.check(L.lib().pbk_decimate2(L.ptr(tmp), L.ptr(out), nsamp, ncols, 0, dev, None))
     return out
@@ -453,22 +559,23 @@ def downsample(data, factor, device=None):
 # FFT / channelize                 reference: fft.py:30-48, contrib/misc.py:17-93
 # --------------------------------------------------------------------------------------------
 def _run_fft_plan(key, factory, data, out_shape, raw_np=None):
-    ent = _get_plan(key, factory)
-    if _is_dev(data):
-        x = data.contiguous()
-        if raw_np is None and x.dtype != np.complex64:
-            x = x.astype(np.complex64)
-        out = DeviceArray.empty(out_shape, np.complex64, x.device)
-        with ent.lock:
-            ent.plan.exec_device(x.ptr, out.ptr, _stream())
-        return out
-    if raw_np is not None:
-        x, odt = np.ascontiguousarray(data, dtype=raw_np), np.complex64
-    else:
-        x, odt = _host_c64(data)
-    out = _result(out_shape, np.complex64)
-    with ent.lock:
-        ent.plan.exec_host(x, out)
+    ctx = _use_plan(key, factory)
+    with ctx as plan:
+        if _is_dev(data):
+            x = data.contiguous()
+            if raw_np is None and x.dtype != np.complex64:
+                x = x.astype(np.complex64)
+            out = DeviceArray.empty(out_shape, np.complex64, x.device)
+            with ctx.lock:
+                plan.exec_device(x.ptr, out.ptr, _stream())
+            return out
+        if raw_np is not None:
+            x, odt = np.ascontiguousarray(data, dtype=raw_np), np.complex64
+        else:
+            x, odt = _host_c64(data)
+        out = _result(out_shape, np.complex64)
+        with ctx.lock:
+            plan.exec_host(x, out)
     return out if odt == np.complex64 else out.astype(odt)
 
 
@@ -540,12 +647,32 @@ def fold(data, coeffs, sample_rate_hz, nbin, n0=0, profile=None, counts=None, wa
     nsamp = shape[0]
     relems = int(np.prod(shape[1:])) if len(shape) > 1 else 1
     c = np.ascontiguousarray(coeffs, dtype=np.float64)
+    if c.ndim != 1 or not np.all(np.isfinite(c)):
+        raise ValueError("coeffs must be a 1-D array of finite numbers")
     cp = c.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+    def check_acc(a, name, dtype, want_shape):
+        # raw pointers go to the kernel: a wrong dtype or shape would corrupt memory silently
+        if a is None:
+            return
+        if np.dtype(a.dtype) != np.dtype(dtype) or tuple(a.shape) != tuple(want_shape):
+            raise ValueError(f"{name} must be {np.dtype(dtype).name} of shape {tuple(want_shape)}, "
+                             f"got {np.dtype(a.dtype).name} {tuple(a.shape)}")
+        if _is_dev(data) != _is_dev(a):
+            raise ValueError(f"{name} must live where the data lives (host array / DeviceArray)")
+        if not _is_dev(a) and not a.flags["C_CONTIGUOUS"]:
+            raise ValueError(f"{name} must be C-contiguous")
+    check_acc(profile, "profile", np.float32, (int(nbin),) + shape[1:])
+    check_acc(counts, "counts", np.int64, (int(nbin),))
     if _is_dev(data):
         x = data.contiguous()
         if x.dtype != np.float32:
             x = x.astype(np.float32)
         dev = x.device
+        if profile is not None:
+            profile = profile.contiguous()
+        if counts is not None:
+            counts = counts.contiguous()
         import torch
         if profile is None:
             profile = DeviceArray(torch.zeros((nbin,) + shape[1:], dtype=torch.float32,

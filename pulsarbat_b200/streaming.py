@@ -10,6 +10,9 @@ three (PCIe is full duplex: the two copies run concurrently).  The arithmetic is
 ``kernels.dedisperse``.
 """
 
+import os
+import threading
+
 import numpy as np
 
 from . import _lib as L
@@ -17,24 +20,60 @@ from . import kernels
 
 __all__ = ["dedisperse_blocks", "clear_stream_cache"]
 
-# the plan, device buffers, pinned result buffers, streams and events of the last stream shape:
-# allocating ~13 GB per call would otherwise cost several milliseconds per block
-_state = {"key": None, "val": None}
+# Plan, device buffers, pinned result buffers, streams and events of a stream shape cost ~13 GB of
+# allocations for cfg2, so finished generators hand theirs back to a small pool instead of freeing
+# them.  Every live generator OWNS its state for its whole lifetime (checked out under a lock,
+# returned in a ``finally``), so two generators that are alive at once -- zip() over two streams,
+# overlap_save_dedispersion called from several dask worker threads -- never share buffers or
+# events, whether or not their shapes agree.
+_MAX_IDLE = int(os.environ.get("PBK_STREAM_CACHE", "2"))
+_pool = []                       # [(key, state)], most recently returned last; idle states only
+_pool_lock = threading.Lock()
+
+
+class _State:
+    __slots__ = ("plan", "d_in", "d_out", "h_out", "s_copy", "s_comp", "s_down", "ev")
+
+    def __init__(self, plan, d_in, d_out, h_out, s_copy, s_comp, s_down, ev):
+        self.plan, self.d_in, self.d_out, self.h_out = plan, d_in, d_out, h_out
+        self.s_copy, self.s_comp, self.s_down, self.ev = s_copy, s_comp, s_down, ev
+
+    def quiesce(self):
+        """Wait until nothing queued by a previous owner is still running on the three streams."""
+        for st in (self.s_copy, self.s_comp, self.s_down):
+            st.synchronize()
+
+    def destroy(self):
+        self.quiesce()           # buffers must not be freed under in-flight copies or kernels
+        self.plan.destroy()
+        self.d_in = self.d_out = self.h_out = None
 
 
 def clear_stream_cache():
-    """Free the cached plan and buffers of :func:`dedisperse_blocks`."""
-    if _state["val"] is not None:
-        _state["val"][0].destroy()
-    _state["key"] = _state["val"] = None
+    """Free the idle cached plans and buffers of :func:`dedisperse_blocks`.  States owned by a
+    live generator are not touched; they are freed (or pooled again) when it finishes."""
+    with _pool_lock:
+        idle, _pool[:] = list(_pool), []
+    for _, st in idle:
+        st.destroy()
 
 
-def _get_state(key, make):
-    if _state["key"] != key:
-        clear_stream_cache()
-        _state["val"] = make()
-        _state["key"] = key
-    return _state["val"]
+def _checkout(key, make):
+    with _pool_lock:
+        for i in range(len(_pool) - 1, -1, -1):
+            if _pool[i][0] == key:
+                return _pool.pop(i)[1]
+    return make()                # built outside the lock: a multi-GB allocation must not block others
+
+
+def _checkin(key, state):
+    drop = []
+    with _pool_lock:
+        _pool.append((key, state))
+        while len(_pool) > max(_MAX_IDLE, 0):
+            drop.append(_pool.pop(0)[1])
+    for st in drop:
+        st.destroy()
 
 
 def dedisperse_blocks(blocks, *, dm, sample_rate_hz, chan_freq_hz, ref_freq_hz, crop=None,
@@ -91,20 +130,30 @@ def dedisperse_blocks(blocks, *, dm, sample_rate_hz, chan_freq_hz, ref_freq_hz, 
         out_trailing = (nchan,) if out_kind == L.OUT_STOKES_I else (nchan,) + tuple(trailing)
         out_shape = (plan.out_rows,) + out_trailing
         with torch.cuda.device(tdev):
-            return (plan,
-                    [torch.empty(shape, dtype=in_t, device=tdev) for _ in range(2)],
-                    [torch.empty(out_shape, dtype=out_t, device=tdev) for _ in range(2)],
-                    [torch.empty(out_shape, dtype=out_t, pin_memory=True) for _ in range(2)],
-                    torch.cuda.Stream(tdev), torch.cuda.Stream(tdev), torch.cuda.Stream(tdev),
-                    [torch.cuda.Event() for _ in range(6)])
+            return _State(plan,
+                          [torch.empty(shape, dtype=in_t, device=tdev) for _ in range(2)],
+                          [torch.empty(out_shape, dtype=out_t, device=tdev) for _ in range(2)],
+                          [torch.empty(out_shape, dtype=out_t, pin_memory=True) for _ in range(2)],
+                          torch.cuda.Stream(tdev), torch.cuda.Stream(tdev), torch.cuda.Stream(tdev),
+                          [torch.cuda.Event() for _ in range(6)])
 
     key = (shape, raw, body, float(dm), float(sample_rate_hz), float(ref_freq_hz),
            freqs.tobytes(), start, stop, int(out_kind), int(downsample), dev)
-    plan, d_in, d_out, h_out, s_copy, s_comp, s_down, ev = _get_state(key, make)
+    state = _checkout(key, make)      # owned by this generator until the finally below
+    try:
+        state.quiesce()               # a previous owner may have been abandoned mid-stream
+        yield from _run_stream(state, first, it, shape, dev, tdev, pinned_out)
+    finally:
+        # runs on exhaustion, on .close() and when an abandoned generator is collected
+        state.quiesce()
+        _checkin(key, state)
+
+
+def _run_stream(state, first, it, shape, dev, tdev, pinned_out):
+    import torch
+    plan, d_in, d_out, h_out = state.plan, state.d_in, state.d_out, state.h_out
+    s_copy, s_comp, s_down, ev = state.s_copy, state.s_comp, state.s_down, state.ev
     copied, consumed, done = ev[0:2], ev[2:4], ev[4:6]   # per slot: H2D done / kernels done / D2H done
-    s_copy.synchronize()      # an earlier, abandoned generator may have left work in flight
-    s_comp.synchronize()
-    s_down.synchronize()
 
     def upload(block, slot, reuse):
         hb = np.ascontiguousarray(block, dtype=first.dtype)

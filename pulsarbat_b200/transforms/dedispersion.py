@@ -9,6 +9,7 @@ import math
 
 import numpy as np
 
+from .. import _dask
 from .. import _lib as L
 from .. import kernels
 from .. import units as u
@@ -128,9 +129,23 @@ def coherent_dedispersion(z, DM, /, *, ref_freq=None, chirp=None):
     if ref_freq is None:
         ref_freq = z.center_freq
     start, stop = crop_range(z, DM, ref_freq)
-    x = kernels.dedisperse(z.data, dm=DM.dm, sample_rate_hz=z.sample_rate_hz,
-                           chan_freq_hz=z.channel_freqs_hz, ref_freq_hz=_hz(ref_freq),
-                           crop=(start, stop), chirp_array=chirp)
+    if _dask.is_dask(z.data):
+        # lazy input: one GPU call per channel chunk when the result is computed, every chunk
+        # with ITS channel frequencies and the GLOBAL ref_freq and crop (transforms.py:49-50)
+        freqs, sr, rf, dm = z.channel_freqs_hz, z.sample_rate_hz, _hz(ref_freq), DM.dm
+        ch = None if chirp is None else np.asarray(chirp).reshape(len(z), z.nchan)
+
+        def chunk(block, lo, hi):
+            return np.asarray(kernels.dedisperse(
+                np.asarray(block), dm=dm, sample_rate_hz=sr, chan_freq_hz=freqs[lo:hi],
+                ref_freq_hz=rf, crop=(start, stop),
+                chirp_array=None if ch is None else ch[:, lo:hi]))
+        x = _dask.map_channel_chunks(z.data, chunk, out_rows=max(0, stop - start),
+                                     out_dtype=z.dtype)
+    else:
+        x = kernels.dedisperse(z.data, dm=DM.dm, sample_rate_hz=z.sample_rate_hz,
+                               chan_freq_hz=z.channel_freqs_hz, ref_freq_hz=_hz(ref_freq),
+                               crop=(start, stop), chirp_array=chirp)
     if stop <= start:
         # empty crop: the reference would hand back a zero-length slice (dedispersion.py:133)
         start = min(start, len(z))
@@ -184,11 +199,31 @@ def dedisperse_detect(z, DM, /, *, ref_freq=None, stokes_I=False, downsample=1, 
     if ref_freq is None:
         ref_freq = z.center_freq
     start, stop = crop_range(z, DM, ref_freq) if crop else (0, len(z))
-    x = kernels.dedisperse(z.data if raw is None else raw, dm=DM.dm,
-                           sample_rate_hz=z.sample_rate_hz, chan_freq_hz=z.channel_freqs_hz,
-                           ref_freq_hz=_hz(ref_freq), crop=(start, stop),
-                           out_kind=L.OUT_STOKES_I if stokes_I else L.OUT_INTENSITY,
-                           downsample=downsample, int8=raw is not None)
+    kind = L.OUT_STOKES_I if stokes_I else L.OUT_INTENSITY
+    src = z.data if raw is None else raw
+    if _dask.is_dask(src):
+        freqs, sr, rf, dm = z.channel_freqs_hz, z.sample_rate_hz, _hz(ref_freq), DM.dm
+
+        def chunk(block, lo, hi):
+            return np.asarray(kernels.dedisperse(
+                np.asarray(block), dm=dm, sample_rate_hz=sr, chan_freq_hz=freqs[lo:hi],
+                ref_freq_hz=rf, crop=(start, stop), out_kind=kind, downsample=downsample,
+                int8=raw is not None))
+        rows = max(0, stop - start) // int(downsample)
+        if raw is not None:        # (N, C, P, 2) int8: the (re, im) axis never survives
+            def chunk_raw(block, lo, hi):
+                y = chunk(block, lo, hi)
+                return y.reshape(y.shape + (1,) * (block.ndim - y.ndim))
+            x = _dask.map_channel_chunks(src, chunk_raw, out_rows=rows, out_dtype=np.float32)
+            x = x.reshape(x.shape[:2] + (() if stokes_I else tuple(z.shape[2:])))
+        else:
+            x = _dask.map_channel_chunks(src, chunk, out_rows=rows, drop_trailing=stokes_I,
+                                         out_dtype=_dask.real_dtype_of(z.dtype))
+    else:
+        x = kernels.dedisperse(src, dm=DM.dm, sample_rate_hz=z.sample_rate_hz,
+                               chan_freq_hz=z.channel_freqs_hz, ref_freq_hz=_hz(ref_freq),
+                               crop=(start, stop), out_kind=kind, downsample=downsample,
+                               int8=raw is not None)
     kw = {"chan_bw": z.chan_bw}
     if downsample > 1:
         kw["sample_rate"] = z.sample_rate / downsample

@@ -152,7 +152,7 @@ def test_type_errors_match_reference():
     assert pb.contrib.stft(z, window="hann") is NotImplemented   # misc.py:31-32
     assert pb.contrib.istft(z, noverlap=2) is NotImplemented
     with pytest.raises(AttributeError):
-        pb.fft.rfft
+        pb.fft.fftshift                              # not in the reference list (fft.py:31-32)
 
 
 def test_phase_predictor_host_side():

@@ -118,6 +118,34 @@ def test_oracle_incoherent_and_real_to_complex_match_reference():
     assert relerr(orc.real_to_complex(G["r2c_x64"]), G["r2c_y64"]) < 1e-14
 
 
+def _check_stft_align(pb, stft_data):
+    """Metadata of contrib.stft for freq_align bottom / top / center inputs with an even number
+    of channels (misc.py:41 + core.py:479-484): center_freq, freq_align, channel_freqs."""
+    u = pb.units
+    for tag, m in META["stft_align"].items():
+        z = pb.BasebandSignal(G["stft_align_x"], sample_rate=1e6 * u.Hz,
+                              center_freq=400e6 * u.Hz, freq_align=m["in_align"],
+                              start_time=pb.Time(*META["T0"]))
+        y = pb.contrib.stft(z, nperseg=m["nperseg"])
+        assert y.nchan == m["nchan"] and y.freq_align == m["freq_align"], tag
+        assert float(y.center_freq.to_value(u.Hz)) == m["center_freq_hz"], tag
+        assert math.isclose(float(y.sample_rate.to_value(u.Hz)), m["sample_rate_hz"],
+                            rel_tol=1e-15)
+        np.testing.assert_allclose(np.asarray(u.to_value(y.channel_freqs, u.Hz)),
+                                   G[f"stft_align_{tag}_freqs_hz"], rtol=1e-15, atol=0)
+        if tag == "bottom_32" and stft_data:
+            assert relerr(np.asarray(y.data), G["stft_align_y"]) < TOL
+
+
+def test_stft_metadata_for_bottom_and_top_alignment(monkeypatch):
+    """Host logic only: the kernel wrapper is replaced by the oracle so this runs without a GPU."""
+    import pulsarbat_b200 as pb
+    monkeypatch.setattr(pb.kernels, "stft",
+                        lambda x, n, **kw: orc.stft(np.asarray(x), n).astype(np.complex64))
+    assert relerr(orc.stft(G["stft_align_x"].astype(np.complex128), 32), G["stft_align_y"]) < 5e-7
+    _check_stft_align(pb, stft_data=False)
+
+
 @pytest.mark.skipif(not ref_run.available(), reason="/root/reference is not on this machine")
 def test_live_reference_reproduces_frozen_vectors(tmp_path, monkeypatch):
     """Re-run the reference's own source now and compare with the committed file: integers and
@@ -207,6 +235,12 @@ def test_cuda_stft_istft_match_reference():
         assert zi.nchan == mm["inv_nchan"] and zi.freq_align == mm["inv_freq_align"]
         assert math.isclose(float(zi.sample_rate.to_value(u.Hz)), mm["inv_sample_rate_hz"],
                             rel_tol=1e-15)
+
+
+@pytest.mark.gpu
+def test_cuda_stft_alignment_metadata_matches_reference():
+    import pulsarbat_b200 as pb
+    _check_stft_align(pb, stft_data=True)
 
 
 @pytest.mark.gpu
