@@ -439,6 +439,10 @@ def run_b200(args, w):
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        # BASELINE.json's "% of HBM roofline": compulsory bytes of the WHOLE fused op (input once +
+        # output once) over the whole step; `frac` above is the dominant launch's
+        "whole_op_frac": op_achieved / peak,
+        "whole_op_frac_of_nominal_8TBs": op_achieved / 8000.0,
         "kernel": desc[top], "kernel_ms": float(avg[top]),
         "kernel_share_of_step": float(avg[top] / avg.sum()),
         "kernel_bytes_per_launch": int(kbytes),
@@ -573,6 +577,10 @@ def run_b200(args, w):
         e2e = {"value": world * nsamp * ke / dts / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": int(hnp.nbytes), "d2h_bytes_per_step": rbytes,
                "steps": ke, "ms_per_step": dts / ke * 1e3,
+               # what a numpy user gets from ordinary pageable memory, one synchronous call per
+               # block through the library's bounce pipeline (the headline e2e streams the SAME
+               # page-locked block every step)
+               "pageable": single["pageable_input"],
                "api": "pulsarbat_b200.streaming.dedisperse_blocks(pinned numpy blocks): upload of "
                       "block i+1, kernels of block i and download of block i-1 overlap (plan and "
                       "buffers cached after the warm-up stream)",
@@ -594,6 +602,13 @@ def run_b200(args, w):
                "sample": f"{nch} of {C} channels x {P} pol x 2^{int(np.log2(N))} samples, one "
                          f"pass, chirp generation included ({dt:.1f} s)"}
 
+    # ---- the sharded north-star workloads + the profile all-reduce (N > 1, or --extras) --------
+    extra = None
+    if (world > 1 or args.extras) and not args.no_extras:
+        plan.destroy()
+        torch.cuda.empty_cache()
+        extra = run_extras(dict(world=world, rank=rank, local=local, dev=dev, dist=dist))
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
@@ -611,10 +626,259 @@ def run_b200(args, w):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(K * info["launches"]),
         }
+        if extra is not None:
+            line["extra"] = extra
         emit(line)
     plan.destroy()
     if world > 1:
         dist.destroy_process_group()
+
+
+
+# ------------------------------------------------------------------------------------------
+# extras at N > 1: the north star's SHARDED workloads and its one collective, beside the headline
+# ------------------------------------------------------------------------------------------
+def _ref_column(x, w, fchan, start, stop):
+    """Reference arithmetic for ONE column, restated here so that the bench never touches
+    oracle/: y = ifft(fft(x) * H)[start:stop], H = exp(-2 pi i phi).astype(c64),
+    phi = K DM f (1/f_ref - 1/f)^2 cycles, f = f_chan + fftfreq(N, dt) (dedispersion.py:19-23,125)."""
+    import scipy.fft
+    n = x.shape[0]
+    f = fchan + np.fft.fftfreq(n, 1.0 / w["sr"])
+    ph = (1.0 / 2.41e-4) * w["dm"] * 1e12 * f * (1.0 / w["fcen"] - 1.0 / f) ** 2
+    h = np.exp(-2j * np.pi * ph).astype(np.complex64)
+    workers = max(1, (os.cpu_count() or 2) // 2)
+    y = scipy.fft.ifft(scipy.fft.fft(x.astype(np.complex128), workers=workers) * h,
+                       workers=workers)
+    return y[start:stop]
+
+
+def _relerr(a, b):
+    a, b = np.asarray(a, dtype=np.complex128 if np.iscomplexobj(b) else np.float64), np.asarray(b)
+    den = float(np.linalg.norm(b))
+    return float(np.linalg.norm(a - b) / (den if den else 1.0))
+
+
+def _sync_all(ctx):
+    import torch
+    if ctx["world"] > 1:
+        ctx["dist"].barrier()
+    torch.cuda.synchronize()
+
+
+def _reduce(ctx, v, op):
+    import torch
+    if ctx["world"] == 1:
+        return v
+    t = torch.tensor([v], dtype=torch.float64, device=ctx["dev"])
+    ctx["dist"].all_reduce(t, op=getattr(ctx["dist"].ReduceOp, op))
+    return float(t.item())
+
+
+def extra_shard(ctx, name, ncols_checked, steps=5):
+    """One GPU's shard of a channel-sharded north-star config (cfg3: int8 -> c64, 128 of 1024
+    channels; cfg5: c64 -> per-pol intensity, 32 of 256 channels), every rank on ITS channel
+    range with the GLOBAL ref_freq and crop; no data-path collective.  Timed with CUDA events,
+    max over ranks; parity of sampled columns against the reference formula on the host."""
+    import torch
+    from pulsarbat_b200 import _lib as L
+    w = WORKLOADS[name]
+    rank, world, local, dev = ctx["rank"], ctx["world"], ctx["local"], ctx["dev"]
+    N, C, P, call = w["N"], w["C"], w["P"], w["Call"]
+    res, ok, err, plan = {}, 1.0, None, None
+    try:
+        shard = rank % (call // C)
+        allf = w["fcen"] + w["sr"] * (np.arange(call) + 0.5 - call / 2)
+        freqs = allf[shard * C:(shard + 1) * C]
+        # global crop from the whole band's edges (dedispersion.py:127-131)
+        import math
+        k = (1.0 / 2.41e-4) * w["dm"]
+        fmin, fmax = (w["fcen"] - call * w["sr"] / 2) / 1e6, (w["fcen"] + call * w["sr"] / 2) / 1e6
+        d_top = k * (1 / fmax ** 2 - 1 / (w["fcen"] / 1e6) ** 2) * w["sr"]
+        d_bot = k * (1 / fmin ** 2 - 1 / (w["fcen"] / 1e6) ** 2) * w["sr"]
+        start, stop = math.ceil(-min(0, d_top, d_bot)), N - math.ceil(max(0, d_top, d_bot))
+        out_kind = L.OUT_C64 if w["stokes"] is None else (L.OUT_STOKES_I if w["stokes"] else
+                                                          L.OUT_INTENSITY)
+        plan = L.DedispPlan(nsamp=N, nchan=C, npol=P, dm=w["dm"], sample_rate_hz=w["sr"],
+                            ref_freq_hz=w["fcen"], chan_freq_hz=freqs, crop=(start, stop),
+                            in_dtype=L.PBK_I8X2 if w["int8"] else L.PBK_C64, out_kind=out_kind,
+                            downsample=w["ds"], device=local)
+        g = torch.Generator(device=dev)
+        g.manual_seed(15 + rank)
+        if w["int8"]:
+            x = torch.empty((N, C, P, 2), device=dev, dtype=torch.int8)
+            for i in range(0, N, 2 ** 20):       # round(clip(N(0, 20^2), +-127)), SURVEY 8d cfg3
+                x[i:i + 2 ** 20] = torch.randn((min(2 ** 20, N - i), C, P, 2), device=dev,
+                                               generator=g).mul_(20).round_().clamp_(-127, 127)
+        else:
+            x = torch.empty((N, C, P, 2), device=dev, dtype=torch.float32)
+            for i in range(0, N, 2 ** 22):
+                x[i:i + 2 ** 22].normal_(generator=g)
+        in_bytes = x.numel() * x.element_size()
+        out_bytes = plan.out_rows * plan.row_elems * plan.elem_bytes
+        out = torch.empty(out_bytes, device=dev, dtype=torch.uint8)
+        st = torch.cuda.current_stream().cuda_stream
+        for _ in range(2):
+            plan.exec_device(x.data_ptr(), out.data_ptr(), None, st)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            plan.exec_device(x.data_ptr(), out.data_ptr(), None, st)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        res.update(ms=ms, plan=plan.describe().split(";"), crop=[start, stop],
+                   in_bytes=int(in_bytes), out_bytes=int(out_bytes),
+                   channels=[int(shard * C), int((shard + 1) * C)], of_channels=call)
+        # parity on sampled columns (a different set on every rank)
+        rng = np.random.default_rng(1000 + rank)
+        errs = []
+        oshape = (plan.out_rows, C) if out_kind == L.OUT_STOKES_I else (plan.out_rows, C, P)
+        odt = torch.complex64 if out_kind == L.OUT_C64 else torch.float32
+        y_dev = out.view(odt).reshape(oshape)
+        for _ in range(ncols_checked):
+            c, pp = int(rng.integers(C)), int(rng.integers(P))
+            col = x[:, c, pp].cpu().numpy()
+            xc = col[:, 0].astype(np.float64) + 1j * col[:, 1].astype(np.float64)
+            want = _ref_column(xc, w, freqs[c], start, stop)
+            got = y_dev[:, c, pp].cpu().numpy()
+            if out_kind != L.OUT_C64:
+                want = want.real ** 2 + want.imag ** 2
+            errs.append(_relerr(got, want))
+        res["parity_relerr_max"] = max(errs) if errs else None
+        ok = 1.0 if all(e <= 1e-5 for e in errs) else 0.0
+        del x, out, y_dev
+    except Exception as exc:                    # keep the collectives below aligned across ranks
+        ok, err = 0.0, f"{type(exc).__name__}: {exc}"
+    finally:
+        if plan is not None:
+            plan.destroy()
+        torch.cuda.empty_cache()
+    ms_max = _reduce(ctx, res.get("ms", 0.0), "MAX")
+    ok_all = _reduce(ctx, ok, "MIN")
+    worst = _reduce(ctx, res.get("parity_relerr_max") or 0.0, "MAX")
+    if "ms" in res:
+        nsamp = N * C * P
+        peak, _ = peaks()
+        res.update(ms=ms_max, value=world * nsamp / (ms_max * 1e-3) / 1e9, unit=UNIT,
+                   whole_op_frac=(res["in_bytes"] + res["out_bytes"]) / (ms_max * 1e-3) / 1e9 / peak,
+                   parity_relerr_max=worst, parity_cols_per_rank=ncols_checked)
+    res["parity_ok"] = bool(ok_all == 1.0)
+    res["workload"] = w["text"]
+    if err:
+        res["error"] = err
+    return res
+
+
+def extra_cfg4(ctx, steps=10):
+    """BASELINE configs[3]: every rank channelizes ITS time slice (2^26 samples x 2 pol, 2^16-point
+    STFT), detects, sums 64 fine channels, folds into 1024 bins x 1024 channels with the CUDA fold
+    kernel, then ONE NCCL all-reduce sums the profiles and the integer counts."""
+    import torch
+    import pulsarbat_b200 as pb
+    from pulsarbat_b200 import sharding
+    rank, world, dev, dist = ctx["rank"], ctx["world"], ctx["dev"], ctx["dist"]
+    n_per_rank, nper, fsum, nbin, npol, sr = 2 ** 26, 2 ** 16, 64, 1024, 2, 400e6
+    coeffs = np.array([0.123, 29.7, 1e-6])
+    seg = n_per_rank // nper
+    res, ok, err = {}, 1.0, None
+    prof = cnt = xd = None
+    try:
+        g = torch.Generator(device=dev)
+        g.manual_seed(16 + rank)
+        x = torch.empty((n_per_rank, 1, npol, 2), device=dev, dtype=torch.float32)
+        x.normal_(generator=g)
+        xd = pb.DeviceArray(torch.view_as_complex(x))
+
+        def local_step():
+            zc = pb.kernels.stft(xd, nper)                               # (seg, 65536, 2)
+            inten = pb.kernels.detect(zc, freq_sum=fsum)                 # (seg, 1024, 2)
+            p, c = pb.kernels.fold(inten, coeffs, sr / nper, nbin, n0=rank * seg)
+            return inten, p, c
+        for _ in range(2):
+            inten, prof, cnt = local_step()
+        torch.cuda.synchronize()
+        # local checks: (i) two segments of the channelizer against numpy's FFT, (ii) the fold
+        # conserves the summed intensity
+        rng = np.random.default_rng(2000 + rank)
+        errs = []
+        for s_i in rng.integers(seg, size=2):
+            s_i, pp = int(s_i), int(rng.integers(npol))
+            blk = xd.tensor[s_i * nper:(s_i + 1) * nper, 0, pp].cpu().numpy().astype(np.complex128)
+            spec = np.fft.fftshift(np.fft.fft(blk)) / nper
+            want = (spec.real ** 2 + spec.imag ** 2).reshape(-1, fsum).sum(1)
+            errs.append(_relerr(inten.tensor[s_i, :, pp].cpu().numpy(), want))
+        tot_in = inten.tensor.double().sum(0).cpu().numpy()
+        tot_pr = prof.tensor.double().sum(0).cpu().numpy()
+        errs.append(_relerr(tot_pr, tot_in))
+        res["local_relerr_max"] = max(errs)
+        if max(errs) > 1e-5:
+            ok = 0.0
+    except Exception as exc:
+        ok, err = 0.0, f"{type(exc).__name__}: {exc}"
+        prof = pb.DeviceArray(torch.zeros((nbin, 1024, npol), device=dev))
+        cnt = pb.DeviceArray(torch.zeros((nbin,), dtype=torch.int64, device=dev))
+    # ---- collective part: the same sequence of all-reduces on every rank, whatever happened above
+    live = ok == 1.0 and err is None
+    _sync_all(ctx)
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    e[0].record()
+    for _ in range(steps):
+        if live:
+            _, prof, cnt = local_step()
+        p2, c2 = sharding.allreduce_profiles(prof, cnt)
+    e[1].record()
+    torch.cuda.synchronize()
+    _sync_all(ctx)
+    e[2].record()
+    for _ in range(steps):                         # the collective alone (4 or 8 MiB + 8 KiB)
+        sharding.allreduce_profiles(prof, cnt)
+    e[3].record()
+    torch.cuda.synchronize()
+    ms_block = _reduce(ctx, e[0].elapsed_time(e[1]) / steps, "MAX")
+    ms_ar = _reduce(ctx, e[2].elapsed_time(e[3]) / steps, "MAX")
+    # exactness of the reduced counts: one fresh fold + reduce, against numpy's polyval binning of
+    # the WHOLE stream (every rank evaluates the same polynomial at absolute sample numbers)
+    if live:
+        _, prof, cnt = local_step()
+    else:
+        prof.tensor.zero_()
+        cnt.tensor.zero_()
+    prof, cnt = sharding.allreduce_profiles(prof, cnt)
+    counts = cnt.tensor.cpu().numpy()
+    t = np.arange(world * seg, dtype=np.float64) / (sr / nper)
+    ph = np.polynomial.polynomial.polyval(t, coeffs)
+    want = np.bincount((np.floor((ph - np.floor(ph)) * nbin).astype(np.int64)) % nbin,
+                       minlength=nbin)
+    counts_exact = bool(np.array_equal(counts, want))
+    ok_all = _reduce(ctx, ok if counts_exact else 0.0, "MIN")
+    res.update(ms_per_block=ms_block, allreduce_ms=ms_ar,
+               value=world * n_per_rank * npol / (ms_block * 1e-3) / 1e9, unit=UNIT,
+               counts_exact=counts_exact, counts_sum=int(counts.sum()),
+               profile_shape=list(prof.shape), allreduce_bytes=int(
+                   prof.tensor.numel() * 4 + cnt.tensor.numel() * 8),
+               collective=f"torch.distributed all_reduce(SUM) over {dist.get_backend()} "
+                          f"({world} ranks)" if world > 1 else "none (1 rank)",
+               parity_ok=bool(ok_all == 1.0),
+               workload="channelize 2^16 -> detect -> x64 channel sum -> fold 1024 bins x 1024 "
+                        "chan x 2 pol, 2^26 samples x 2 pol per rank, profile all-reduce")
+    if err:
+        res["error"] = err
+    del xd
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_extras(ctx):
+    out = {}
+    for key, fn in (("cfg4", lambda: extra_cfg4(ctx)),
+                    ("cfg3_shard", lambda: extra_shard(ctx, "cfg3_shard", 2)),
+                    ("cfg5_shard", lambda: extra_shard(ctx, "cfg5_shard", 1, steps=3))):
+        t0 = time.perf_counter()
+        out[key] = fn()
+        out[key]["wall_s"] = round(time.perf_counter() - t0, 1)
+    return out
 
 
 def time_pinned_results(call, ke, world, nsamp, max_over_ranks):
@@ -646,6 +910,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--extras", action="store_true",
+                    help="run the sharded-workload extras (cfg4 fold + all-reduce, cfg3 / cfg5 "
+                         "shards) also at N = 1; they always run at N > 1")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
