@@ -22,6 +22,7 @@
 
 #include "../../include/pbk.h"
 #include "pbk_fast_launch.h"
+#include "pbk_tma_launch.h"
 #include "pbk_blue.cuh"
 #include "pbk_fft.cuh"
 #include "pbk_hostcopy.h"
@@ -105,6 +106,9 @@ struct Pass {
   FastInfo finfo{};
   long long ntiles = 0;
   size_t ftab_off = 0;  // float2 offset into plan->d_ftab
+  // TMA-pipelined variant of the same tile shape (pbk_tma.cuh); decided by setup_tma
+  bool tma = false;
+  TmaInfo tinfo{};
 };
 
 struct BlueState;   // arbitrary-length (Bluestein) plans, see below
@@ -487,6 +491,98 @@ static int setup_fast(pbk_plan* pl) {
   }
   CUDA_TRY(cudaDeviceGetAttribute(&pl->num_sms, cudaDevAttrMultiProcessorCount, pl->device));
   return PBK_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// TMA-pipelined passes (pbk_tma.cuh)
+// ------------------------------------------------------------------------------------------
+// Which pass kinds use the TMA kernels: $PBK_TMA = 0 (none), 1 / unset (default set), or a list of
+// kinds "tsum,inv,fwd,mid,final" (final = last inverse pass without a time sum).
+static bool tma_kind_enabled(const char* kind) {
+  // default: the passes measured faster with TMA staging on B200 (profiles/r02_tma_passes.log)
+  static const char* dflt = "tsum,inv,fwd,mid,final";
+  const char* e = getenv("PBK_TMA");
+  if (e && !strcmp(e, "0")) return false;
+  const char* list = (!e || !strcmp(e, "1")) ? dflt : e;
+  const size_t n = strlen(kind);
+  for (const char* q = list; (q = strstr(q, kind)) != nullptr; q += n)
+    if ((q == list || q[-1] == ',') && (q[n] == 0 || q[n] == ',')) return true;
+  return false;
+}
+
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                      const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder() {
+  static TensorMapEncodeFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess)
+      f = nullptr;
+    cudaGetLastError();
+    return reinterpret_cast<TensorMapEncodeFn>(f);
+  }();
+  return fn;
+}
+
+// rank-4 float32 view of a pass input: (2 I floats | R inner time offsets | L tile rows | blocks),
+// box = one tile's rows (at most 256 per box) x 2 W floats.  See pbk_tma.cuh: issue().
+static bool tma_encode(const Pass& ps, const void* base, CUtensorMap* tm) {
+  TensorMapEncodeFn enc = tensor_map_encoder();
+  if (!enc) return false;
+  const PassArgs& a = ps.a;
+  const cuuint64_t I = (cuuint64_t)a.I, RI = (cuuint64_t)a.RI, L = 1ull << a.log2L;
+  const cuuint64_t dims[4] = {2 * I, RI / I, L, (cuuint64_t)(a.Q / a.RI)};
+  const cuuint64_t strides[3] = {I * 8, RI * 8, L * RI * 8};
+  const cuuint32_t box[4] = {(cuuint32_t)(4u << ps.tinfo.log2pw), 1, (cuuint32_t)ps.tinfo.box_rows, 1};
+  const cuuint32_t es[4] = {1, 1, 1, 1};
+  static const int promo = [] {
+    const char* e = getenv("PBK_TMA_L2PROMO");
+    return e ? atoi(e) : 0;
+  }();
+  const CUtensorMapL2promotion l2p = promo == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                   : promo == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                   : promo == 64  ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                                  : CU_TENSOR_MAP_L2_PROMOTION_NONE;
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box,
+             es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, l2p,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// decide which fast passes run on the TMA-pipelined kernels (called after setup_fast and after the
+// fused time sum has been chosen)
+static void setup_tma(pbk_plan* pl) {
+  if (!tensor_map_encoder()) return;
+  for (auto& ps : pl->passes) {
+    ps.tma = false;
+    if (ps.family < 0 || ps.signinv || ps.fast_load_transposed) continue;
+    const PassArgs& a = ps.a;
+    TmaInfo ti;
+    if (!tma_info(a.log2L, &ti) || ti.log2pw != ps.finfo.log2pw) continue;
+    const long long W = 2ll << ti.log2pw, L = 1ll << a.log2L;
+    if (a.I % W || W % a.P || a.Q % W) continue;                 // wide tiles only
+    const bool planar_in = ps.in_role == ROLE_SCRATCH && a.load_kind == LOAD_PLANAR;
+    const bool c64_in = ps.in_role == ROLE_USER_IN && a.load_kind == LOAD_C64 && ps.mode == MODE_FWD;
+    if (!planar_in && !c64_in) continue;
+    if (ps.mode == MODE_FWD && (a.final_epi || ps.out_role != ROLE_SCRATCH)) continue;
+    if (ps.mode == MODE_MID && (a.final_epi || a.split)) continue;
+    if (a.fxor || a.kxor || a.scale != 1.0f && ps.mode != MODE_MID) continue;
+    // the input must be the plain (blocks, L, R, I) array the tensor map describes
+    const AddrMap& m = a.min;
+    if (m.a_n != a.I || m.a_row != a.RI || m.a_kp != L * a.RI || m.a_c != a.P || m.a_p != 1 ||
+        !(m.a_o == 0 || m.a_o == (L * a.RI) << a.log2Kprev))
+      continue;
+    if (a.Q / a.RI >= (1ll << 31) || 2ll * a.I >= (1ll << 32)) continue;
+    const bool tsum = ps.mode == MODE_INV && a.tsum_log2 > 0;
+    if (tsum && !ti.tsum_ok) continue;
+    const char* kind = ps.mode == MODE_FWD ? "fwd" : ps.mode == MODE_MID ? "mid"
+                       : tsum ? "tsum" : a.final_epi ? "final" : "inv";
+    if (!tma_kind_enabled(kind)) continue;
+    ps.tma = true;
+    ps.tinfo = ti;
+  }
 }
 
 static int upload_tables(pbk_plan* pl, TableSet& ts) {
@@ -890,6 +986,7 @@ static int dedisp_plan_create_impl(const pbk_dedisp_desc* d, const RampSpec* ram
       pl->scratch2 = nullptr;
     cudaGetLastError();
   }
+  if (pl->l2_chunks == 0) setup_tma(pl);
   const int ds = (d->downsample > 1 && !pl->fused_tsum) ? 1 : 0;
   if (pl->l2_chunks > 0) {
     pl->launches = 2 + 3 * pl->l2_chunks + ds;
@@ -935,7 +1032,11 @@ static int launch_one(pbk_plan* pl, const Pass& ps, const void* d_in, void* d_ou
   p.a.tile0 = tile0;
   const bool aligned = (((uintptr_t)p.a.in | (uintptr_t)p.a.out) & 15) == 0;
   cudaError_t e;
-  if (ps.family >= 0 && aligned) {
+  CUtensorMap tm;
+  if (ps.tma && aligned && tile0 == 0 && tile_end < 0 && tma_encode(ps, p.a.in, &tm)) {
+    e = tma_launch(ps.a.log2L, ps.mode, p.a, tm, pl->d_ftab + ps.ftab_off, ps.ntiles,
+                   pl->num_sms, st);
+  } else if (ps.family >= 0 && aligned) {
     if (ps.fast_load_transposed) p.a.load_kind = LOAD_TRANSP;
     e = fast_launch(ps.family, ps.a.log2L, ps.mode, p.a, pl->d_ftab + ps.ftab_off,
                     tile_end < 0 ? ps.ntiles : tile_end, pl->num_sms, st);
@@ -1158,6 +1259,7 @@ static int build_fft_plan(long long O, long long n, long long C, long long P, bo
                   cudaGetErrorString(e));
     }
   }
+  setup_tma(pl);
   pl->launches = (int)pl->passes.size();
   pl->segments = pl->launches;
   *out = pl;
@@ -1538,8 +1640,8 @@ extern "C" int pbk_plan_describe(const pbk_plan* pl, char* buf, size_t n) {
     const char* sep = i == 0 ? "" : (blocked && (i == 2 || i == 3)) ? "+" : ";";
     if (ps.family >= 0)
       w = snprintf(buf + off, n - off, "%s%s:L=2^%d:%s:W=%d:tiles=%lld:threads=%d%s%s", sep,
-                   mode, ps.a.log2L, "fast-r16",
-                   2 << ps.finfo.log2pw, ps.ntiles, ps.finfo.threads,
+                   mode, ps.a.log2L, ps.tma ? "tma-r16" : "fast-r16",
+                   2 << ps.finfo.log2pw, ps.ntiles, ps.tma ? ps.tinfo.threads : ps.finfo.threads,
                    ps.a.tsum_log2 > 0 ? ":timesum" : "", ps.a.split ? ":evenodd" : "");
     else
       w = snprintf(buf + off, n - off, "%s%s:L=2^%d:%s:W=%d:tiles=%u:threads=%d", sep,

@@ -479,15 +479,22 @@ __device__ __forceinline__ void mid_stage(float4* tile, const float2* tws, int t
   }
 }
 
-template <class C, bool DIT, bool SIGNINV>
-__device__ __forceinline__ void mid_stages(float4* tile, const float2* tws, int tid) {
+// barrier of the threads that share a tile: the whole CTA here, a named barrier of one thread
+// group in the TMA-pipelined kernel (pbk_tma.cuh)
+struct CtaSync {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+
+template <class C, bool DIT, bool SIGNINV, class Sync = CtaSync>
+__device__ __forceinline__ void mid_stages(float4* tile, const float2* tws, int tid,
+                                           Sync sync = Sync()) {
   // forward order 1..NS-2, inverse order NS-2..1
   if constexpr (!DIT) {
-    if constexpr (C::NS > 2) { mid_stage<C, 1, false, SIGNINV>(tile, tws, tid); __syncthreads(); }
-    if constexpr (C::NS > 3) { mid_stage<C, 2, false, SIGNINV>(tile, tws, tid); __syncthreads(); }
+    if constexpr (C::NS > 2) { mid_stage<C, 1, false, SIGNINV>(tile, tws, tid); sync(); }
+    if constexpr (C::NS > 3) { mid_stage<C, 2, false, SIGNINV>(tile, tws, tid); sync(); }
   } else {
-    if constexpr (C::NS > 3) { mid_stage<C, 2, true, false>(tile, tws, tid); __syncthreads(); }
-    if constexpr (C::NS > 2) { mid_stage<C, 1, true, false>(tile, tws, tid); __syncthreads(); }
+    if constexpr (C::NS > 3) { mid_stage<C, 2, true, false>(tile, tws, tid); sync(); }
+    if constexpr (C::NS > 2) { mid_stage<C, 1, true, false>(tile, tws, tid); sync(); }
   }
 }
 

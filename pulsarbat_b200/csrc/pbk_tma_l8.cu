@@ -1,0 +1,16 @@
+// TMA-pipelined pass kernels for tiles of 2^8 points (same tile shape as pbk_fast_l8.cu); one
+// translation unit per tile length so that the units build in parallel.
+#include "pbk_tma_inst.cuh"
+
+namespace pbk {
+
+using Cfg = FastCfg<16, 16, 1, 1, 4, 256, 2>;
+
+void tma_info_l8(TmaInfo* info) { tma_cfg_info<Cfg>(info); }
+cudaError_t tma_launch_l8(int mode, const PassArgs& a, const CUtensorMap& tm,
+                           const float2* d_tables, long long ntiles, int num_sms,
+                           cudaStream_t st) {
+  return tma_cfg_launch<Cfg>(mode, a, tm, d_tables, ntiles, num_sms, st);
+}
+
+}  // namespace pbk
