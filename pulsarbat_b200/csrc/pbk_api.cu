@@ -555,8 +555,12 @@ static bool tma_encode(const Pass& ps, const void* base, CUtensorMap* tm) {
 // fused time sum has been chosen)
 static void setup_tma(pbk_plan* pl) {
   if (!tensor_map_encoder()) return;
+  const char* only = getenv("PBK_TMA_PASS");     // developer knob: TMA on this pass index only
+  int idx = -1;
   for (auto& ps : pl->passes) {
     ps.tma = false;
+    ++idx;
+    if (only && atoi(only) != idx) continue;
     if (ps.family < 0 || ps.signinv || ps.fast_load_transposed) continue;
     const PassArgs& a = ps.a;
     TmaInfo ti;

@@ -10,10 +10,14 @@
 //   * the CTA is NG thread GROUPS of C::NT threads (the unit that owned a CTA in pbk_fast.cuh); a
 //     group works on one tile at a time, synchronises with a named barrier, and keeps the same
 //     per-tile code (stage functions, level twiddle, chirp, epilogues, TSUM accumulators);
-//   * NBUF = NG + NG/2 buffers: NG being computed in place, the rest in flight.  Slot s of the
-//     CTA's tile sequence (group s % NG, that group's (s / NG)-th tile) lives in buffer s % NBUF;
-//     the group that finishes slot s issues the TMA load of slot s + NBUF into the buffer it just
-//     released, so no "empty" barrier is needed and a load has a whole tile time to land;
+//   * NBUF = NG + NG/2 buffers: NG being computed in place, the rest in flight.  The tiles of the
+//     CTA form ONE sequence (round k of group 0, of group 1, ...; groups that have run out of
+//     tiles are skipped); the tile of rank k lives in buffer k % NBUF.  The group that finishes
+//     rank k issues the TMA load of rank k + NBUF into the buffer it just released -- no "empty"
+//     barrier, and a load has a whole tile time to land.  A consumer first waits (a shared-memory
+//     word per buffer) until ITS load has been issued, then on the buffer's mbarrier: without the
+//     first wait a group that runs more than one use of a buffer ahead would see the barrier's
+//     parity of the use before last and walk into a tile another group has not consumed yet;
 //   * a tile is a dense box of the 4-D view (lane, inner time offset, tile row, outer block) of
 //     the pass input -- the tensor map is encoded by the host per pass (pbk_api.cu: tma_encode).
 //
@@ -27,6 +31,7 @@
 // pair-planar input, plain pass-after-pass schedule.
 #pragma once
 #include <cuda.h>
+#include <cstdio>
 
 #include "pbk_fast.cuh"
 
@@ -91,7 +96,8 @@ struct TmaCfg {
   static constexpr size_t OFF_G = OFF_TW + (size_t)C::TW_PAD * sizeof(float2);
   static constexpr size_t OFF_INFO = OFF_G + (size_t)NG * C::RL * sizeof(float4);
   static constexpr size_t OFF_BAR = OFF_INFO + (size_t)NG * 64;
-  static constexpr size_t SMEM_BYTES = OFF_BAR + (size_t)NBUF * 8 + 64;
+  static constexpr size_t OFF_ISSUED = OFF_BAR + (size_t)NBUF * 8;   // rank last issued per buffer
+  static constexpr size_t SMEM_BYTES = OFF_ISSUED + (size_t)NBUF * 8 + 64;
   static_assert(C::PW >= 8, "TMA tiles are row-major: rows of at least 128 B (no XOR swizzle)");
   static_assert(C::NT * NG == CTA_THREADS && NG >= 2, "thread groups tile the CTA");
   static_assert(sizeof(TileInfo) <= 64, "tile record slot");
@@ -152,6 +158,7 @@ tma_pass_kernel(const __grid_constant__ PassArgs p, const __grid_constant__ CUte
   float4* G4 = reinterpret_cast<float4*>(smem_raw + T_::OFF_G) + g * C::RL;
   TileInfo* sinfo = reinterpret_cast<TileInfo*>(smem_raw + T_::OFF_INFO + (size_t)g * 64);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + T_::OFF_BAR);
+  volatile long long* issued = reinterpret_cast<volatile long long*>(smem_raw + T_::OFF_ISSUED);
   const GroupSync<NT> gsync{1 + g};
 
   constexpr int in_bits = 64;
@@ -172,7 +179,6 @@ tma_pass_kernel(const __grid_constant__ PassArgs p, const __grid_constant__ CUte
     return u;
   };
   long long t0[NG], cnt[NG];
-  long long nmax = 0;
 #pragma unroll
   for (int gg = 0; gg < NG; ++gg) {
     const long long vb = (long long)blockIdx.x * NG + gg;
@@ -184,8 +190,17 @@ tma_pass_kernel(const __grid_constant__ PassArgs p, const __grid_constant__ CUte
       t0[gg] = vb;
       cnt[gg] = vb < ntiles ? (ntiles - vb + vgrid - 1) / vgrid : 0;
     }
-    nmax = cnt[gg] > nmax ? cnt[gg] : nmax;
   }
+  // rank of tile j of group gg in the CTA's sequence (rounds of the groups, exhausted ones skipped)
+  auto rank_of = [&](int gg, long long j) -> long long {
+    long long k = 0;
+#pragma unroll
+    for (int h = 0; h < NG; ++h) {
+      const long long upto = j + (h < gg ? 1 : 0);
+      k += cnt[h] < upto ? cnt[h] : upto;
+    }
+    return k;
+  };
   // j-th tile of group gg
   auto tile_of = [&](int gg, long long j) -> long long {
     if (!TSUM) return t0[gg] + j * vgrid;
@@ -194,8 +209,9 @@ tma_pass_kernel(const __grid_constant__ PassArgs p, const __grid_constant__ CUte
     const int cgq = (int)(((long long)blockIdx.x * NG + gg) % tq);
     return nr * ncg + cb * tq + cgq;
   };
-  // one thread: arm the buffer's barrier and start the tile's box(es)
-  auto issue = [&](long long tile, int buf) {
+  // one thread: arm the buffer's barrier, start the tile's box(es), publish the rank
+  auto issue = [&](long long tile, long long rank) {
+    const int buf = (int)(rank % NBUF);
     const long long q0 = tile * C::W;
     const long long o = q0 / p.RI;
     const long long r0 = q0 - o * p.RI;
@@ -207,19 +223,36 @@ tma_pass_kernel(const __grid_constant__ PassArgs p, const __grid_constant__ CUte
       tma_load_4d(reinterpret_cast<unsigned char*>(ring) + (size_t)buf * T_::TILE_BYTES +
                       (size_t)bx * T_::BOX_ROWS * C::PW * sizeof(float4),
                   &tmap, 2 * col0, (int)nrest, bx * T_::BOX_ROWS, (int)o, &full[buf]);
+    __threadfence_block();
+    issued[buf] = rank;
+  };
+  // one thread: issue the tile that comes `ahead` places after tile j of group gg, if there is one
+  auto issue_ahead = [&](int gg, long long j, long long rank, int ahead) {
+    int h = gg;
+    long long jj = j;
+    for (int found = 0;;) {
+      if (++h == NG) { h = 0; ++jj; }
+      bool any = false;                 // is any group still alive in this or a later round?
+#pragma unroll
+      for (int q = 0; q < NG; ++q) any = any || jj < cnt[q];
+      if (!any) return;
+      if (jj < cnt[h] && ++found == ahead) break;
+    }
+    issue(tile_of(h, jj), rank + ahead);
   };
 
   for (int i = threadIdx.x; i < C::TW_TOTAL; i += T_::CTA_THREADS) tws[i] = tables[i];
   if (threadIdx.x == 0) {
-    for (int b = 0; b < NBUF; ++b) mbar_init(&full[b], 1);
+    for (int b = 0; b < NBUF; ++b) {
+      mbar_init(&full[b], 1);
+      issued[b] = -1;
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid == 0 && cnt[g] > 0) fast_tile_info<C, EPI>(p, tile_of(g, 0), *sinfo, in_bits, out_eb);
   __syncthreads();
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int s = 0; s < NBUF; ++s)
-      if (s / NG < cnt[s % NG]) issue(tile_of(s % NG, s / NG), s);
+  if (threadIdx.x == 0) {     // ranks 0 .. NBUF-1: "ahead of the tile before the first"
+    for (int a = 1; a <= NBUF; ++a) issue_ahead(NG - 1, -1, -1, a);
   }
 
   // per-thread part of the output address (wide tiles: the tile sits inside one row of lanes)
@@ -239,10 +272,10 @@ tma_pass_kernel(const __grid_constant__ PassArgs p, const __grid_constant__ CUte
   const long long ts_rowbytes = p.mout.a_n * out_eb;
   if (TSUM) tacc.clear();
 
-  for (long long j = 0; j < nmax; ++j) {
-    const long long s = j * NG + g;
-    const int buf = (int)(s % NBUF);
-    if (j < cnt[g]) {
+  for (long long j = 0; j < cnt[g]; ++j) {
+    const long long rank = rank_of(g, j);
+    const int buf = (int)(rank % NBUF);
+    {
       float4* tile = ring + (size_t)buf * (C::L * C::PW);
       FastTile T;
       unsigned nrest0;
@@ -264,7 +297,7 @@ tma_pass_kernel(const __grid_constant__ PassArgs p, const __grid_constant__ CUte
         T.chan = ti.chan0 + chant;
         T.row_lo = ti.row_lo;
         T.row_cnt = ti.row_cnt;
-      }
+          }
       if (MODE != MODE_MID && tid < RL) {
         const float2 gv = unit_root((unsigned long long)nrest0 * (unsigned)(C::KS * tid), p.log2M);
         G4[tid] = make_float4(gv.x, gv.y, gv.y, gv.x);
@@ -273,7 +306,8 @@ tma_pass_kernel(const __grid_constant__ PassArgs p, const __grid_constant__ CUte
   if (tid == 0 && j + 1 < cnt[g])                                                \
     fast_tile_info<C, EPI>(p, tile_of(g, j + 1), *sinfo, in_bits, out_eb)
 
-      mbar_wait(&full[buf], (uint32_t)((s / NBUF) & 1));   // the tile has landed
+      while (issued[buf] < rank) {}                               // our load has been issued ...
+      mbar_wait(&full[buf], (uint32_t)((rank / NBUF) & 1));       // ... and has landed
 
       if (MODE == MODE_FWD) {
         fwd_first_smem<C, LOADK, false>(tile, tws, tid);
@@ -343,15 +377,10 @@ tma_pass_kernel(const __grid_constant__ PassArgs p, const __grid_constant__ CUte
 #undef PBK_TMA_NEXT_INFO
     }
     // the buffer is released: generic-proxy accesses of this group are ordered before the TMA
-    // write that refills it, then one thread starts the load of slot s + NBUF (same buffer)
+    // write that refills it, then one thread starts the load of rank + NBUF (same buffer)
     fence_proxy_async();
     gsync();
-    if (tid == 0) {
-      const long long s2 = s + NBUF;
-      const int g2 = (int)(s2 % NG);
-      const long long j2 = s2 / NG;
-      if (j2 < cnt[g2]) issue(tile_of(g2, j2), buf);
-    }
+    if (tid == 0) issue_ahead(g, j, rank, NBUF);
   }
   if constexpr (TSUM) {
     if (ts_colbase != nullptr) tsum_flush<C, EPI>(p, tacc, ts_colbase, ts_nrest, tid, ts_rowbytes);
