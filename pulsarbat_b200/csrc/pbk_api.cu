@@ -497,17 +497,33 @@ static int setup_fast(pbk_plan* pl) {
 // ------------------------------------------------------------------------------------------
 // TMA-pipelined passes (pbk_tma.cuh)
 // ------------------------------------------------------------------------------------------
-// Which pass kinds use the TMA kernels: $PBK_TMA = 0 (none), 1 / unset (default set), or a list of
-// kinds "tsum,inv,fwd,mid,final" (final = last inverse pass without a time sum).
-static bool tma_kind_enabled(const char* kind) {
-  // default: the passes measured faster with TMA staging on B200 (profiles/r02_tma_passes.log)
-  static const char* dflt = "tsum,inv,fwd,mid,final";
+// Which passes use the TMA kernels.  $PBK_TMA = 0: none; unset: the (kind, tile length) pairs that
+// measured at least as fast as the LDG kernels on B200 (profiles/r02_tma_vs_ldg_passes.log -- both
+// variants produce bit-identical results, so this is purely a speed choice); 1: every eligible
+// pass; or a list of kinds "tsum,inv,fwd,mid,final" (final = last inverse pass without a time
+// sum) to force those kinds at every length.
+static bool tma_kind_enabled(const char* kind, int log2L) {
   const char* e = getenv("PBK_TMA");
   if (e && !strcmp(e, "0")) return false;
-  const char* list = (!e || !strcmp(e, "1")) ? dflt : e;
-  const size_t n = strlen(kind);
-  for (const char* q = list; (q = strstr(q, kind)) != nullptr; q += n)
-    if ((q == list || q[-1] == ',') && (q[n] == 0 || q[n] == ',')) return true;
+  if (e && !strcmp(e, "1")) return true;
+  if (e) {
+    const size_t n = strlen(kind);
+    for (const char* q = e; (q = strstr(q, kind)) != nullptr; q += n)
+      if ((q == e || q[-1] == ',') && (q[n] == 0 || q[n] == ',')) return true;
+    return false;
+  }
+  // measured on cfg2 / cfg3-shard sized arrays, LDG -> TMA per pass:
+  //   fwd   l6 0.373->0.366  l7 1.488->1.439  l8 1.447->1.416  l9 1.910->1.884 ms
+  //   inv   l7 1.478->1.473  l8 1.431->1.433  (l6 0.363->0.369)
+  //   mid   l8 1.879->1.740  (l6 1.500->1.606, l7 0.410->0.440: the extra trip of the tile
+  //         through shared memory costs more than the hidden load latency saves)
+  //   tsum  l8 0.963->0.963  l9 1.203->1.184  (l7 0.906->1.050)
+  //   final l7 1.498->1.454  l8 1.414->1.412  (l9 1.894->1.914)
+  if (!strcmp(kind, "fwd")) return true;
+  if (!strcmp(kind, "inv")) return log2L >= 7;
+  if (!strcmp(kind, "mid")) return log2L >= 8;
+  if (!strcmp(kind, "tsum")) return log2L >= 8;
+  if (!strcmp(kind, "final")) return log2L == 7 || log2L == 8;
   return false;
 }
 
@@ -583,7 +599,7 @@ static void setup_tma(pbk_plan* pl) {
     if (tsum && !ti.tsum_ok) continue;
     const char* kind = ps.mode == MODE_FWD ? "fwd" : ps.mode == MODE_MID ? "mid"
                        : tsum ? "tsum" : a.final_epi ? "final" : "inv";
-    if (!tma_kind_enabled(kind)) continue;
+    if (!tma_kind_enabled(kind, a.log2L)) continue;
     ps.tma = true;
     ps.tinfo = ti;
   }

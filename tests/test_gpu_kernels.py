@@ -1042,3 +1042,46 @@ def test_single_column_even_odd_split(N, out_kind, crop_odd, monkeypatch):
     ref = plan.exec_host(x, plan.out_array()).copy()
     plan.destroy()
     assert relerr(got, ref) < 3e-6
+
+
+# ------------------------------------------------------------------------------------------
+# TMA-pipelined pass kernels (csrc/pbk_tma.cuh) against the LDG kernels: same arithmetic per
+# element, so voltages and intensities must be bit-identical; the fused time sum adds at most two
+# float contributions per output in either order, so it must be bit-identical too
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n, C, P, out_kind, ds, crop, levels", [
+    (16, 16, 2, 0, 1, None, None),                       # complex64 out, 2 levels, one tile per group
+    (20, 64, 1, 0, 1, (77, 2 ** 20 - 101), None),        # single pol, 3 levels, long tile runs
+    (20, 32, 2, 2, 64, None, None),                      # Stokes I, fused time sum
+    (20, 32, 2, 1, 8, (1000, 2 ** 20 - 3000), "8,6,6"),  # intensity, time sum with a ragged crop
+    (20, 16, 2, 1, 1, None, "7,7,6"),                    # 2^7-point tiles, 4 groups per CTA
+    (21, 8, 2, 0, 1, None, "9,6,6"),                     # 2^9-point tiles, two boxes per tile
+])
+def test_tma_passes_are_bit_identical_to_ldg_passes(monkeypatch, n, C, P, out_kind, ds, crop, levels):
+    import torch
+    L = _lib()
+    N = 2 ** n
+    sr, fcen = 6.25e6, 600e6
+    freqs = fcen + sr * (np.arange(C) + 0.5 - C / 2)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(n * 100 + C)
+    x = torch.randn((N, C, P, 2), device="cuda", dtype=torch.float32, generator=g)
+    if levels:
+        monkeypatch.setenv("PBK_LEVELS", levels)
+    outs, descs = [], []
+    for tma in ("0", "1"):
+        monkeypatch.setenv("PBK_TMA", tma)
+        plan = L.DedispPlan(nsamp=N, nchan=C, npol=P, dm=3.0, sample_rate_hz=sr, ref_freq_hz=fcen,
+                            chan_freq_hz=freqs, crop=crop or (0, N), out_kind=out_kind,
+                            downsample=ds)
+        nout = plan.out_rows * plan.row_elems * plan.elem_bytes
+        out = torch.zeros(nout, device="cuda", dtype=torch.uint8)
+        for _ in range(2):       # twice: the second run starts from warm caches and other timing
+            plan.exec_device(x.data_ptr(), out.data_ptr(), None,
+                             torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        outs.append(out.clone())
+        descs.append(plan.describe())
+        plan.destroy()
+    assert "tma-r16" not in descs[0] and descs[1].count("tma-r16") >= 2, descs
+    assert torch.equal(outs[0], outs[1]), descs[1]
