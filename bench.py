@@ -792,8 +792,9 @@ def extra_cfg4(ctx, steps=10):
         xd = pb.DeviceArray(torch.view_as_complex(x))
 
         def local_step():
-            zc = pb.kernels.stft(xd, nper)                               # (seg, 65536, 2)
-            inten = pb.kernels.detect(zc, freq_sum=fsum)                 # (seg, 1024, 2)
+            # channelize + detect + x64 channel sum as ONE plan (detection in the epilogue of
+            # the last FFT pass): (seg, 1024, 2) float32, the channelized voltages never exist
+            inten = pb.kernels.stft_detect(xd, nper, freq_sum=fsum)
             p, c = pb.kernels.fold(inten, coeffs, sr / nper, nbin, n0=rank * seg)
             return inten, p, c
         for _ in range(2):

@@ -154,6 +154,22 @@ int pbk_fft_plan_create(int64_t outer, int64_t n, int64_t inner, int32_t inverse
  */
 int pbk_stft_plan_create(int64_t nseg, int64_t nperseg, int64_t nchan, int64_t npol,
                          int32_t inverse, int32_t device, pbk_plan** plan);
+/* Channelizer with a DETECTED, frequency-summed output (BASELINE configs[3]: channelize, then
+ * power per fine channel, then sum over `freq_sum` adjacent fine channels -- misc.py:41-52 followed
+ * by core.py:766-774 / :948 and the builder-defined channel sum of pbk_detect_scrunch) as ONE plan:
+ * the detection runs in the epilogue of the last FFT pass, so the channelized voltages never
+ * reach HBM.
+ *   in  (nseg*nperseg, 1, npol) complex64
+ *   out (nseg, nperseg/freq_sum, npol) float32   out_kind INTENSITY, npol 1 or 2
+ *       (nseg, nperseg/freq_sum)       float32   out_kind STOKES_I (npol 2)
+ * with out[s, c', p] = sum_{f < freq_sum} |stft(in)[s, c'*freq_sum + f, p]|^2, fftshift and 1/n
+ * scale of the reference's stft included.  One channel only, a power-of-two segment length that
+ * the plan splits into two levels (2^13 .. 2^24) and a power-of-two freq_sum that divides the first
+ * level; other shapes return PBK_ERR_UNSUPPORTED (use pbk_stft_plan_create + pbk_detect_scrunch).
+ * Executed with pbk_fft_exec_device / pbk_fft_exec_host. */
+int pbk_stft_detect_plan_create(int64_t nseg, int64_t nperseg, int64_t nchan, int64_t npol,
+                                int32_t out_kind, int64_t freq_sum, int32_t device,
+                                pbk_plan** plan);
 /* the channelizer fed with raw baseband (PBK_I8X2 / PBK_U4X2 / PBK_U2X2, decoded in the load of the
  * first pass; forward transform only): what readers/_baseband_readers.py:139-153 + misc.py:17-55
  * do in two steps on the host */

@@ -1193,9 +1193,18 @@ static int blue_fft_plan_create(long long O, long long n, long long C, long long
                                 int device, pbk_plan** out, int in_kind);
 
 // in_kind: load kind of the user's input (LOAD_C64, or raw baseband decoded in the first pass)
+// detected channelizer output (pbk_stft_detect_plan_create): |z|^2 summed over `fsum` adjacent
+// fine channels in the epilogue of the last pass
+struct DetectSpec {
+  int pq = 0;          // floats per output cell: 0 = no detection, 1 = summed over the pair, 2 = per pol
+  long long fsum = 1;
+  bool split = false;  // the pair is the even / odd samples of one single-pol column (n is HALF)
+};
+
 static int build_fft_plan(long long O, long long n, long long C, long long P, bool inverse,
                           ExtMap in, ExtMap outm, float scale, bool shift_out, bool shift_in,
-                          int device, pbk_plan** out, int in_kind = LOAD_C64) {
+                          int device, pbk_plan** out, int in_kind = LOAD_C64,
+                          const DetectSpec* det = nullptr) {
   *out = nullptr;
   const int ln = ilog2_exact(n);
   if (ln < 1) {
@@ -1270,6 +1279,40 @@ static int build_fft_plan(long long O, long long n, long long C, long long P, bo
   int rc = upload_tables(pl, ts);
   if (rc == PBK_OK) rc = setup_fast(pl);
   if (rc != PBK_OK) { pbk_plan_destroy(pl); return rc; }
+  if (det && det->pq) {
+    // The epilogue sums the 2^k first-level bins that share an output cell: it needs the two-level
+    // plan of a long segment (fine channel = kprev + Kprev * row), one channel (I == 2: a lane
+    // pair per bin) on the compile-time-shaped narrow kernel, and F a multiple of the bins a tile
+    // holds that divides Kprev.  Anything else: PBK_ERR_UNSUPPORTED (callers then detect the
+    // channelized voltages with pbk_detect_scrunch).
+    Pass& last = pl->passes.back();
+    const long long Kp = 1ll << l[0];
+    const long long rows_per_tile = last.family >= 0 ? (2ll << last.finfo.log2pw) / I : 0;
+    const int lf = ilog2_exact(det->fsum);
+    const bool ok = m == 2 && I == 2 && !inverse && last.family >= 0 && last.a.final_epi &&
+                    !last.a.out_transpose && last.a.load_kind == LOAD_PLANAR && lf > 0 &&
+                    rows_per_tile > 0 && det->fsum % rows_per_tile == 0 && Kp % det->fsum == 0 &&
+                    last.ntiles % (det->fsum / rows_per_tile) == 0;
+    if (!ok) {
+      pbk_plan_destroy(pl);
+      return fail(PBK_ERR_UNSUPPORTED, "fused detection needs one channel, a two-level segment "
+                  "length and a frequency sum that divides its first level (got n = %lld, "
+                  "nchan*npol = %lld, freq_sum = %lld)", (long long)n, (long long)I,
+                  (long long)det->fsum);
+    }
+    PassArgs& a = last.a;
+    a.fsum_log2 = lf;
+    a.fsum_g_log2 = ilog2_exact(det->fsum / rows_per_tile);
+    a.fsum_row_shift = l[0] - lf;
+    a.fsum_pq = det->pq;
+    a.fsum_split = det->split ? 1 : 0;
+    a.fsum_log2n = ln + 1;                      // split: the full segment is twice this plan's n
+    a.log2Kmul = l[0];
+    a.epi_kind = EPI_INTENSITY;
+    const long long cells = (det->split ? 2 * n : n) / det->fsum;     // output cells per segment
+    a.mout = AddrMap{cells * det->pq, 0, 0, 0, 0, 0, 0};
+    pl->out_bytes = (size_t)O * cells * det->pq * 4;
+  }
   if (m > 1) {
     pl->scratch_bytes = (size_t)O * n * I * 8;
     cudaError_t e = cudaMalloc(&pl->scratch, pl->scratch_bytes);
@@ -1541,6 +1584,42 @@ static int stft_plan_create(int64_t nseg, int64_t nperseg, int64_t nchan, int64_
 extern "C" int pbk_stft_plan_create(int64_t nseg, int64_t nperseg, int64_t nchan, int64_t npol,
                                     int32_t inverse, int32_t device, pbk_plan** plan) {
   return stft_plan_create(nseg, nperseg, nchan, npol, inverse, PBK_C64, device, plan);
+}
+
+extern "C" int pbk_stft_detect_plan_create(int64_t nseg, int64_t nperseg, int64_t nchan,
+                                           int64_t npol, int32_t out_kind, int64_t freq_sum,
+                                           int32_t device, pbk_plan** plan) {
+  if (!plan) return fail(PBK_ERR_INVALID, "plan is NULL");
+  if (nseg <= 0 || nperseg <= 0 || nchan <= 0 || npol <= 0 || freq_sum < 1)
+    return fail(PBK_ERR_INVALID, "shape must be positive");
+  if (out_kind != PBK_OUT_INTENSITY && out_kind != PBK_OUT_STOKES_I)
+    return fail(PBK_ERR_INVALID, "out_kind must be INTENSITY or STOKES_I");
+  if (out_kind == PBK_OUT_STOKES_I && npol != 2)
+    return fail(PBK_ERR_INVALID, "Stokes I needs npol == 2");
+  if (nchan != 1 || (npol != 1 && npol != 2) || nperseg % 2)
+    return fail(PBK_ERR_UNSUPPORTED, "fused detection is built for one channel of one or two "
+                "polarisations and an even segment length");
+  const long long n = nperseg;
+  DetectSpec det;
+  det.fsum = freq_sum;
+  if (npol == 1) {
+    // one single-pol column: its even and odd samples are a lane pair -- the (n/2, 2) view of the
+    // same memory is channelized at half length and the radix-2 recombination X[k] = E + wO,
+    // X[k + n/2] = E - wO happens in registers in front of the detection (the same trick as the
+    // single-column dedispersion plan)
+    det.pq = 1;
+    det.split = true;
+    const long long h = n / 2;
+    ExtMap in{h * 2, 2, 2, 1};
+    ExtMap om{h * 2, 2, h * 2, 1};     // unused: the detected epilogue has its own output map
+    return build_fft_plan(nseg, h, 1, 2, false, in, om, (float)(1.0 / (double)n), false, false,
+                          device, plan, LOAD_C64, &det);
+  }
+  det.pq = out_kind == PBK_OUT_STOKES_I ? 1 : 2;
+  ExtMap in{n * 2, 2, 2, 1};
+  ExtMap om{n * 2, 2, n * 2, 1};
+  return build_fft_plan(nseg, n, 1, 2, false, in, om, (float)(1.0 / (double)n), true, false,
+                        device, plan, LOAD_C64, &det);
 }
 
 extern "C" int pbk_stft_plan_create_raw(int64_t nseg, int64_t nperseg, int64_t nchan,

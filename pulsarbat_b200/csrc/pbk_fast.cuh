@@ -643,7 +643,21 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
   const int ncg = TSUM ? p.I / C::W : 1;
   const int tq = TSUM ? p.tsum_q : 1;
   const int cgq = TSUM ? (int)(blockIdx.x % tq) : 0;
+  // FSUM (FWD-last pass with a detected, frequency-summed output): G = 2^fsum_g_log2 consecutive
+  // tiles are the consecutive groups of first-level bins that land in the same output cells; a CTA
+  // takes whole groups of G tiles (iteration i -> tile (blockIdx + (i / G) grid) G + i % G), keeps
+  // the power sums in registers and stores them once per group: deterministic, no atomics.
+  constexpr bool FSUM = MODE == MODE_FWD && (EPI == EPI_INTENSITY || EPI == EPI_STOKES_I);
+  static_assert(!FSUM || NARROW, "the detected channelizer epilogue is built for few-lane arrays");
+  const int fs_g = FSUM ? p.fsum_g_log2 : 0;
+  auto fs_tile_at = [&](long long i) -> long long {
+    return ((blockIdx.x + (i >> fs_g) * (long long)gridDim.x) << fs_g) + (i & ((1ll << fs_g) - 1));
+  };
+  const long long fs_groups = FSUM ? ntiles >> fs_g : 0;
+  const long long fs_iters = FSUM && blockIdx.x < fs_groups
+      ? ((fs_groups - blockIdx.x + gridDim.x - 1) / gridDim.x) << fs_g : 0;
   auto tile_at = [&](long long i) -> long long {
+    if (FSUM) return fs_tile_at(i);
     if (!TSUM) return i;
     const long long cb = i >> p.log2nmul, nr = i & ((1ll << p.log2nmul) - 1);
     return nr * ncg + cb * tq + cgq;
@@ -663,9 +677,9 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
     if (nr > tail) return u - nr + tail;
     return u;
   };
-  long long t = TSUM ? ts_snap(ts_total * ts_r / ts_nr) : p.tile0 + blockIdx.x;
-  const long long t_end = TSUM ? ts_snap(ts_total * (ts_r + 1) / ts_nr) : ntiles;
-  const long long t_step = TSUM ? 1 : gridDim.x;
+  long long t = TSUM ? ts_snap(ts_total * ts_r / ts_nr) : FSUM ? 0 : p.tile0 + blockIdx.x;
+  const long long t_end = TSUM ? ts_snap(ts_total * (ts_r + 1) / ts_nr) : FSUM ? fs_iters : ntiles;
+  const long long t_step = (TSUM || FSUM) ? 1 : gridDim.x;
   for (int i = tid; i < C::TW_TOTAL; i += C::NT) tws[i] = tables[i];
   if (tid == 0 && t < t_end) fast_tile_info<C, EPI>(p, tile_at(t), *sinfo, in_bits, out_eb);
   __syncthreads();
@@ -695,6 +709,7 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
   constexpr int LTASKS = (C::L / RL) * C::PW;
   constexpr int LITERS = (LTASKS + C::NT - 1) / C::NT;
 
+  float2 fs_acc[FSUM ? ((C::L / C::RL) * C::PW + C::NT - 1) / C::NT * C::RL : 1];
   TsumAcc<C, TSUM ? EPI : EPI_STOKES_I> tacc;
   char* ts_colbase = nullptr;   // TSUM: output columns and inner offset of the running sums
   unsigned ts_nrest = 0;
@@ -804,7 +819,63 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
             v[it][i].im = p_mul(v[it][i].im, sc);
           }
         }
-        if (!p.out_transpose) {
+        if constexpr (FSUM) {
+          // detected output: |z|^2 of every register, summed over the G tiles of a group (registers),
+          // then over the lane rows of the tile (the 16 threads of a half-warp hold 16 adjacent
+          // first-level bins), stored by one lane per row.  p.I == 2: the pair is (pol 0, pol 1)
+          // of the one channel, or the (even, odd) samples of a single-pol column (fsum_split).
+          static_assert(LITERS * RL <= 32, "power sums stay in registers");
+          if ((t & ((1ll << fs_g) - 1)) == 0) {
+#pragma unroll
+            for (int q = 0; q < LITERS * RL; ++q) fs_acc[q] = make_float2(0.f, 0.f);
+          }
+#pragma unroll
+          for (int it = 0; it < LITERS; ++it)
+#pragma unroll
+            for (int i = 0; i < RL; ++i) {
+              c2 z = v[it][i];
+              if (p.fsum_split) {
+                // half-length spectra E (lane 0), O (lane 1) at bin k = klow + Kprev * row
+                const unsigned long long k =
+                    (unsigned long long)T.klow + ((unsigned long long)(klo[it] + i * C::KS) << p.log2Kmul);
+                const float2 w = unit_root(k, p.fsum_log2n);      // exp(-2 pi i k / n), n = 2 * half
+                const float tr = w.x * z.re.y - w.y * z.im.y, ti2 = w.x * z.im.y + w.y * z.re.y;
+                z.re = make_float2(z.re.x + tr, z.re.x - tr);     // X[k], X[k + n/2]
+                z.im = make_float2(z.im.x + ti2, z.im.x - ti2);
+              }
+              fs_acc[it * RL + i] = p_fma(z.re, z.re, p_fma(z.im, z.im, fs_acc[it * RL + i]));
+            }
+          if ((t & ((1ll << fs_g) - 1)) == (1ll << fs_g) - 1) {
+            // lane rows of a tile: pr (nrows == PW when I == 2); reduce over them
+            float* outf = reinterpret_cast<float*>(T.gout);       // this segment's output row
+            const unsigned kp_cell = (unsigned)(T.klow >> p.fsum_log2);   // same for the whole group
+#pragma unroll
+            for (int it = 0; it < LITERS; ++it)
+#pragma unroll
+              for (int i = 0; i < RL; ++i) {
+                float2 a = fs_acc[it * RL + i];
+#pragma unroll
+                for (int sft = 1; sft < C::PW; sft <<= 1) {
+                  a.x += __shfl_xor_sync(0xffffffffu, a.x, sft);
+                  a.y += __shfl_xor_sync(0xffffffffu, a.y, sft);
+                }
+                if ((i & (C::PW - 1)) == pr) {     // spread the stores over the lanes
+                  const unsigned row = (unsigned)(klo[it] + i * C::KS);
+                  if (p.fsum_split) {
+                    // fftshift of the full length: bin k lands at k + n/2, bin k + n/2 at k
+                    const unsigned cell = (row << p.fsum_row_shift) + kp_cell;
+                    const unsigned half = 1u << (p.log2L + p.fsum_row_shift);   // (n/2) / F
+                    outf[cell + half] = a.x;
+                    outf[cell] = a.y;
+                  } else {
+                    const unsigned cell = ((row ^ (unsigned)p.kxor) << p.fsum_row_shift) + kp_cell;
+                    if (p.fsum_pq == 2) *reinterpret_cast<float2*>(outf + 2 * cell) = a;
+                    else outf[cell] = a.x + a.y;
+                  }
+                }
+              }
+          }
+        } else if (!p.out_transpose) {
           // output lanes are adjacent in memory: one natural-order 16-byte store per row
 #pragma unroll
           for (int it = 0; it < LITERS; ++it)

@@ -40,6 +40,8 @@ static cudaError_t cfg_launch_variant(const PassArgs& a, const float2* d_tables,
     grid = (unsigned)(q * std::max<long long>(1, std::min<long long>(resident / q,
                                                                       (ntiles / q) >> (a.tsum_log2 + 1))));
   }
+  if (MODE == MODE_FWD && EPI == EPI_INTENSITY)   // whole groups of 2^fsum_g_log2 tiles per CTA
+    grid = (unsigned)std::min<long long>(std::max<long long>(1, ntiles >> a.fsum_g_log2), resident);
   kern<<<grid, C::NT, smem, st>>>(a, d_tables, ntiles);
   return cudaGetLastError();
 }
@@ -80,6 +82,9 @@ static cudaError_t cfg_launch(int mode, const PassArgs& a, const float2* d_table
         return cfg_launch_mode<MODE_FWD, C, LK_C64, EPI_SCRATCH, false, true>(a, d_tables, ntiles,
                                                                               num_sms, st);
       }
+      if (a.final_epi && a.fsum_log2 > 0)   // channelizer with a detected, frequency-summed output
+        return cfg_launch_variant<MODE_FWD, C, LK_PLANAR, EPI_INTENSITY, false, true>(
+            a, d_tables, ntiles, num_sms, st);
       if (a.final_epi) {   // last pass of a forward FFT / STFT plan: scaled natural-order output
         if (a.load_kind == LOAD_PLANAR)
           return cfg_launch_mode<MODE_FWD, C, LK_PLANAR, EPI_C64>(a, d_tables, ntiles, num_sms, st);

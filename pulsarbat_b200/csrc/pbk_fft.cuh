@@ -101,6 +101,16 @@ struct PassArgs {
   int tsum_log2;      // fast final INV pass: > 0 = sum 2^tsum_log2 consecutive time rows of the
                       // detected output in the epilogue (row R fused; see fast_pass_kernel TSUM)
   int tsum_q;         // ... with groups of tsum_q adjacent CTAs covering adjacent column groups
+  // fast FWD-last pass of a channelizer plan with a DETECTED output (pbk_stft_detect_plan_create):
+  // |z|^2 summed over 2^fsum_log2 adjacent fine channels in the epilogue, so the channelized
+  // voltages never reach HBM; see pbk_fast.cuh (FSUM).
+  int fsum_log2;      // > 0 enables; F = 2^fsum_log2 divides the number of first-level bins Kprev
+  int fsum_g_log2;    // consecutive tiles that land in the same output cells (G = F / rows per tile)
+  int fsum_row_shift; // coarse index = ((row ^ kxor) << fsum_row_shift) + (kprev >> fsum_log2)
+  int fsum_pq;        // floats per output cell (2 = per-pol intensity, 1 = Stokes I / single pol)
+  int fsum_split;     // the lane pair is the even / odd samples of ONE single-pol column of twice the
+                      // length: X[k] = E + wO, X[k+n/2] = E - wO, w = exp(-2 pi i k / 2^fsum_log2n)
+  int fsum_log2n;
   int split;          // fast MID pass, P == 1: the lane pair is the even / odd samples of ONE column
                       // of length 2N (see fast_chirp); N, df and the tables are the half length's
 };

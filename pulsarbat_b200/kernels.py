@@ -19,7 +19,7 @@ from . import _lib as L
 from .device import DeviceArray
 
 __all__ = ["default_device", "dedisperse", "chirp", "detect", "shift_channels", "phase_ramp", "mix", "analytic_decimate", "stokes", "pol_basis",
-           "downsample", "fft", "stft", "istft", "fold", "predict_phase", "clear_plan_cache",
+           "downsample", "fft", "stft", "istft", "stft_detect", "fold", "predict_phase", "clear_plan_cache",
            "pinned_results"]
 
 
@@ -618,6 +618,50 @@ def stft(data, nperseg, device=None, raw=None, raw_shape=None):
     return _run_fft_plan(key, lambda: L.STFTPlan(nseg, n, nchan, npol, inverse=False, device=dev,
                                                  in_dtype=in_dtype),
                          data, (nseg, nchan * n) + shape[2:], raw_np=raw_np)
+
+
+def stft_detect(data, nperseg, freq_sum=1, stokes=False, device=None):
+    """``detect(stft(data, nperseg), freq_sum=freq_sum, stokes=stokes)`` -- channelize, power per
+    fine channel, sum over ``freq_sum`` adjacent fine channels (BASELINE configs[3]).
+
+    One channel of one or two polarisations with a two-level power-of-two segment length runs as
+    ONE plan whose last FFT pass detects in its epilogue (the channelized voltages never reach
+    HBM; a single-pol column is transformed at half length from its even / odd samples); every
+    other shape runs the channelizer and ``detect`` back to back.  Same result either way.
+    """
+    shape = tuple(data.shape)
+    n, F = int(nperseg), int(freq_sum)
+    nseg, nchan = shape[0] // n, shape[1]
+    npol = int(np.prod(shape[2:])) if len(shape) > 2 else 1
+    if stokes and (len(shape) != 3 or shape[2] != 2):
+        raise ValueError("Stokes I needs shape (nsamp, nchan, 2)")
+    if F < 1 or (nchan * n) % F:
+        raise ValueError("freq_sum must divide the number of fine channels")
+    kind = L.OUT_STOKES_I if stokes else L.OUT_INTENSITY
+    out_shape = (nseg, nchan * n // F) + (() if stokes else shape[2:])
+    dev = data.device if _is_dev(data) else (default_device() if device is None else device)
+    fused = (nchan == 1 and npol in (1, 2) and F > 1 and n >= 2 ** 13 and n & (n - 1) == 0 and
+             F & (F - 1) == 0 and os.environ.get("PBK_NO_FUSED_DETECT", "0") in ("", "0") and
+             np.dtype(data.dtype) == np.complex64)
+    if fused:
+        key = ("stft_detect", nseg, n, nchan, npol, int(kind), F, dev)
+        ctx = _use_plan(key, lambda: L.STFTDetectPlan(nseg, n, nchan, npol, kind, F, device=dev))
+        try:
+            with ctx as plan:
+                if _is_dev(data):
+                    x = data.contiguous()
+                    out = DeviceArray.empty(out_shape, np.float32, dev)
+                    with ctx.lock:
+                        plan.exec_device(x.ptr, out.ptr, _stream())
+                    return out
+                x = np.ascontiguousarray(data, dtype=np.complex64)
+                out = _result(out_shape, np.float32)
+                with ctx.lock:
+                    plan.exec_host(x, out)
+                return out
+        except L.PbkUnsupported:
+            pass                  # a shape the fused epilogue does not cover: two steps below
+    return detect(stft(data, n, device=device), stokes=stokes, freq_sum=F, device=device)
 
 
 def istft(data, nperseg, device=None):

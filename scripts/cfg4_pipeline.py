@@ -54,8 +54,11 @@ seg_per_rank = n_per_rank // nper
 
 
 def step(src=None):
-    zc = pb.kernels.stft(xd if src is None else src, nper, **raw_kw)   # (segments, 65536)
-    inten = pb.kernels.detect(zc, freq_sum=fsum)                     # (segments, 1024)
+    if raw is None:   # detection + channel sum in the epilogue of the channelizer's last pass
+        inten = pb.kernels.stft_detect(xd if src is None else src, nper, freq_sum=fsum)
+    else:
+        zc = pb.kernels.stft(xd if src is None else src, nper, **raw_kw)   # (segments, 65536)
+        inten = pb.kernels.detect(zc, freq_sum=fsum)                     # (segments, 1024)
     prof, cnt = pb.kernels.fold(inten, coeffs, sr / nper, nbin, n0=rank * seg_per_rank)
     return sharding.allreduce_profiles(prof, cnt)
 

@@ -496,6 +496,70 @@ def test_cfg4_channelize_detect_fold_pipeline():
     assert relerr(prof, want_p) < 1e-5
 
 
+@pytest.mark.parametrize("log2n, npol, fsum, stokes", [
+    (14, 2, 64, False), (14, 2, 16, True), (16, 2, 64, False), (16, 2, 256, True),
+    (14, 1, 64, False), (16, 1, 64, False), (16, 1, 32, False), (13, 2, 32, False),
+    (17, 2, 64, True), (18, 1, 128, False)])
+def test_fused_channelize_detect_matches_oracle_and_two_step_path(monkeypatch, log2n, npol, fsum,
+                                                                  stokes):
+    """pbk_stft_detect_plan_create (detection in the epilogue of the last channelizer pass; a
+    single-pol column from its even / odd samples) against the oracle's stft -> |.|^2 -> channel
+    sum at BASELINE configs[3]'s segment length 2^16 and around it, host and device arrays, and
+    against the two-step GPU path."""
+    import pulsarbat_b200 as pb
+    from pulsarbat_b200 import kernels
+    rng = np.random.default_rng(log2n * 10 + npol)
+    n, nseg = 2 ** log2n, 6
+    shape = (nseg * n, 1, 2) if npol == 2 else (nseg * n, 1)
+    x = crandn(rng, shape)
+    # a tone in one segment makes a wrong fine-channel order (fftshift, even/odd recombination)
+    # visible: noise alone would hide a permutation of equal-power bins
+    t = np.arange(n)
+    x[2 * n:3 * n, 0, ...] += (8 * np.exp(2j * np.pi * (0.3137 * n // 1) * t / n)).astype(
+        np.complex64).reshape((n,) + (1,) * (x.ndim - 2))
+    ch = orc.stft(x.astype(np.complex128), n)
+    pw = np.abs(ch) ** 2
+    if stokes:
+        want = pw.sum(axis=2).reshape(nseg, n // fsum, fsum).sum(axis=2)
+    else:
+        want = pw.reshape((nseg, n // fsum, fsum) + pw.shape[2:]).sum(axis=2)
+    got = kernels.stft_detect(x, n, freq_sum=fsum, stokes=stokes)
+    assert got.shape == want.shape and got.dtype == np.float32
+    assert relerr(got, want) < 1e-5
+    assert int(np.argmax(got[2].reshape(n // fsum, -1)[:, 0])) == \
+        int(np.argmax(want[2].reshape(n // fsum, -1)[:, 0]))
+    dgot = kernels.stft_detect(pb.DeviceArray.from_numpy(x), n, freq_sum=fsum, stokes=stokes)
+    assert np.array_equal(np.asarray(dgot), got)            # deterministic: no atomics
+    monkeypatch.setenv("PBK_NO_FUSED_DETECT", "1")
+    two = kernels.stft_detect(x, n, freq_sum=fsum, stokes=stokes)
+    assert relerr(got, two) < 2e-6
+    # the fused plan exists for this shape (otherwise the test would compare a path with itself)
+    L = _lib()
+    try:
+        plan = L.STFTDetectPlan(nseg, n, 1, npol, L.OUT_STOKES_I if stokes else L.OUT_INTENSITY,
+                                fsum)
+    except L.PbkUnsupported:
+        assert log2n != 16, "BASELINE configs[3]'s segment length must take the fused plan"
+        pytest.skip("no fused plan for this level split; the two-step path was checked above")
+    assert plan.describe().count("fast-r16") + plan.describe().count("tma-r16") == 2
+    plan.destroy()
+
+
+def test_fused_channelize_detect_falls_back_for_other_shapes():
+    from pulsarbat_b200 import kernels
+    L = _lib()
+    rng = np.random.default_rng(4)
+    x = crandn(rng, (4 * 256, 3, 2))                         # three channels, short segments
+    got = kernels.stft_detect(x, 256, freq_sum=4)
+    ch = orc.stft(x.astype(np.complex128), 256)
+    want = (np.abs(ch) ** 2).reshape(4, 192, 4, 2).sum(axis=2)
+    assert relerr(got, want) < 1e-5
+    with pytest.raises(L.PbkUnsupported):
+        L.STFTDetectPlan(4, 256, 3, 2, L.OUT_INTENSITY, 4)
+    with pytest.raises(L.PbkUnsupported):
+        L.STFTDetectPlan(4, 2 ** 14, 1, 2, L.OUT_INTENSITY, 3)      # not a power of two
+
+
 # ------------------------------------------------------------------------------ incoherent
 @pytest.mark.parametrize("dm", [50.0, 200.0])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex64])
