@@ -791,14 +791,22 @@ def extra_cfg4(ctx, steps=10):
         x.normal_(generator=g)
         xd = pb.DeviceArray(torch.view_as_complex(x))
 
-        def local_step():
-            # channelize + detect + x64 channel sum as ONE plan (detection in the epilogue of
-            # the last FFT pass): (seg, 1024, 2) float32, the channelized voltages never exist
-            inten = pb.kernels.stft_detect(xd, nper, freq_sum=fsum)
+        def two_step():
+            # channelize + detect + x64 channel sum as one plan (detection in the epilogue of the
+            # last FFT pass), then the fold kernel: keeps the detected spectra for the checks below
+            inten = pb.kernels.stft_detect(xd, nper, freq_sum=fsum)          # (seg, 1024, 2)
             p, c = pb.kernels.fold(inten, coeffs, sr / nper, nbin, n0=rank * seg)
             return inten, p, c
+
+        def local_step():
+            # the timed path: ONE library call (bins + counts, first FFT pass, last FFT pass adding
+            # its power sums into the profile); neither voltages nor spectra reach HBM
+            p, c = pb.kernels.stft_fold(xd, nper, coeffs, sr / nper, nbin, freq_sum=fsum,
+                                        n0=rank * seg)
+            return None, p, c
         for _ in range(2):
-            inten, prof, cnt = local_step()
+            _, prof, cnt = local_step()
+        inten, prof2, cnt2 = two_step()
         torch.cuda.synchronize()
         # local checks: (i) two segments of the channelizer against numpy's FFT, (ii) the fold
         # conserves the summed intensity
@@ -812,7 +820,10 @@ def extra_cfg4(ctx, steps=10):
             errs.append(_relerr(inten.tensor[s_i, :, pp].cpu().numpy(), want))
         tot_in = inten.tensor.double().sum(0).cpu().numpy()
         tot_pr = prof.tensor.double().sum(0).cpu().numpy()
-        errs.append(_relerr(tot_pr, tot_in))
+        errs.append(_relerr(tot_pr, tot_in))                  # the fold conserves the power
+        errs.append(_relerr(prof.tensor.cpu().numpy(), prof2.tensor.cpu().numpy()))  # fused = two-step
+        if not torch.equal(cnt.tensor, cnt2.tensor):
+            errs.append(1.0)
         res["local_relerr_max"] = max(errs)
         if max(errs) > 1e-5:
             ok = 0.0

@@ -170,6 +170,14 @@ int pbk_stft_plan_create(int64_t nseg, int64_t nperseg, int64_t nchan, int64_t n
 int pbk_stft_detect_plan_create(int64_t nseg, int64_t nperseg, int64_t nchan, int64_t npol,
                                 int32_t out_kind, int64_t freq_sum, int32_t device,
                                 pbk_plan** plan);
+/* ... and the fold behind it (row F) in the same launches: the power sums of segment s are ADDED
+ * to profile[bin(s), :, :] (float32 (nbin, nperseg/freq_sum[, npol]), caller-zeroed or carrying
+ * earlier blocks) and counts[bin(s)] += 1 (int64 (nbin,)), bin(s) from the phase polynomial at
+ * t = (n0 + s) / sample_rate_hz exactly as pbk_fold (sample_rate_hz is the SEGMENT rate).  `plan`
+ * comes from pbk_stft_detect_plan_create; device pointers, enqueued on `stream`. */
+int pbk_stft_fold_exec_device(pbk_plan* plan, const void* d_in, void* d_profile, void* d_counts,
+                              const double* coeffs, int32_t ncoef, double sample_rate_hz,
+                              int64_t n0, int32_t nbin, void* stream);
 /* the channelizer fed with raw baseband (PBK_I8X2 / PBK_U4X2 / PBK_U2X2, decoded in the load of the
  * first pass; forward transform only): what readers/_baseband_readers.py:139-153 + misc.py:17-55
  * do in two steps on the host */

@@ -18,7 +18,7 @@ EXPORTS = [
     "pbk_device_pci_bus_id", "pbk_device_mem_info", "pbk_phase_predict",
     "pbk_dedisp_plan_create", "pbk_dedisp_out_shape", "pbk_dedisp_exec_host",
     "pbk_dedisp_exec_device", "pbk_fft_plan_create", "pbk_stft_plan_create", "pbk_stft_plan_create_raw",
-    "pbk_stft_detect_plan_create",
+    "pbk_stft_detect_plan_create", "pbk_stft_fold_exec_device",
     "pbk_fft_exec_host", "pbk_fft_exec_device", "pbk_detect", "pbk_detect_scrunch", "pbk_shift_channels", "pbk_downsample", "pbk_fold",
     "pbk_stokes", "pbk_pol_basis", "pbk_chirp", "pbk_ramp_plan_create", "pbk_mix", "pbk_decimate2",
     "pbk_plan_destroy", "pbk_plan_info", "pbk_plan_describe", "pbk_plan_profile",
@@ -88,6 +88,8 @@ def lib():
         L.pbk_stft_plan_create_raw.argtypes = [i64, i64, i64, i64, i32, i32, ctypes.POINTER(vp)]
         L.pbk_stft_detect_plan_create.argtypes = [i64, i64, i64, i64, i32, i64, i32,
                                                   ctypes.POINTER(vp)]
+        L.pbk_stft_fold_exec_device.argtypes = [vp, vp, vp, vp, ctypes.POINTER(dbl), i32, dbl, i64,
+                                                i32, vp]
         L.pbk_fft_exec_host.argtypes = [vp, vp, vp]
         L.pbk_fft_exec_device.argtypes = [vp, vp, vp, vp]
         L.pbk_detect.argtypes = [vp, vp, i64, i64, i64, i32, i64, i32, i32, vp]
@@ -318,3 +320,10 @@ class STFTDetectPlan(FFTPlan):
         check(lib().pbk_stft_detect_plan_create(nseg, nperseg, nchan, npol, int(out_kind),
                                                 int(freq_sum), device, ctypes.byref(h)))
         Plan.__init__(self, h)
+
+    def fold_device(self, d_in, d_profile, d_counts, coeffs, sample_rate_hz, n0, nbin, stream=0):
+        c = np.ascontiguousarray(coeffs, dtype=np.float64)
+        check(lib().pbk_stft_fold_exec_device(
+            self.handle, ptr(d_in), ptr(d_profile), ptr(d_counts),
+            c.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(c), float(sample_rate_hz),
+            int(n0), int(nbin), ctypes.c_void_p(stream)))

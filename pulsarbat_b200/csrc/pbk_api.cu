@@ -136,6 +136,11 @@ struct pbk_plan {
   void* d_tmpf = nullptr;       // pre-downsample float buffer
   size_t tmpf_bytes = 0;
   bool fused_tsum = false;      // the time sum runs in the epilogue of the last pass (no d_tmpf)
+  // channelizer plans with a detected output (pbk_stft_detect_plan_create)
+  long long det_nseg = 0, det_cells = 0;
+  int det_pq = 0;
+  int* d_segbins = nullptr;          // phase bin per segment of the current folded execution
+  const int* exec_segbins = nullptr; // non-null while pbk_stft_fold_exec_device runs the passes
   bool split_column = false;    // single column run as its even / odd samples (see plan creation)
   bool split_ragged = false;    // ... with an odd crop edge: passes write d_tmpf, then a D2D copy
   size_t split_skip = 0;
@@ -1050,6 +1055,7 @@ static int launch_one(pbk_plan* pl, const Pass& ps, const void* d_in, void* d_ou
   }
   p.a.chirp_arr = reinterpret_cast<const float2*>(d_chirp);
   p.a.tile0 = tile0;
+  if (p.a.fsum_log2 > 0) p.a.fsum_bins = pl->exec_segbins;
   const bool aligned = (((uintptr_t)p.a.in | (uintptr_t)p.a.out) & 15) == 0;
   cudaError_t e;
   CUtensorMap tm;
@@ -1311,7 +1317,11 @@ static int build_fft_plan(long long O, long long n, long long C, long long P, bo
     a.epi_kind = EPI_INTENSITY;
     const long long cells = (det->split ? 2 * n : n) / det->fsum;     // output cells per segment
     a.mout = AddrMap{cells * det->pq, 0, 0, 0, 0, 0, 0};
+    a.fsum_cells = cells;
     pl->out_bytes = (size_t)O * cells * det->pq * 4;
+    pl->det_nseg = O;
+    pl->det_cells = cells;
+    pl->det_pq = det->pq;
   }
   if (m > 1) {
     pl->scratch_bytes = (size_t)O * n * I * 8;
@@ -1638,6 +1648,44 @@ extern "C" int pbk_fft_exec_device(pbk_plan* pl, const void* d_in, void* d_out, 
   return run_passes(pl, d_in, d_out, nullptr, reinterpret_cast<cudaStream_t>(stream));
 }
 
+extern "C" int pbk_stft_fold_exec_device(pbk_plan* pl, const void* d_in, void* d_profile,
+                                         void* d_counts, const double* coeffs, int32_t ncoef,
+                                         double sample_rate_hz, int64_t n0, int32_t nbin,
+                                         void* stream) {
+  if (!pl || pl->kind != PLAN_FFT || pl->det_pq == 0)
+    return fail(PBK_ERR_INVALID, "not a detected channelizer plan");
+  if (!d_in || !d_profile || !d_counts || !coeffs) return fail(PBK_ERR_INVALID, "NULL pointer");
+  if (nbin <= 0) return fail(PBK_ERR_INVALID, "nbin must be positive");
+  if (ncoef < 1 || ncoef > kFoldMaxCoef)
+    return fail(PBK_ERR_INVALID, "ncoef must be in [1, %d]", kFoldMaxCoef);
+  if (!(sample_rate_hz > 0) || !std::isfinite(sample_rate_hz))
+    return fail(PBK_ERR_INVALID, "sample_rate_hz must be finite and > 0");
+  for (int i = 0; i < ncoef; ++i)
+    if (!std::isfinite(coeffs[i]))
+      return fail(PBK_ERR_INVALID, "phase coefficient %d is not finite", i);
+  CUDA_TRY(cudaSetDevice(pl->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!pl->d_segbins) CUDA_TRY(cudaMalloc(&pl->d_segbins, (size_t)pl->det_nseg * sizeof(int)));
+  FoldArgs fa;
+  memset(&fa, 0, sizeof(fa));
+  for (int i = 0; i < ncoef; ++i) fa.coef[i] = coeffs[i];
+  fa.ncoef = ncoef;
+  fa.sample_rate = sample_rate_hz;
+  fa.n0 = n0;
+  fa.nbin = nbin;
+  fa.nsamp = pl->det_nseg;
+  fa.row_elems = pl->det_cells * pl->det_pq;
+  fa.counts = reinterpret_cast<unsigned long long*>(d_counts);
+  const unsigned blocks = (unsigned)std::min<long long>((pl->det_nseg + 255) / 256, 148 * 4);
+  fold_bins_kernel<<<blocks, 256, 0, st>>>(fa, pl->d_segbins);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "fold bins launch: %s", cudaGetErrorString(e));
+  pl->exec_segbins = pl->d_segbins;
+  const int rc = run_passes(pl, d_in, d_profile, nullptr, st);
+  pl->exec_segbins = nullptr;
+  return rc;
+}
+
 extern "C" int pbk_fft_exec_host(pbk_plan* pl, const void* in, void* out) {
   if (!pl || pl->kind != PLAN_FFT) return fail(PBK_ERR_INVALID, "not an FFT plan");
   if (!in || !out) return fail(PBK_ERR_INVALID, "NULL data pointer");
@@ -1703,6 +1751,7 @@ extern "C" void pbk_plan_destroy(pbk_plan* pl) {
   cudaFree(pl->d_ramp_shift);
   cudaFree(pl->d_ramp_zero);
   cudaFree(pl->d_tmpf);
+  cudaFree(pl->d_segbins);
   cudaFree(pl->h_din);
   cudaFree(pl->h_dout);
   cudaFree(pl->h_dchirp);

@@ -848,6 +848,12 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
           if ((t & ((1ll << fs_g) - 1)) == (1ll << fs_g) - 1) {
             // lane rows of a tile: pr (nrows == PW when I == 2); reduce over them
             float* outf = reinterpret_cast<float*>(T.gout);       // this segment's output row
+            const bool folded = p.fsum_bins != nullptr;
+            if (folded) {   // row of the segment's phase bin in the profile; sums are added to it
+              const long long rowf = p.fsum_cells * p.fsum_pq;
+              const long long seg = (outf - reinterpret_cast<float*>(p.out)) / rowf;
+              outf = reinterpret_cast<float*>(p.out) + (long long)p.fsum_bins[seg] * rowf;
+            }
             const unsigned kp_cell = (unsigned)(T.klow >> p.fsum_log2);   // same for the whole group
 #pragma unroll
             for (int it = 0; it < LITERS; ++it)
@@ -865,12 +871,27 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
                     // fftshift of the full length: bin k lands at k + n/2, bin k + n/2 at k
                     const unsigned cell = (row << p.fsum_row_shift) + kp_cell;
                     const unsigned half = 1u << (p.log2L + p.fsum_row_shift);   // (n/2) / F
-                    outf[cell + half] = a.x;
-                    outf[cell] = a.y;
+                    if (folded) {
+                      atomicAdd(outf + cell + half, a.x);
+                      atomicAdd(outf + cell, a.y);
+                    } else {
+                      outf[cell + half] = a.x;
+                      outf[cell] = a.y;
+                    }
                   } else {
                     const unsigned cell = ((row ^ (unsigned)p.kxor) << p.fsum_row_shift) + kp_cell;
-                    if (p.fsum_pq == 2) *reinterpret_cast<float2*>(outf + 2 * cell) = a;
-                    else outf[cell] = a.x + a.y;
+                    if (folded) {
+                      if (p.fsum_pq == 2) {
+                        atomicAdd(outf + 2 * cell, a.x);
+                        atomicAdd(outf + 2 * cell + 1, a.y);
+                      } else {
+                        atomicAdd(outf + cell, a.x + a.y);
+                      }
+                    } else if (p.fsum_pq == 2) {
+                      *reinterpret_cast<float2*>(outf + 2 * cell) = a;
+                    } else {
+                      outf[cell] = a.x + a.y;
+                    }
                   }
                 }
               }

@@ -111,6 +111,10 @@ struct PassArgs {
   int fsum_split;     // the lane pair is the even / odd samples of ONE single-pol column of twice the
                       // length: X[k] = E + wO, X[k+n/2] = E - wO, w = exp(-2 pi i k / 2^fsum_log2n)
   int fsum_log2n;
+  const int* fsum_bins;   // fold fused behind the detection (pbk_stft_fold_exec_device): phase bin of
+                          // every segment; the sums are ADDED to out[bin, cell, p] instead of stored
+                          // at out[segment, cell, p]
+  long long fsum_cells;   // output cells per segment (row length of `out` in cells)
   int split;          // fast MID pass, P == 1: the lane pair is the even / odd samples of ONE column
                       // of length 2N (see fast_chirp); N, df and the tables are the half length's
 };

@@ -381,6 +381,17 @@ static inline cudaError_t launch_phase_predict(const PredictArgs& a, cudaStream_
   return cudaGetLastError();
 }
 
+// phase bin of every sample (and the counts) without touching any data: the fold behind a fused
+// channelizer epilogue (pbk_stft_fold_exec_device) adds its sums to the bin's row itself
+__global__ void __launch_bounds__(256) fold_bins_kernel(const FoldArgs a, int* __restrict__ bins) {
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < a.nsamp;
+       n += (long long)gridDim.x * blockDim.x) {
+    const int b = fold_bin(a, n);
+    bins[n] = b;
+    atomicAdd(a.counts + b, 1ull);
+  }
+}
+
 // ---- wide rows (row_elems >= 32): one CTA owns SPAN consecutive samples x up to 256 elements.
 // Bins of a chunk of 64 samples are computed once into shared memory; every thread walks its
 // element down the chunk (coalesced row segments, 8 loads in flight) and keeps the running sum of

@@ -19,7 +19,7 @@ from . import _lib as L
 from .device import DeviceArray
 
 __all__ = ["default_device", "dedisperse", "chirp", "detect", "shift_channels", "phase_ramp", "mix", "analytic_decimate", "stokes", "pol_basis",
-           "downsample", "fft", "stft", "istft", "stft_detect", "fold", "predict_phase", "clear_plan_cache",
+           "downsample", "fft", "stft", "istft", "stft_detect", "stft_fold", "fold", "predict_phase", "clear_plan_cache",
            "pinned_results"]
 
 
@@ -662,6 +662,58 @@ def stft_detect(data, nperseg, freq_sum=1, stokes=False, device=None):
         except L.PbkUnsupported:
             pass                  # a shape the fused epilogue does not cover: two steps below
     return detect(stft(data, n, device=device), stokes=stokes, freq_sum=F, device=device)
+
+
+def stft_fold(data, nperseg, coeffs, sample_rate_hz, nbin, *, freq_sum=1, stokes=False, n0=0,
+              profile=None, counts=None):
+    """``fold(stft_detect(data, nperseg, freq_sum, stokes), coeffs, sample_rate_hz, nbin, n0)`` for
+    a device-resident block: channelize, detect, sum fine channels and fold the segments into
+    phase bins (BASELINE configs[3]).  ``sample_rate_hz`` is the SEGMENT rate (input rate /
+    nperseg) and ``n0`` the index of the block's first segment in the stream, as in :func:`fold`.
+
+    Shapes the fused plan covers (see :func:`stft_detect`) run as ONE library call of three
+    launches -- bins and counts, first FFT pass, last FFT pass adding its power sums straight into
+    the profile -- so neither the channelized voltages nor the detected spectra reach HBM; other
+    shapes run ``stft_detect`` and ``fold``.  ``profile`` / ``counts`` are accumulated into when
+    given (DeviceArrays).  Returns (profile, counts)."""
+    if not _is_dev(data):
+        raise TypeError("stft_fold takes a DeviceArray (host blocks: stft_detect + fold)")
+    import torch
+    shape = tuple(data.shape)
+    n, F = int(nperseg), int(freq_sum)
+    nseg, nchan = shape[0] // n, shape[1]
+    npol = int(np.prod(shape[2:])) if len(shape) > 2 else 1
+    dev = data.device
+    cells_shape = (nchan * n // F,) + (() if stokes else shape[2:])
+    c = np.ascontiguousarray(coeffs, dtype=np.float64)
+    if c.ndim != 1 or not np.all(np.isfinite(c)):
+        raise ValueError("coeffs must be a 1-D array of finite numbers")
+    if profile is None:
+        profile = DeviceArray(torch.zeros((int(nbin),) + cells_shape, dtype=torch.float32,
+                                          device=f"cuda:{dev}"))
+    if counts is None:
+        counts = DeviceArray(torch.zeros((int(nbin),), dtype=torch.int64, device=f"cuda:{dev}"))
+    if (tuple(profile.shape) != (int(nbin),) + cells_shape or profile.dtype != np.float32 or
+            tuple(counts.shape) != (int(nbin),) or counts.dtype != np.int64):
+        raise ValueError("profile must be float32 (nbin, cells[, npol]) and counts int64 (nbin,)")
+    fused = (nchan == 1 and npol in (1, 2) and F > 1 and n >= 2 ** 13 and n & (n - 1) == 0 and
+             F & (F - 1) == 0 and os.environ.get("PBK_NO_FUSED_DETECT", "0") in ("", "0") and
+             np.dtype(data.dtype) == np.complex64 and shape[0] == nseg * n)
+    if fused:
+        kind = L.OUT_STOKES_I if stokes else L.OUT_INTENSITY
+        key = ("stft_detect", nseg, n, nchan, npol, int(kind), F, dev)
+        ctx = _use_plan(key, lambda: L.STFTDetectPlan(nseg, n, nchan, npol, kind, F, device=dev))
+        try:
+            with ctx as plan:
+                x, prof, cnt = data.contiguous(), profile.contiguous(), counts.contiguous()
+                with ctx.lock:
+                    plan.fold_device(x.ptr, prof.ptr, cnt.ptr, c, sample_rate_hz, n0, nbin,
+                                     _stream())
+                return prof, cnt
+        except L.PbkUnsupported:
+            pass
+    inten = stft_detect(data, n, freq_sum=F, stokes=stokes)
+    return fold(inten, c, sample_rate_hz, nbin, n0=n0, profile=profile, counts=counts)
 
 
 def istft(data, nperseg, device=None):

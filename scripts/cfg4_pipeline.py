@@ -54,12 +54,15 @@ seg_per_rank = n_per_rank // nper
 
 
 def step(src=None):
-    if raw is None:   # detection + channel sum in the epilogue of the channelizer's last pass
-        inten = pb.kernels.stft_detect(xd if src is None else src, nper, freq_sum=fsum)
+    if raw is None:
+        # ONE library call: bins + counts, first FFT pass, last FFT pass whose epilogue detects,
+        # sums 64 fine channels and adds the result to the profile row of the segment's phase bin
+        prof, cnt = pb.kernels.stft_fold(xd if src is None else src, nper, coeffs, sr / nper, nbin,
+                                         freq_sum=fsum, n0=rank * seg_per_rank)
     else:
         zc = pb.kernels.stft(xd if src is None else src, nper, **raw_kw)   # (segments, 65536)
         inten = pb.kernels.detect(zc, freq_sum=fsum)                     # (segments, 1024)
-    prof, cnt = pb.kernels.fold(inten, coeffs, sr / nper, nbin, n0=rank * seg_per_rank)
+        prof, cnt = pb.kernels.fold(inten, coeffs, sr / nper, nbin, n0=rank * seg_per_rank)
     return sharding.allreduce_profiles(prof, cnt)
 
 

@@ -541,8 +541,36 @@ def test_fused_channelize_detect_matches_oracle_and_two_step_path(monkeypatch, l
     except L.PbkUnsupported:
         assert log2n != 16, "BASELINE configs[3]'s segment length must take the fused plan"
         pytest.skip("no fused plan for this level split; the two-step path was checked above")
-    assert plan.describe().count("fast-r16") + plan.describe().count("tma-r16") == 2
+    assert plan.describe().count("fast-r16") >= 1, plan.describe()   # the detecting last pass
     plan.destroy()
+
+
+@pytest.mark.parametrize("log2n, npol, fsum, stokes", [(16, 2, 64, False), (14, 2, 64, True),
+                                                       (16, 1, 64, False), (10, 2, 16, False)])
+def test_fused_channelize_detect_fold_matches_oracle(log2n, npol, fsum, stokes):
+    """kernels.stft_fold (bins + counts, first FFT pass, last FFT pass adding its power sums into
+    the profile row of the segment's phase bin) against oracle stft -> |.|^2 -> channel sum -> fold,
+    accumulated over two blocks of one stream: counts bit-exact, profile <= 1e-5."""
+    import pulsarbat_b200 as pb
+    from pulsarbat_b200 import kernels
+    rng = np.random.default_rng(77 + log2n + npol)
+    n, nseg, nbin = 2 ** log2n, 24, 16
+    shape = (2 * nseg * n, 1, 2) if npol == 2 else (2 * nseg * n, 1)
+    x = crandn(rng, shape)
+    coeffs, rate = [0.123, 29.7e3 if log2n > 12 else 2.97e5, 1e-3], 400e6 / n
+    prof = cnt = None
+    for blk in range(2):
+        xb = pb.DeviceArray.from_numpy(x[blk * nseg * n:(blk + 1) * nseg * n])
+        prof, cnt = kernels.stft_fold(xb, n, coeffs, rate, nbin, freq_sum=fsum, stokes=stokes,
+                                      n0=blk * nseg, profile=prof, counts=cnt)
+    pw = np.abs(orc.stft(x.astype(np.complex128), n)) ** 2
+    if stokes:
+        pw = pw.sum(axis=2)
+    inten = pw.reshape((2 * nseg, n // fsum, fsum) + pw.shape[2:]).sum(axis=2)
+    want_p, want_c = orc.fold(inten, coeffs, rate, nbin)
+    assert np.array_equal(np.asarray(cnt), want_c) and len(np.unique(want_c)) > 1
+    assert np.asarray(prof).shape == want_p.shape
+    assert relerr(np.asarray(prof), want_p) < 1e-5
 
 
 def test_fused_channelize_detect_falls_back_for_other_shapes():
