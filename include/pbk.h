@@ -188,6 +188,31 @@ int pbk_stft_plan_create_raw(int64_t nseg, int64_t nperseg, int64_t nchan, int64
 int pbk_fft_exec_host(pbk_plan* plan, const void* in, void* out);
 int pbk_fft_exec_device(pbk_plan* plan, const void* d_in, void* d_out, void* stream);
 
+/* ---- complex128 -----------------------------------------------------------------------------
+ * The reference keeps complex128 through its transforms (scipy preserves the dtype:
+ * dedispersion.py:125, fft.py:34, misc.py:47,87; core.py:766-774 returns float64 power), and its
+ * own test of +-DM reversibility asserts atol 3e-8 (tests/test_dedispersion.py:73-98).  These entry
+ * points compute in FP64 (Stockham radix-4 passes, csrc/pbk_f64.cuh) for power-of-two lengths and
+ * return PBK_ERR_UNSUPPORTED for any other length: complex128 is never narrowed to complex64.
+ * Plan-less; host pointers (synchronous) or device pointers (`on_device`, enqueued on `stream`).
+ *   pbk_dedisp_c128: in (nsamp, nchan, npol) complex128 -> out rows [crop_start, crop_stop) as
+ *                    complex128 (C64 kind), float64 per-pol power or float64 Stokes I; the chirp
+ *                    is generated in FP64 and rounded to complex64 exactly as dedispersion.py:23
+ *                    does, or taken from `chirp` ((nsamp, nchan) complex64) when non-NULL
+ *   pbk_fft_c128:    (outer, n, inner) complex128, axis 1, scipy "backward" normalisation
+ *   pbk_stft_c128:   stft / istft of (nseg*nperseg, nchan, npol) complex128
+ *   pbk_detect_c128: float64 |z|^2 per element, or Stokes I over pol pairs */
+int pbk_dedisp_c128(const void* in, void* out, int64_t nsamp, int64_t nchan, int64_t npol,
+                    int32_t out_kind, double dm, double sample_rate_hz, double ref_freq_hz,
+                    const double* chan_freq_hz, int64_t crop_start, int64_t crop_stop,
+                    const void* chirp, int32_t on_device, int32_t device, void* stream);
+int pbk_fft_c128(const void* in, void* out, int64_t outer, int64_t n, int64_t inner,
+                 int32_t inverse, int32_t on_device, int32_t device, void* stream);
+int pbk_stft_c128(const void* in, void* out, int64_t nseg, int64_t nperseg, int64_t nchan,
+                  int64_t npol, int32_t inverse, int32_t on_device, int32_t device, void* stream);
+int pbk_detect_c128(const void* in, void* out, int64_t nsamp, int64_t nchan, int64_t npol,
+                    int32_t out_kind, int32_t on_device, int32_t device, void* stream);
+
 /* ---- detection / integration ---------------------------------------------------------------
  * pbk_detect:     float32 power from complex64 voltages (core.py:766-774; Stokes I core.py:948).
  *                 in (nsamp, nchan, npol) c64 -> out (nsamp/downsample, nchan[, npol]) f32

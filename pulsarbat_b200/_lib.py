@@ -19,6 +19,7 @@ EXPORTS = [
     "pbk_dedisp_plan_create", "pbk_dedisp_out_shape", "pbk_dedisp_exec_host",
     "pbk_dedisp_exec_device", "pbk_fft_plan_create", "pbk_stft_plan_create", "pbk_stft_plan_create_raw",
     "pbk_stft_detect_plan_create", "pbk_stft_fold_exec_device",
+    "pbk_dedisp_c128", "pbk_fft_c128", "pbk_stft_c128", "pbk_detect_c128",
     "pbk_fft_exec_host", "pbk_fft_exec_device", "pbk_detect", "pbk_detect_scrunch", "pbk_shift_channels", "pbk_downsample", "pbk_fold",
     "pbk_stokes", "pbk_pol_basis", "pbk_chirp", "pbk_ramp_plan_create", "pbk_mix", "pbk_decimate2",
     "pbk_plan_destroy", "pbk_plan_info", "pbk_plan_describe", "pbk_plan_profile",
@@ -90,6 +91,11 @@ def lib():
                                                   ctypes.POINTER(vp)]
         L.pbk_stft_fold_exec_device.argtypes = [vp, vp, vp, vp, ctypes.POINTER(dbl), i32, dbl, i64,
                                                 i32, vp]
+        L.pbk_dedisp_c128.argtypes = [vp, vp, i64, i64, i64, i32, dbl, dbl, dbl, ctypes.POINTER(dbl),
+                                      i64, i64, vp, i32, i32, vp]
+        L.pbk_fft_c128.argtypes = [vp, vp, i64, i64, i64, i32, i32, i32, vp]
+        L.pbk_stft_c128.argtypes = [vp, vp, i64, i64, i64, i64, i32, i32, i32, vp]
+        L.pbk_detect_c128.argtypes = [vp, vp, i64, i64, i64, i32, i32, i32, vp]
         L.pbk_fft_exec_host.argtypes = [vp, vp, vp]
         L.pbk_fft_exec_device.argtypes = [vp, vp, vp, vp]
         L.pbk_detect.argtypes = [vp, vp, i64, i64, i64, i32, i64, i32, i32, vp]

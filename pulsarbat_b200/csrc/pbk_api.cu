@@ -24,6 +24,7 @@
 #include "pbk_fast_launch.h"
 #include "pbk_tma_launch.h"
 #include "pbk_blue.cuh"
+#include "pbk_f64.cuh"
 #include "pbk_fft.cuh"
 #include "pbk_hostcopy.h"
 #include "pbk_misc.cuh"
@@ -2182,6 +2183,214 @@ extern "C" int pbk_chirp(int64_t nsamp, int64_t nchan, double dm, double sample_
   if (rc == PBK_OK && on_device)
     CUDA_TRY(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));  // df is freed here
   return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// complex128 (FP64) transforms: pbk_f64.cuh.  Plan-less: two work arrays per call from the
+// stream-ordered allocator; complex128 is the accuracy path, not the throughput path.
+// ------------------------------------------------------------------------------------------
+struct F64Work {   // stream-ordered scratch (+ staging for host pointers), freed on scope exit
+  cudaStream_t st;
+  std::vector<void*> ptrs;
+  explicit F64Work(cudaStream_t s) : st(s) {}
+  cudaError_t get(void** p, size_t bytes) {
+    cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 16, st);
+    if (e == cudaSuccess) ptrs.push_back(*p);
+    return e;
+  }
+  ~F64Work() { for (void* p : ptrs) cudaFreeAsync(p, st); }
+};
+
+static int f64_check_len(long long n) {
+  if (ilog2_exact(n) < 0)
+    return fail(PBK_ERR_UNSUPPORTED, "complex128 transforms need a power-of-two length (got %lld); "
+                "there is no FP64 path for other lengths and complex128 is never computed in "
+                "complex64 behind the caller's back -- cast to complex64 to use the any-length "
+                "kernels", n);
+  return PBK_OK;
+}
+
+extern "C" int pbk_fft_c128(const void* in, void* out, int64_t outer, int64_t n, int64_t inner,
+                            int32_t inverse, int32_t on_device, int32_t device, void* stream) {
+  if (!in || !out) return fail(PBK_ERR_INVALID, "NULL data pointer");
+  if (outer <= 0 || n <= 0 || inner <= 0) return fail(PBK_ERR_INVALID, "shape must be positive");
+  int rc = f64_check_len(n);
+  if (rc != PBK_OK) return rc;
+  CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t st = on_device ? reinterpret_cast<cudaStream_t>(stream) : cudaStreamPerThread;
+  const size_t bytes = (size_t)outer * n * inner * sizeof(double2);
+  F64Work w(st);
+  double2 *a, *b, *res, *din = nullptr;
+  CUDA_TRY(w.get((void**)&a, bytes));
+  CUDA_TRY(w.get((void**)&b, bytes));
+  const double2* src = reinterpret_cast<const double2*>(in);
+  if (!on_device) {
+    CUDA_TRY(w.get((void**)&din, bytes));
+    CUDA_TRY(host_to_device(din, in, bytes, st));
+    src = din;
+  }
+  CUDA_TRY(f64_fft(src, a, b, outer, n, inner, inverse ? +1 : -1, st, &res));
+  double2* dst = on_device ? reinterpret_cast<double2*>(out) : (res == a ? b : a);
+  f64_store_kernel<<<f64_blocks(outer * n * inner), 256, 0, st>>>(
+      res, dst, 0, outer * n, inner, inverse ? 1.0 / (double)n : 1.0, 0);
+  CUDA_TRY(cudaGetLastError());
+  if (!on_device) {
+    CUDA_TRY(device_to_host(out, dst, bytes, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return PBK_OK;
+}
+
+extern "C" int pbk_stft_c128(const void* in, void* out, int64_t nseg, int64_t nperseg,
+                             int64_t nchan, int64_t npol, int32_t inverse, int32_t on_device,
+                             int32_t device, void* stream) {
+  if (!in || !out) return fail(PBK_ERR_INVALID, "NULL data pointer");
+  if (nseg <= 0 || nperseg <= 0 || nchan <= 0 || npol <= 0)
+    return fail(PBK_ERR_INVALID, "shape must be positive");
+  int rc = f64_check_len(nperseg);
+  if (rc != PBK_OK) return rc;
+  CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t st = on_device ? reinterpret_cast<cudaStream_t>(stream) : cudaStreamPerThread;
+  const long long n = nperseg, I = nchan * npol, total = nseg * n * I;
+  const size_t bytes = (size_t)total * sizeof(double2);
+  F64Work w(st);
+  double2 *a, *b, *c, *res, *din = nullptr;
+  CUDA_TRY(w.get((void**)&a, bytes));
+  CUDA_TRY(w.get((void**)&b, bytes));
+  const double2* src = reinterpret_cast<const double2*>(in);
+  if (!on_device) {
+    CUDA_TRY(w.get((void**)&din, bytes));
+    CUDA_TRY(host_to_device(din, in, bytes, st));
+    src = din;
+  }
+  double2* dst = reinterpret_cast<double2*>(out);
+  if (!on_device) CUDA_TRY(w.get((void**)&dst, bytes));
+  if (!inverse) {   // segments are (n, C P) blocks: transform, then shift / scale / regroup
+    CUDA_TRY(f64_fft(src, a, b, nseg, n, I, -1, st, &res));
+    f64_stft_permute_kernel<<<f64_blocks(total), 256, 0, st>>>(res, dst, nseg, n, nchan, npol, 0,
+                                                                1.0 / (double)n);
+  } else {          // (x * n) then ifft (misc.py:82-87): ungroup / ifftshift, unscaled inverse
+    CUDA_TRY(w.get((void**)&c, bytes));
+    f64_stft_permute_kernel<<<f64_blocks(total), 256, 0, st>>>(src, c, nseg, n, nchan, npol, 1, 1.0);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(f64_fft(c, a, b, nseg, n, I, +1, st, &res));
+    f64_store_kernel<<<f64_blocks(total), 256, 0, st>>>(res, dst, 0, nseg * n, I, 1.0, 0);
+  }
+  CUDA_TRY(cudaGetLastError());
+  if (!on_device) {
+    CUDA_TRY(device_to_host(out, dst, bytes, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return PBK_OK;
+}
+
+extern "C" int pbk_dedisp_c128(const void* in, void* out, int64_t nsamp, int64_t nchan,
+                               int64_t npol, int32_t out_kind, double dm, double sample_rate_hz,
+                               double ref_freq_hz, const double* chan_freq_hz, int64_t crop_start,
+                               int64_t crop_stop, const void* chirp, int32_t on_device,
+                               int32_t device, void* stream) {
+  if (!in || !chan_freq_hz) return fail(PBK_ERR_INVALID, "NULL pointer");
+  if (nsamp <= 0 || nchan <= 0 || npol <= 0) return fail(PBK_ERR_INVALID, "shape must be positive");
+  if (!(sample_rate_hz > 0)) return fail(PBK_ERR_INVALID, "sample_rate_hz must be > 0");
+  if (out_kind < PBK_OUT_C64 || out_kind > PBK_OUT_STOKES_I)
+    return fail(PBK_ERR_INVALID, "unknown out_kind %d", out_kind);
+  if (out_kind == PBK_OUT_STOKES_I && npol != 2) return fail(PBK_ERR_INVALID, "Stokes I needs npol == 2");
+  if (crop_start < 0 || crop_stop > nsamp) return fail(PBK_ERR_INVALID, "crop outside the signal");
+  int rc = f64_check_len(nsamp);
+  if (rc != PBK_OK) return rc;
+  const long long rows = std::max<long long>(0, crop_stop - crop_start);
+  if (rows == 0) return PBK_OK;
+  if (!out) return fail(PBK_ERR_INVALID, "output pointer is NULL");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t st = on_device ? reinterpret_cast<cudaStream_t>(stream) : cudaStreamPerThread;
+  const long long N = nsamp, I = nchan * npol;
+  const size_t bytes = (size_t)N * I * sizeof(double2);
+  const long long E = out_kind == PBK_OUT_STOKES_I ? nchan : I;
+  const size_t obytes = (size_t)rows * E * (out_kind == PBK_OUT_C64 ? 16 : 8);
+  F64Work w(st);
+  double2 *a, *b, *res, *din = nullptr;
+  double* dfreq;
+  float2* dchirp = nullptr;
+  CUDA_TRY(w.get((void**)&a, bytes));
+  CUDA_TRY(w.get((void**)&b, bytes));
+  CUDA_TRY(w.get((void**)&dfreq, (size_t)nchan * 8));
+  CUDA_TRY(cudaMemcpyAsync(dfreq, chan_freq_hz, (size_t)nchan * 8, cudaMemcpyHostToDevice, st));
+  const double2* src = reinterpret_cast<const double2*>(in);
+  if (!on_device) {
+    CUDA_TRY(w.get((void**)&din, bytes));
+    CUDA_TRY(host_to_device(din, in, bytes, st));
+    src = din;
+    if (chirp) {
+      CUDA_TRY(w.get((void**)&dchirp, (size_t)N * nchan * 8));
+      CUDA_TRY(host_to_device(dchirp, chirp, (size_t)N * nchan * 8, st));
+    }
+  } else {
+    dchirp = const_cast<float2*>(reinterpret_cast<const float2*>(chirp));
+  }
+  CUDA_TRY(f64_fft(src, a, b, 1, N, I, -1, st, &res));
+  F64Chirp c;
+  c.N = N; c.nchan = nchan; c.npol = npol;
+  c.df = 1.0 / ((double)N * (1.0 / sample_rate_hz));
+  if (std::isinf(ref_freq_hz)) { c.fr_sub = 0; c.inv_fr = 0; c.a0 = -1.0; }
+  else { c.fr_sub = ref_freq_hz; c.inv_fr = 1.0 / ref_freq_hz; c.a0 = 0; }
+  c.D = (1.0 / 2.41e-4) * dm * 1e12;
+  c.chan_freq = dfreq;
+  c.chirp_arr = dchirp;
+  f64_chirp_kernel<<<f64_blocks(N * I), 256, 0, st>>>(res, c);
+  CUDA_TRY(cudaGetLastError());
+  double2* spec = res;
+  double2* other = res == a ? b : a;
+  // the inverse must not read and write the same array: `spec` is the source, results alternate
+  // between `other` and a third array
+  double2* third;
+  CUDA_TRY(w.get((void**)&third, bytes));
+  CUDA_TRY(f64_fft(spec, other, third, 1, N, I, +1, st, &res));
+  void* dst = out;
+  if (!on_device) CUDA_TRY(w.get(&dst, obytes));
+  f64_store_kernel<<<f64_blocks(rows * E), 256, 0, st>>>(res, dst, crop_start, crop_stop, I,
+                                                         1.0 / (double)N, out_kind);
+  CUDA_TRY(cudaGetLastError());
+  if (!on_device) {
+    CUDA_TRY(device_to_host(out, dst, obytes, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  } else {
+    // the host array of channel frequencies was copied asynchronously: it must stay valid until
+    // the copy has run, so wait for it here (a few KB; the kernels stay queued)
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return PBK_OK;
+}
+
+// power detection of complex128 voltages in FP64 (core.py:766-774 keeps float64 for complex128)
+extern "C" int pbk_detect_c128(const void* in, void* out, int64_t nsamp, int64_t nchan,
+                               int64_t npol, int32_t out_kind, int32_t on_device, int32_t device,
+                               void* stream) {
+  if (!in || !out) return fail(PBK_ERR_INVALID, "NULL data pointer");
+  if (nsamp <= 0 || nchan <= 0 || npol <= 0) return fail(PBK_ERR_INVALID, "bad shape");
+  if (out_kind != PBK_OUT_INTENSITY && out_kind != PBK_OUT_STOKES_I)
+    return fail(PBK_ERR_INVALID, "out_kind must be INTENSITY or STOKES_I");
+  if (out_kind == PBK_OUT_STOKES_I && npol != 2) return fail(PBK_ERR_INVALID, "Stokes I needs npol == 2");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t st = on_device ? reinterpret_cast<cudaStream_t>(stream) : cudaStreamPerThread;
+  const long long I = nchan * npol, E = out_kind == PBK_OUT_STOKES_I ? nchan : I;
+  const size_t ib = (size_t)nsamp * I * 16, ob = (size_t)nsamp * E * 8;
+  F64Work w(st);
+  const double2* src = reinterpret_cast<const double2*>(in);
+  void* dst = out;
+  if (!on_device) {
+    double2* din;
+    CUDA_TRY(w.get((void**)&din, ib));
+    CUDA_TRY(w.get(&dst, ob));
+    CUDA_TRY(host_to_device(din, in, ib, st));
+    src = din;
+  }
+  f64_store_kernel<<<f64_blocks(nsamp * E), 256, 0, st>>>(src, dst, 0, nsamp, I, 1.0, out_kind);
+  CUDA_TRY(cudaGetLastError());
+  if (!on_device) {
+    CUDA_TRY(device_to_host(out, dst, ob, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return PBK_OK;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -280,7 +280,10 @@ __device__ __forceinline__ void fast_store_out(const FastTile& T, unsigned row,
 // level twiddle for the R registers of a last-stage group: W_M^(nrest*(klo + KS*m))
 //   = E * G[m],  E = W_M^(nrest*klo) (one exact root per task), G[m] = W_M^(nrest*KS*m) (per tile,
 //   kept in shared memory as {G.x, G.y, G.y, G.x} so that E*G[m] is two packed instructions)
-template <int R, bool CONJ>
+// (GS = float4 stride between consecutive m: 1 for the one table of a wide tile; narrow tiles keep
+// a table per lane row stored m-major, [m][row], so that the threads of a quarter-warp -- eight
+// different lane rows -- read eight consecutive 16-byte entries instead of one bank group 8 times)
+template <int R, bool CONJ, int GS = 1>
 __device__ __forceinline__ void level_twiddle(const PassArgs& p, c2* v, unsigned nrest,
                                               unsigned klo, const float4* G4) {
   const float2 E = unit_root((unsigned long long)nrest * klo, p.log2M);
@@ -289,7 +292,7 @@ __device__ __forceinline__ void level_twiddle(const PassArgs& p, c2* v, unsigned
   for (int m = 0; m < R; ++m) {
     float2 w = E;
     if (m > 0) {
-      const float4 g = G4[m];
+      const float4 g = G4[m * GS];
       w = p_fma(make_float2(g.x, g.y), ex, p_mul(make_float2(g.z, g.w), ey));
     }
     v[m] = cmul(v[m], p_bc(w.x), p_bc(CONJ ? -w.y : w.y));
@@ -703,7 +706,8 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
   const long long off_out =
       (jr * row_out + (long long)(colt / p.P) * p.mout.a_c + (colt % p.P) * p.mout.a_p) * out_eb;
   const int chant = colt / p.P;
-  const float4* G4t = G4 + jr * C::RL;   // this thread's row of the level-twiddle tables
+  constexpr int GS = NARROW ? C::G_ROWS : 1;   // level-twiddle tables: [m][lane row]
+  const float4* G4t = G4 + jr;                 // this thread's lane row
 
   constexpr int RL = C::RL;
   constexpr int LTASKS = (C::L / RL) * C::PW;
@@ -761,7 +765,7 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
           const int j = i / RL, m = i - j * RL;
           const float2 g =
               unit_root((unsigned long long)(nrest0 + j) * (unsigned)(C::KS * m), p.log2M);
-          G4[i] = make_float4(g.x, g.y, g.y, g.x);
+          G4[m * C::G_ROWS + j] = make_float4(g.x, g.y, g.y, g.x);
         }
       } else if (tid < RL) {
         const float2 g = unit_root((unsigned long long)nrest0 * (unsigned)(C::KS * tid), p.log2M);
@@ -795,7 +799,7 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
           for (int i = 0; i < RL; ++i) v[i] = lds_c2(tile, last_idx<C>(b, i, pr));
           Butterfly<RL, SIGNINV>::run(v);
           const int klo = klo_of<C>(b);
-          level_twiddle<RL, SIGNINV>(p, v, T.nrest, (unsigned)klo, G4t);
+          level_twiddle<RL, SIGNINV, GS>(p, v, T.nrest, (unsigned)klo, G4t);
 #pragma unroll
           for (int i = 0; i < RL; ++i) fast_store_c64(T, (unsigned)(klo + i * C::KS), rb_out, v[i]);
         }
@@ -963,7 +967,7 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
         c2 v[RL];
 #pragma unroll
         for (int i = 0; i < RL; ++i) v[i] = fast_load<LK_PLANAR>(T, (unsigned)(klo + i * C::KS), rb_in);
-        level_twiddle<RL, true>(p, v, T.nrest, (unsigned)klo, G4t);
+        level_twiddle<RL, true, GS>(p, v, T.nrest, (unsigned)klo, G4t);
         Butterfly<RL, true>::run(v);
 #pragma unroll
         for (int i = 0; i < RL; ++i) sts_c2(tile, last_idx<C>(b, i, pr), v[i]);

@@ -4,8 +4,12 @@ One function per reference operation on the hot path.  Every function accepts ei
 array (host round trip through ``*_exec_host``; safe to call from several threads, which is what
 a dask ``map_blocks`` does -- reference transforms.py:49-50) or a
 :class:`~pulsarbat_b200.device.DeviceArray` (no copies; work is queued on torch's current
-stream).  complex128 input is computed in complex64 on the GPU and returned as complex128, so the
-reference's dtype contract holds (core.py:773, fft.py:34) at complex64 precision.
+stream).  complex128 input to the transforms the reference keeps in complex128 -- ``dedisperse``,
+``fft``, ``stft`` / ``istft``, ``detect`` (dedispersion.py:125, fft.py:34, misc.py:47,87,
+core.py:766-774) -- is computed in FP64 (csrc/pbk_f64.cuh, power-of-two lengths; other lengths
+raise ``PbkUnsupported`` rather than being narrowed silently).  The remaining helpers
+(``phase_ramp``, ``mix``, ``stokes``, ``pol_basis``) compute complex128 input in complex64 and
+say so in their docstrings.
 """
 
 import collections
@@ -193,6 +197,25 @@ def _host_c64(x):
     return np.ascontiguousarray(x, dtype=np.complex64), x.dtype
 
 
+def _is_c128(x):
+    return np.dtype(x.dtype) == np.complex128
+
+
+def _c128_call(fn, data, out_shape, out_dtype, args_after, dev):
+    """Run one of the plan-less FP64 entry points (pbk_*_c128) on a host array or DeviceArray:
+    fn(in, out, *args_after, on_device, device, stream)."""
+    if _is_dev(data):
+        x = data.contiguous()
+        out = DeviceArray.empty(out_shape, out_dtype, x.device)
+        L.check(fn(L.ptr(x.ptr), L.ptr(out.ptr), *args_after, 1, x.device,
+                   ctypes.c_void_p(_stream())))
+        return out
+    x = np.ascontiguousarray(data, dtype=np.complex128)
+    out = _result(out_shape, out_dtype)
+    L.check(fn(L.ptr(x), L.ptr(out), *args_after, 0, dev, None))
+    return out
+
+
 _pinned_results = os.environ.get("PBK_PINNED_RESULTS", "0") not in ("", "0")
 
 
@@ -270,6 +293,9 @@ def dedisperse(data, *, dm, sample_rate_hz, chan_freq_hz, ref_freq_hz, crop=None
         start, stop = 0, 0
     freqs = np.ascontiguousarray(chan_freq_hz, dtype=np.float64)
     dev = (data.device if _is_dev(data) else (default_device() if device is None else device))
+    if raw is None and _is_c128(data):
+        return _dedisperse_c128(data, nsamp, nchan, npol, trailing, dm, sample_rate_hz, freqs,
+                                ref_freq_hz, start, stop, out_kind, downsample, chirp_array, dev)
     key = ("dedisp", nsamp, nchan, npol, raw, int(out_kind), float(dm),
            float(sample_rate_hz), float(ref_freq_hz), freqs.tobytes(), start, stop,
            int(downsample), chirp_array is not None, dev)
@@ -281,6 +307,41 @@ def dedisperse(data, *, dm, sample_rate_hz, chan_freq_hz, ref_freq_hz, crop=None
     with ctx as plan:
         return _dedisperse_with(ctx, plan, data, nsamp, nchan, trailing, out_kind, chirp_array,
                                 int8, raw_np, dev)
+
+
+def _dedisperse_c128(data, nsamp, nchan, npol, trailing, dm, sample_rate_hz, freqs, ref_freq_hz,
+                     start, stop, out_kind, downsample, chirp_array, dev):
+    """complex128 in -> complex128 (or float64 power) out, FP64 arithmetic (pbk_dedisp_c128); the
+    chirp is rounded to complex64 exactly where the reference rounds it (dedispersion.py:23)."""
+    rows = max(0, stop - start)
+    out_trailing = (nchan,) if out_kind == L.OUT_STOKES_I else (nchan,) + tuple(trailing)
+    odt = np.complex128 if out_kind == L.OUT_C64 else np.float64
+    ch = None
+    if chirp_array is not None:
+        ch = chirp_array if _is_dev(chirp_array) else np.ascontiguousarray(
+            np.asarray(chirp_array).reshape(nsamp, nchan), dtype=np.complex64)
+        if _is_dev(data) and not _is_dev(ch):
+            ch = DeviceArray.from_numpy(ch, dev)
+        elif not _is_dev(data) and _is_dev(ch):
+            ch = np.asarray(ch)
+    fp = freqs.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    chp = None if ch is None else L.ptr(ch.ptr if _is_dev(ch) else ch)
+    args = (nsamp, nchan, npol, int(out_kind), float(dm), float(sample_rate_hz),
+            float(ref_freq_hz), fp, start, stop, chp)
+    if rows == 0:
+        out = (DeviceArray.empty((0,) + out_trailing, odt, dev) if _is_dev(data)
+               else np.empty((0,) + out_trailing, odt))
+    else:
+        out = _c128_call(L.lib().pbk_dedisp_c128, data, (rows,) + out_trailing, odt, args, dev)
+    if downsample > 1:                       # time sum of the float64 power (rare: not fused)
+        m = int(downsample)
+        n = rows // m * m
+        if _is_dev(out):
+            t = out.tensor[:n].reshape((n // m, m) + tuple(out.shape[1:])).sum(dim=1)
+            out = DeviceArray(t.contiguous())
+        else:
+            out = out[:n].reshape((n // m, m) + out.shape[1:]).sum(axis=1)
+    return out
 
 
 def _dedisperse_with(ent, plan, data, nsamp, nchan, trailing, out_kind, chirp_array, int8, raw_np,
@@ -349,6 +410,20 @@ def detect(data, stokes=False, downsample=1, freq_sum=1, device=None):
     cout = nchan // freq_sum
     out_shape = (rows, cout) if stokes else (rows, cout) + shape[2:]
     kind = L.OUT_STOKES_I if stokes else L.OUT_INTENSITY
+    if _is_c128(data):
+        # float64 power from complex128 voltages (core.py:766-774 keeps the precision); the sums
+        # over time / channels are not fused on this path
+        dev = data.device if _is_dev(data) else (default_device() if device is None else device)
+        full = (nsamp, nchan) if stokes else shape
+        out = _c128_call(L.lib().pbk_detect_c128, data, full, np.float64,
+                         (nsamp, nchan, npol, int(kind)), dev)
+        m = int(downsample)
+        if m > 1 or freq_sum > 1:
+            a = out.tensor if _is_dev(out) else out
+            a = a[:rows * m].reshape((rows, m, cout, freq_sum) + tuple(a.shape[2:]))
+            a = a.sum(dim=(1, 3)) if _is_dev(out) else a.sum(axis=(1, 3))
+            out = DeviceArray(a.contiguous()) if _is_dev(out) else a
+        return out
 
     def call(pin, pout, on_dev, dev, stream):
         if freq_sum > 1:
@@ -587,6 +662,9 @@ def fft(data, axis=0, inverse=False, device=None):
     n = shape[axis]
     inner = int(np.prod(shape[axis + 1:])) if axis + 1 < len(shape) else 1
     dev = data.device if _is_dev(data) else (default_device() if device is None else device)
+    if _is_c128(data):
+        return _c128_call(L.lib().pbk_fft_c128, data, shape, np.complex128,
+                          (outer, n, inner, int(bool(inverse))), dev)
     key = ("fft", outer, n, inner, bool(inverse), dev)
     return _run_fft_plan(key, lambda: L.FFTPlan(outer, n, inner, inverse=inverse, device=dev),
                          data, shape)
@@ -614,6 +692,9 @@ def stft(data, nperseg, device=None, raw=None, raw_shape=None):
     npol = int(np.prod(shape[2:])) if len(shape) > 2 else 1
     in_dtype, raw_np = _RAW_KINDS[raw] if raw is not None else (L.PBK_C64, None)
     dev = data.device if _is_dev(data) else (default_device() if device is None else device)
+    if raw is None and _is_c128(data):
+        return _c128_call(L.lib().pbk_stft_c128, data, (nseg, nchan * n) + shape[2:],
+                          np.complex128, (nseg, n, nchan, npol, 0), dev)
     key = ("stft", nseg, n, nchan, npol, False, raw, dev)
     return _run_fft_plan(key, lambda: L.STFTPlan(nseg, n, nchan, npol, inverse=False, device=dev,
                                                  in_dtype=in_dtype),
@@ -723,6 +804,9 @@ def istft(data, nperseg, device=None):
     nseg, nchan = shape[0], shape[1] // n
     npol = int(np.prod(shape[2:])) if len(shape) > 2 else 1
     dev = data.device if _is_dev(data) else (default_device() if device is None else device)
+    if _is_c128(data):
+        return _c128_call(L.lib().pbk_stft_c128, data, (nseg * n, nchan) + shape[2:],
+                          np.complex128, (nseg, n, nchan, npol, 1), dev)
     key = ("stft", nseg, n, nchan, npol, True, dev)
     return _run_fft_plan(key, lambda: L.STFTPlan(nseg, n, nchan, npol, inverse=True, device=dev),
                          data, (nseg * n, nchan) + shape[2:])

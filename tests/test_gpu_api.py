@@ -7,6 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 import pytest
+import scipy.fft
 
 from oracle import pbk_oracle as orc
 
@@ -432,3 +433,70 @@ def test_raw_packed_blocks_through_the_api():
         pb.kernels.dedisperse(raw2[0], raw="u2", **kw)               # raw_shape missing
     with pytest.raises(ValueError):
         pb.kernels.dedisperse(raw2[0], raw="u3", **kw)
+
+
+# ------------------------------------------------------------------------------------------
+# complex128: FP64 arithmetic end to end (csrc/pbk_f64.cuh), never narrowed to complex64
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", [4, 8, 15, 16, 23, 42])
+def test_complex128_reversibility_kat_at_the_reference_tolerance(seed):
+    """reference tests/test_dedispersion.py:73-98, verbatim tolerance: dedisperse by +DM then -DM
+    and recover the input to atol 3e-8 -- only possible if complex128 is computed in FP64."""
+    import scipy.signal
+    import pulsarbat_b200 as pb
+    u = pb.units
+    N, M = 2 ** 18, 2 ** 12
+    R = np.random.default_rng(seed=seed)
+    x = R.standard_normal(N) + 1j * R.standard_normal(N)
+    x *= np.exp(-(((np.arange(N) - N // 2) / M) ** 2))
+    x = scipy.signal.sosfilt(scipy.signal.butter(10, 0.45, "lowpass", fs=1.0, output="sos"), x)
+    sig = pb.BasebandSignal(x.reshape(-1, 1), sample_rate=400 * u.MHz, center_freq=600 * u.MHz,
+                            start_time=pb.Time(56000.0))
+    assert sig.dtype == np.complex128
+    temp = pb.coherent_dedispersion(sig, pb.DM(0.01))
+    sig2 = pb.coherent_dedispersion(temp, -pb.DM(0.01))
+    assert temp.dtype == np.complex128 and sig2.dtype == np.complex128
+    toffset = sig2.start_time - sig.start_time
+    noffset = int(np.rint(float((toffset * sig.sample_rate).to_value(u.one))))
+    res = np.asarray(sig[noffset:noffset + len(sig2)].data) - np.asarray(sig2.data)
+    assert np.allclose(res, 0, atol=3e-8), float(np.abs(res).max())
+
+
+def test_complex128_paths_match_the_oracle_to_double_precision():
+    import pulsarbat_b200 as pb
+    from pulsarbat_b200 import kernels
+    rng = np.random.default_rng(128)
+    N, C = 4096, 3
+    x = rng.standard_normal((N, C, 2)) + 1j * rng.standard_normal((N, C, 2))
+    freqs = orc.channel_freqs(600e6, 1e6, C)
+    want, s0, s1 = orc.coherent_dedispersion(x, 2.0, sample_rate=1e6, center_freq=600e6)
+    for src in (x, pb.DeviceArray.from_numpy(x)):
+        got = kernels.dedisperse(src, dm=2.0, sample_rate_hz=1e6, chan_freq_hz=freqs,
+                                 ref_freq_hz=600e6, crop=(s0, s1))
+        assert got.dtype == np.complex128 and relerr(np.asarray(got), want) < 1e-12
+    chirp = orc.chirp_from_signal(2.0, N, 1e6, freqs, 600e6)
+    got = kernels.dedisperse(x, dm=2.0, sample_rate_hz=1e6, chan_freq_hz=freqs, ref_freq_hz=600e6,
+                             crop=(s0, s1), chirp_array=chirp)
+    assert relerr(got, want) < 1e-12
+    gi = kernels.dedisperse(x, dm=2.0, sample_rate_hz=1e6, chan_freq_hz=freqs, ref_freq_hz=600e6,
+                            crop=(s0, s1), out_kind=2, downsample=4)
+    wi = orc.downsample(orc.stokes_I(want), 4)
+    assert gi.dtype == np.float64 and relerr(gi, wi) < 1e-12
+    # plain transforms, channelizer, detection
+    for n in (2, 8, 64, 1024, 2 ** 15):
+        y = rng.standard_normal((3, n, 5)) + 1j * rng.standard_normal((3, n, 5))
+        assert relerr(kernels.fft(y, axis=1), scipy.fft.fft(y, axis=1)) < 1e-13
+        assert relerr(kernels.fft(y, axis=1, inverse=True), scipy.fft.ifft(y, axis=1)) < 1e-13
+    xs = rng.standard_normal((16 * 64, 3, 2)) + 1j * rng.standard_normal((16 * 64, 3, 2))
+    ys = kernels.stft(xs, 64)
+    assert ys.dtype == np.complex128 and relerr(ys, orc.stft(xs, 64)) < 1e-13
+    assert relerr(kernels.istft(ys, 64), xs) < 1e-13
+    assert relerr(kernels.detect(xs), orc.to_intensity(xs)) < 1e-15
+    assert relerr(kernels.detect(xs, stokes=True, downsample=4, freq_sum=3),
+                  orc.stokes_I(xs).reshape(256, 4, 1, 3).sum(axis=(1, 3))) < 1e-14
+    # other lengths are refused, never narrowed
+    with pytest.raises(pb.PbkUnsupported, match="power-of-two"):
+        kernels.fft(np.zeros((12, 2), np.complex128))
+    with pytest.raises(pb.PbkUnsupported, match="power-of-two"):
+        kernels.dedisperse(np.zeros((1000, 2), np.complex128), dm=1.0, sample_rate_hz=1e6,
+                           chan_freq_hz=[1e9, 1.001e9], ref_freq_hz=1e9)
