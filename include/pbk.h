@@ -192,8 +192,8 @@ int pbk_fft_exec_device(pbk_plan* plan, const void* d_in, void* d_out, void* str
  * The reference keeps complex128 through its transforms (scipy preserves the dtype:
  * dedispersion.py:125, fft.py:34, misc.py:47,87; core.py:766-774 returns float64 power), and its
  * own test of +-DM reversibility asserts atol 3e-8 (tests/test_dedispersion.py:73-98).  These entry
- * points compute in FP64 (Stockham radix-4 passes, csrc/pbk_f64.cuh) for power-of-two lengths and
- * return PBK_ERR_UNSUPPORTED for any other length: complex128 is never narrowed to complex64.
+ * points compute in FP64 (Stockham radix-4 passes, csrc/pbk_f64.cuh; any other length through
+ * Bluestein's chirp-z identity on top of them): complex128 is never narrowed to complex64.
  * Plan-less; host pointers (synchronous) or device pointers (`on_device`, enqueued on `stream`).
  *   pbk_dedisp_c128: in (nsamp, nchan, npol) complex128 -> out rows [crop_start, crop_stop) as
  *                    complex128 (C64 kind), float64 per-pol power or float64 Stokes I; the chirp

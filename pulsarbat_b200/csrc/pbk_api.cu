@@ -2202,11 +2202,8 @@ struct F64Work {   // stream-ordered scratch (+ staging for host pointers), free
 };
 
 static int f64_check_len(long long n) {
-  if (ilog2_exact(n) < 0)
-    return fail(PBK_ERR_UNSUPPORTED, "complex128 transforms need a power-of-two length (got %lld); "
-                "there is no FP64 path for other lengths and complex128 is never computed in "
-                "complex64 behind the caller's back -- cast to complex64 to use the any-length "
-                "kernels", n);
+  if (n > (1ll << 28))
+    return fail(PBK_ERR_UNSUPPORTED, "complex128 transform length %lld is too long", n);
   return PBK_OK;
 }
 
@@ -2220,17 +2217,17 @@ extern "C" int pbk_fft_c128(const void* in, void* out, int64_t outer, int64_t n,
   cudaStream_t st = on_device ? reinterpret_cast<cudaStream_t>(stream) : cudaStreamPerThread;
   const size_t bytes = (size_t)outer * n * inner * sizeof(double2);
   F64Work w(st);
-  double2 *a, *b, *res, *din = nullptr;
-  CUDA_TRY(w.get((void**)&a, bytes));
-  CUDA_TRY(w.get((void**)&b, bytes));
+  auto alloc = [&](void** p, size_t b) { return w.get(p, b); };
+  double2 *res, *din = nullptr;
   const double2* src = reinterpret_cast<const double2*>(in);
   if (!on_device) {
     CUDA_TRY(w.get((void**)&din, bytes));
     CUDA_TRY(host_to_device(din, in, bytes, st));
     src = din;
   }
-  CUDA_TRY(f64_fft(src, a, b, outer, n, inner, inverse ? +1 : -1, st, &res));
-  double2* dst = on_device ? reinterpret_cast<double2*>(out) : (res == a ? b : a);
+  CUDA_TRY(f64_fft_any(src, alloc, outer, n, inner, inverse ? +1 : -1, st, &res));
+  double2* dst = reinterpret_cast<double2*>(out);
+  if (!on_device) CUDA_TRY(w.get((void**)&dst, bytes));
   f64_store_kernel<<<f64_blocks(outer * n * inner), 256, 0, st>>>(
       res, dst, 0, outer * n, inner, inverse ? 1.0 / (double)n : 1.0, 0);
   CUDA_TRY(cudaGetLastError());
@@ -2254,9 +2251,8 @@ extern "C" int pbk_stft_c128(const void* in, void* out, int64_t nseg, int64_t np
   const long long n = nperseg, I = nchan * npol, total = nseg * n * I;
   const size_t bytes = (size_t)total * sizeof(double2);
   F64Work w(st);
-  double2 *a, *b, *c, *res, *din = nullptr;
-  CUDA_TRY(w.get((void**)&a, bytes));
-  CUDA_TRY(w.get((void**)&b, bytes));
+  auto alloc = [&](void** p, size_t b) { return w.get(p, b); };
+  double2 *c, *res, *din = nullptr;
   const double2* src = reinterpret_cast<const double2*>(in);
   if (!on_device) {
     CUDA_TRY(w.get((void**)&din, bytes));
@@ -2266,14 +2262,14 @@ extern "C" int pbk_stft_c128(const void* in, void* out, int64_t nseg, int64_t np
   double2* dst = reinterpret_cast<double2*>(out);
   if (!on_device) CUDA_TRY(w.get((void**)&dst, bytes));
   if (!inverse) {   // segments are (n, C P) blocks: transform, then shift / scale / regroup
-    CUDA_TRY(f64_fft(src, a, b, nseg, n, I, -1, st, &res));
+    CUDA_TRY(f64_fft_any(src, alloc, nseg, n, I, -1, st, &res));
     f64_stft_permute_kernel<<<f64_blocks(total), 256, 0, st>>>(res, dst, nseg, n, nchan, npol, 0,
                                                                 1.0 / (double)n);
   } else {          // (x * n) then ifft (misc.py:82-87): ungroup / ifftshift, unscaled inverse
     CUDA_TRY(w.get((void**)&c, bytes));
     f64_stft_permute_kernel<<<f64_blocks(total), 256, 0, st>>>(src, c, nseg, n, nchan, npol, 1, 1.0);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(f64_fft(c, a, b, nseg, n, I, +1, st, &res));
+    CUDA_TRY(f64_fft_any(c, alloc, nseg, n, I, +1, st, &res));
     f64_store_kernel<<<f64_blocks(total), 256, 0, st>>>(res, dst, 0, nseg * n, I, 1.0, 0);
   }
   CUDA_TRY(cudaGetLastError());
@@ -2308,11 +2304,10 @@ extern "C" int pbk_dedisp_c128(const void* in, void* out, int64_t nsamp, int64_t
   const long long E = out_kind == PBK_OUT_STOKES_I ? nchan : I;
   const size_t obytes = (size_t)rows * E * (out_kind == PBK_OUT_C64 ? 16 : 8);
   F64Work w(st);
-  double2 *a, *b, *res, *din = nullptr;
+  auto alloc = [&](void** p, size_t b) { return w.get(p, b); };
+  double2 *res, *din = nullptr;
   double* dfreq;
   float2* dchirp = nullptr;
-  CUDA_TRY(w.get((void**)&a, bytes));
-  CUDA_TRY(w.get((void**)&b, bytes));
   CUDA_TRY(w.get((void**)&dfreq, (size_t)nchan * 8));
   CUDA_TRY(cudaMemcpyAsync(dfreq, chan_freq_hz, (size_t)nchan * 8, cudaMemcpyHostToDevice, st));
   const double2* src = reinterpret_cast<const double2*>(in);
@@ -2327,7 +2322,7 @@ extern "C" int pbk_dedisp_c128(const void* in, void* out, int64_t nsamp, int64_t
   } else {
     dchirp = const_cast<float2*>(reinterpret_cast<const float2*>(chirp));
   }
-  CUDA_TRY(f64_fft(src, a, b, 1, N, I, -1, st, &res));
+  CUDA_TRY(f64_fft_any(src, alloc, 1, N, I, -1, st, &res));
   F64Chirp c;
   c.N = N; c.nchan = nchan; c.npol = npol;
   c.df = 1.0 / ((double)N * (1.0 / sample_rate_hz));
@@ -2339,12 +2334,7 @@ extern "C" int pbk_dedisp_c128(const void* in, void* out, int64_t nsamp, int64_t
   f64_chirp_kernel<<<f64_blocks(N * I), 256, 0, st>>>(res, c);
   CUDA_TRY(cudaGetLastError());
   double2* spec = res;
-  double2* other = res == a ? b : a;
-  // the inverse must not read and write the same array: `spec` is the source, results alternate
-  // between `other` and a third array
-  double2* third;
-  CUDA_TRY(w.get((void**)&third, bytes));
-  CUDA_TRY(f64_fft(spec, other, third, 1, N, I, +1, st, &res));
+  CUDA_TRY(f64_fft_any(spec, alloc, 1, N, I, +1, st, &res));
   void* dst = out;
   if (!on_device) CUDA_TRY(w.get(&dst, obytes));
   f64_store_kernel<<<f64_blocks(rows * E), 256, 0, st>>>(res, dst, crop_start, crop_stop, I,

@@ -7,7 +7,9 @@
 // radix-4 FFT along the slow axis of an (outer, n, inner) array, one full read + write of the array
 // per stage (32 B per sample and stage; B200's FP64 rate is far above what that needs), lanes
 // (`inner`) innermost so that every access is coalesced, twiddles from sincospi in FP64.
-// Power-of-two n only; other lengths are refused by the host (PBK_ERR_UNSUPPORTED), never narrowed.
+// Other lengths (the reference accepts any: a dedispersed, cropped signal is dedispersed again in
+// its own reversibility test) go through Bluestein's chirp-z identity on top of the same stages, with
+// the chirp phases pi j^2 / n reduced exactly in integers (f64_fft_any).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -145,8 +147,62 @@ __global__ void __launch_bounds__(256) f64_stft_permute_kernel(const double2* __
       out[chan_side] = make_double2(v.x * scale, v.y * scale);
     } else {
       // np.fft.ifftshift then ifft: bin k of the transform input is the channel at shifted position
-      out[g] = in[((s * C + c) * n + ((k + (n + 1) / 2) % n)) * P + p];
+      out[g] = in[chan_side];   // ifftshift(y)[k] = y[(k + n // 2) mod n]
     }
+  }
+}
+
+// ---- Bluestein: X[k] = w[k] sum_j (x[j] w[j]) conj(w)[k - j],  w[j] = exp(sign i pi j^2 / n) ----
+__device__ __forceinline__ double2 f64_blue_w(long long j, long long n, int sign) {
+  const long long e = (long long)(((unsigned long long)j * (unsigned long long)j) % (unsigned long long)(2 * n));
+  double s, c;
+  sincospi((double)e / (double)n, &s, &c);       // e / n in [0, 2): exact argument reduction
+  return make_double2(c, sign < 0 ? -s : s);
+}
+// a[o, j, i] = x[o, j, i] w[j] for j < n, 0 for n <= j < M
+__global__ void __launch_bounds__(256) f64_blue_pre_kernel(const double2* __restrict__ x,
+                                                           double2* __restrict__ a, long long outer,
+                                                           long long n, long long M, long long inner,
+                                                           int sign) {
+  const long long total = outer * M * inner;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const long long i = g % inner, r = g / inner, j = r % M, o = r / M;
+    a[g] = j < n ? zmul(x[(o * n + j) * inner + i], f64_blue_w(j, n, sign)) : make_double2(0.0, 0.0);
+  }
+}
+// b[j] = conj(w[|j|]) on the circle of length M (j = -(n-1) .. n-1), 0 elsewhere
+__global__ void __launch_bounds__(256) f64_blue_filter_kernel(double2* __restrict__ b, long long n,
+                                                              long long M, int sign) {
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < M;
+       j += (long long)gridDim.x * blockDim.x) {
+    const long long d = j < n ? j : (M - j < n ? M - j : -1);
+    double2 v = make_double2(0.0, 0.0);
+    if (d >= 0) { v = f64_blue_w(d, n, sign); v.y = -v.y; }
+    b[j] = v;
+  }
+}
+__global__ void __launch_bounds__(256) f64_blue_mul_kernel(double2* __restrict__ a,
+                                                           const double2* __restrict__ bhat,
+                                                           long long outer, long long M,
+                                                           long long inner) {
+  const long long total = outer * M * inner;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x)
+    a[g] = zmul(a[g], bhat[(g / inner) % M]);
+}
+// X[o, k, i] = w[k] c[o, k, i] / M for k < n
+__global__ void __launch_bounds__(256) f64_blue_post_kernel(const double2* __restrict__ c,
+                                                            double2* __restrict__ X, long long outer,
+                                                            long long n, long long M, long long inner,
+                                                            int sign) {
+  const long long total = outer * n * inner;
+  const double sc = 1.0 / (double)M;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const long long i = g % inner, r = g / inner, k = r % n, o = r / n;
+    const double2 v = zmul(c[(o * M + k) * inner + i], f64_blue_w(k, n, sign));
+    X[g] = make_double2(v.x * sc, v.y * sc);
   }
 }
 
@@ -189,6 +245,46 @@ static inline cudaError_t f64_fft(const double2* src, double2* a, double2* b, lo
   }
   *result = const_cast<double2*>(x);
   return cudaSuccess;
+}
+
+// Any length.  `alloc(bytes)` hands out device arrays that live until the caller's work is queued
+// (stream-ordered scratch); the unscaled transform of `src` ends in *result.
+template <class Alloc>
+static inline cudaError_t f64_fft_any(const double2* src, Alloc&& alloc, long long outer,
+                                      long long n, long long inner, int sign, cudaStream_t st,
+                                      double2** result) {
+  cudaError_t e;
+  double2 *a = nullptr, *b = nullptr;
+  bool pow2 = n > 0 && (n & (n - 1)) == 0;
+  if (pow2) {
+    const size_t bytes = (size_t)outer * n * inner * sizeof(double2);
+    if ((e = alloc((void**)&a, bytes)) != cudaSuccess) return e;
+    if ((e = alloc((void**)&b, bytes)) != cudaSuccess) return e;
+    return f64_fft(src, a, b, outer, n, inner, sign, st, result);
+  }
+  long long M = 16;
+  while (M < 2 * n - 1) M <<= 1;
+  const size_t bytes = (size_t)outer * M * inner * sizeof(double2);
+  double2 *pad, *filt, *fa, *fb, *bhat, *A, *c;
+  if ((e = alloc((void**)&pad, bytes)) != cudaSuccess) return e;
+  if ((e = alloc((void**)&a, bytes)) != cudaSuccess) return e;
+  if ((e = alloc((void**)&b, bytes)) != cudaSuccess) return e;
+  if ((e = alloc((void**)&filt, (size_t)M * sizeof(double2))) != cudaSuccess) return e;
+  if ((e = alloc((void**)&fa, (size_t)M * sizeof(double2))) != cudaSuccess) return e;
+  if ((e = alloc((void**)&fb, (size_t)M * sizeof(double2))) != cudaSuccess) return e;
+  f64_blue_filter_kernel<<<f64_blocks(M), 256, 0, st>>>(filt, n, M, sign);
+  if ((e = f64_fft(filt, fa, fb, 1, M, 1, -1, st, &bhat)) != cudaSuccess) return e;
+  f64_blue_pre_kernel<<<f64_blocks(outer * M * inner), 256, 0, st>>>(src, pad, outer, n, M, inner,
+                                                                      sign);
+  if ((e = f64_fft(pad, a, b, outer, M, inner, -1, st, &A)) != cudaSuccess) return e;
+  f64_blue_mul_kernel<<<f64_blocks(outer * M * inner), 256, 0, st>>>(A, bhat, outer, M, inner);
+  // inverse M-point transform: A is the source; results alternate between the other two arrays
+  double2* o1 = A == a ? b : a;
+  if ((e = f64_fft(A, o1, pad, outer, M, inner, +1, st, &c)) != cudaSuccess) return e;
+  double2* X = c == pad ? o1 : pad;       // n <= M: the first outer*n*inner entries of a free array
+  f64_blue_post_kernel<<<f64_blocks(outer * n * inner), 256, 0, st>>>(c, X, outer, n, M, inner, sign);
+  *result = X;
+  return cudaGetLastError();
 }
 
 }  // namespace pbk

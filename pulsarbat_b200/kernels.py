@@ -6,8 +6,8 @@ a dask ``map_blocks`` does -- reference transforms.py:49-50) or a
 :class:`~pulsarbat_b200.device.DeviceArray` (no copies; work is queued on torch's current
 stream).  complex128 input to the transforms the reference keeps in complex128 -- ``dedisperse``,
 ``fft``, ``stft`` / ``istft``, ``detect`` (dedispersion.py:125, fft.py:34, misc.py:47,87,
-core.py:766-774) -- is computed in FP64 (csrc/pbk_f64.cuh, power-of-two lengths; other lengths
-raise ``PbkUnsupported`` rather than being narrowed silently).  The remaining helpers
+core.py:766-774) -- is computed in FP64 (csrc/pbk_f64.cuh: Stockham passes, Bluestein for lengths
+that are not powers of two), never narrowed to complex64.  The remaining helpers
 (``phase_ramp``, ``mix``, ``stokes``, ``pol_basis``) compute complex128 input in complex64 and
 say so in their docstrings.
 """

@@ -494,9 +494,17 @@ def test_complex128_paths_match_the_oracle_to_double_precision():
     assert relerr(kernels.detect(xs), orc.to_intensity(xs)) < 1e-15
     assert relerr(kernels.detect(xs, stokes=True, downsample=4, freq_sum=3),
                   orc.stokes_I(xs).reshape(256, 4, 1, 3).sum(axis=(1, 3))) < 1e-14
-    # other lengths are refused, never narrowed
-    with pytest.raises(pb.PbkUnsupported, match="power-of-two"):
-        kernels.fft(np.zeros((12, 2), np.complex128))
-    with pytest.raises(pb.PbkUnsupported, match="power-of-two"):
-        kernels.dedisperse(np.zeros((1000, 2), np.complex128), dm=1.0, sample_rate_hz=1e6,
-                           chan_freq_hz=[1e9, 1.001e9], ref_freq_hz=1e9)
+    # any length (Bluestein in FP64): the reference's own tests use 4224, 4233, nperseg = 33
+    for n in (3, 33, 1000, 4233):
+        y = rng.standard_normal((2, n, 3)) + 1j * rng.standard_normal((2, n, 3))
+        assert relerr(kernels.fft(y, axis=1), scipy.fft.fft(y, axis=1)) < 1e-12
+        assert relerr(kernels.fft(y, axis=1, inverse=True), scipy.fft.ifft(y, axis=1)) < 1e-12
+    xo = rng.standard_normal((4224, 2)) + 1j * rng.standard_normal((4224, 2))
+    fo = orc.channel_freqs(600e6, 1e6, 2)
+    wo, a0, a1 = orc.coherent_dedispersion(xo, 2.0, sample_rate=1e6, center_freq=600e6)
+    go = kernels.dedisperse(xo, dm=2.0, sample_rate_hz=1e6, chan_freq_hz=fo, ref_freq_hz=600e6,
+                            crop=(a0, a1))
+    assert go.dtype == np.complex128 and relerr(go, wo) < 1e-11
+    x33 = rng.standard_normal((33 * 8, 2, 2)) + 1j * rng.standard_normal((33 * 8, 2, 2))
+    y33 = kernels.stft(x33, 33)
+    assert relerr(y33, orc.stft(x33, 33)) < 1e-12 and relerr(kernels.istft(y33, 33), x33) < 1e-12
