@@ -1064,7 +1064,8 @@ static int launch_one(pbk_plan* pl, const Pass& ps, const void* d_in, void* d_ou
     e = tma_launch(ps.a.log2L, ps.mode, p.a, tm, pl->d_ftab + ps.ftab_off, ps.ntiles,
                    pl->num_sms, st);
   } else if (ps.family >= 0 && aligned) {
-    if (ps.fast_load_transposed) p.a.load_kind = LOAD_TRANSP;
+    if (ps.fast_load_transposed)
+      p.a.load_kind = ps.a.load_kind == LOAD_PLANAR ? LOAD_TRANSP_PLANAR : LOAD_TRANSP;
     e = fast_launch(ps.family, ps.a.log2L, ps.mode, p.a, pl->d_ftab + ps.ftab_off,
                     tile_end < 0 ? ps.ntiles : tile_end, pl->num_sms, st);
   }
@@ -1319,6 +1320,9 @@ static int build_fft_plan(long long O, long long n, long long C, long long P, bo
     const long long cells = (det->split ? 2 * n : n) / det->fsum;     // output cells per segment
     a.mout = AddrMap{cells * det->pq, 0, 0, 0, 0, 0, 0};
     a.fsum_cells = cells;
+    // I == 2: a lane row of the tile is a contiguous run of L rows of the scratch array (16 B per
+    // row), so the tile is read coalesced and transposed through shared memory
+    if (!getenv("PBK_NO_TRANSP_DETECT")) last.fast_load_transposed = true;
     pl->out_bytes = (size_t)O * cells * det->pq * 4;
     pl->det_nseg = O;
     pl->det_cells = cells;

@@ -156,7 +156,9 @@ enum { LK_C64 = 0, LK_I8 = 1, LK_PLANAR = 2,
        LK_TRANSP = 3 /* user complex64 where every lane pair owns a contiguous run of rows
                         (ISTFT input): transposed through shared memory */,
        LK_U4 = 4 /* packed 4+4-bit complex: two bytes per lane pair */,
-       LK_U2 = 5 /* packed 2+2-bit complex: one byte per lane pair */ };
+       LK_U2 = 5 /* packed 2+2-bit complex: one byte per lane pair */,
+       LK_TRANSP_PLANAR = 6 /* scratch (pair-planar) where every lane pair owns a contiguous run of
+                               rows: the last level of an array with ONE lane pair per row */ };
 // bits per complex input element
 __host__ __device__ constexpr int lk_bits(int lk) {
   return lk == LK_I8 ? 16 : lk == LK_U4 ? 8 : lk == LK_U2 ? 4 : 64;
@@ -413,10 +415,13 @@ __device__ __forceinline__ void fwd_first(const FastTile& T, float4* tile, const
 // while the pairs are far apart (ISTFT input, misc.py:81-86): the tile is copied in with
 // consecutive threads on consecutive rows, transposed through shared memory, then the stage runs
 // from there.  `fxor` is the ifftshift (row index xor) of the reference's np.fft.ifftshift.
-template <class C, bool SIGNINV>
+// PLANAR: the input is the pair-planar scratch array and pair q of the tile starts pair_bytes * q
+// after pair 0 (lane rows of the last level, see LK_TRANSP_PLANAR)
+template <class C, bool SIGNINV, bool PLANAR = false>
 __device__ __forceinline__ void fwd_first_transposed(const PassArgs& p, const char* gin_tile,
                                                      float4* tile, const float2* tws, int tid,
-                                                     unsigned rowbytes_in) {
+                                                     unsigned rowbytes_in,
+                                                     long long pair_bytes = 0) {
   constexpr int R = C::radix(0), S = C::stride(0);
   constexpr int TASKS = S * C::PW;
   static_assert(TASKS % C::NT == 0, "whole first-stage tasks per thread");
@@ -425,7 +430,8 @@ __device__ __forceinline__ void fwd_first_transposed(const PassArgs& p, const ch
   for (int j = tid; j < C::PW * C::L; j += C::NT) {
     const int pair = j >> C::LOG2L, kk = j & (C::L - 1);
     const int cp = 2 * pair;
-    const long long po = ((long long)(cp / p.P) * p.min.a_c + (cp % p.P) * p.min.a_p) * 8;
+    const long long po = PLANAR ? pair * pair_bytes
+                                : ((long long)(cp / p.P) * p.min.a_c + (cp % p.P) * p.min.a_p) * 8;
     tile[pair * C::L + (kk ^ (pair & 7))] =
         __ldcg(reinterpret_cast<const float4*>(gin_tile + po + (unsigned long long)kk * rowbytes_in));
   }
@@ -438,8 +444,13 @@ __device__ __forceinline__ void fwd_first_transposed(const PassArgs& p, const ch
     for (int i = 0; i < R; ++i) {
       const int row = (b + i * S) ^ p.fxor;
       const float4 t = tile[pr * C::L + (row ^ (pr & 7))];
-      v[it][i].re = make_float2(t.x, t.z);
-      v[it][i].im = make_float2(t.y, t.w);
+      if (PLANAR) {
+        v[it][i].re = make_float2(t.x, t.y);
+        v[it][i].im = make_float2(t.z, t.w);
+      } else {
+        v[it][i].re = make_float2(t.x, t.z);
+        v[it][i].im = make_float2(t.y, t.w);
+      }
     }
   }
   __syncthreads();   // every thread holds its inputs: the tile buffer can take the stage output
@@ -783,6 +794,9 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
     if (MODE == MODE_FWD) {
       if constexpr (LOADK == LK_TRANSP)
         fwd_first_transposed<C, SIGNINV>(p, T.gin - off_in, tile, tws, tid, rb_in);
+      else if constexpr (LOADK == LK_TRANSP_PLANAR)
+        fwd_first_transposed<C, SIGNINV, true>(p, T.gin - off_in, tile, tws, tid, rb_in,
+                                               row_in * 8);
       else
         fwd_first<C, LOADK, SIGNINV>(T, tile, tws, tid, rb_in);
       __syncthreads();

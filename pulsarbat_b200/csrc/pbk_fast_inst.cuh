@@ -82,9 +82,15 @@ static cudaError_t cfg_launch(int mode, const PassArgs& a, const float2* d_table
         return cfg_launch_mode<MODE_FWD, C, LK_C64, EPI_SCRATCH, false, true>(a, d_tables, ntiles,
                                                                               num_sms, st);
       }
-      if (a.final_epi && a.fsum_log2 > 0)   // channelizer with a detected, frequency-summed output
+      if (a.final_epi && a.fsum_log2 > 0) {  // channelizer with a detected, frequency-summed output
+        // one lane pair per row: every lane row of the tile is a contiguous run of L rows in the
+        // scratch array, read coalesced and transposed through shared memory
+        if (a.load_kind == LOAD_TRANSP_PLANAR)
+          return cfg_launch_variant<MODE_FWD, C, LK_TRANSP_PLANAR, EPI_INTENSITY, false, true>(
+              a, d_tables, ntiles, num_sms, st);
         return cfg_launch_variant<MODE_FWD, C, LK_PLANAR, EPI_INTENSITY, false, true>(
             a, d_tables, ntiles, num_sms, st);
+      }
       if (a.final_epi) {   // last pass of a forward FFT / STFT plan: scaled natural-order output
         if (a.load_kind == LOAD_PLANAR)
           return cfg_launch_mode<MODE_FWD, C, LK_PLANAR, EPI_C64>(a, d_tables, ntiles, num_sms, st);

@@ -35,7 +35,8 @@ namespace pbk {
 enum { MODE_FWD = 0, MODE_MID = 1, MODE_INV = 2 };
 enum { LOAD_C64 = 0, LOAD_I8X2 = 1, LOAD_PLANAR = 2, LOAD_F32 = 3 /* real input, im = 0 */,
        LOAD_TRANSP = 4 /* fast kernels only: complex64 input transposed through shared memory */,
-       LOAD_U4X2 = 5 /* packed 4+4-bit complex */, LOAD_U2X2 = 6 /* packed 2+2-bit complex */ };
+       LOAD_U4X2 = 5 /* packed 4+4-bit complex */, LOAD_U2X2 = 6 /* packed 2+2-bit complex */,
+       LOAD_TRANSP_PLANAR = 7 /* fast kernels only: scratch input transposed through shared memory */ };
 
 // bits per complex input element of a load kind
 __host__ __device__ constexpr int load_bits(int kind) {
