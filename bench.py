@@ -574,8 +574,27 @@ def run_b200(args, w):
         stream(ke)
         torch.cuda.synchronize()
         dts = max_over_ranks(time.perf_counter() - t0)
+        # what the HOST can deliver: every rank copies the same page-locked block to its GPU at
+        # the same time, nothing else running (profiles/r02_h2d_probe_8gpu.log: on this pool's
+        # 8-GPU boxes GPUs 0-3 share ~115 GB/s and all eight ~225 GB/s whatever the allocation
+        # kind -- a platform ceiling below 8 x 55 GB/s that the end-to-end number cannot exceed)
+        dbuf = torch.empty(hx.shape, dtype=hx.dtype, device=dev)
+        dbuf.copy_(hx, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            dbuf.copy_(hx, non_blocking=True)
+        torch.cuda.synchronize()
+        dth = max_over_ranks(time.perf_counter() - t0)
+        host_gbs = world * 3 * hnp.nbytes / dth / 1e9
+        del dbuf
         e2e = {"value": world * nsamp * ke / dts / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": int(hnp.nbytes), "d2h_bytes_per_step": rbytes,
+               "host_limit_gbs": host_gbs,
+               "host_limit_value": host_gbs / (hnp.nbytes / nsamp),
+               "host_limit_note": "aggregate rate of concurrent cudaMemcpyAsync H2D from page-locked "
+                                  "memory on all ranks (bare copies, measured in this run) and "
+                                  "the Gsamples/s it allows at 8 B per sample",
                "steps": ke, "ms_per_step": dts / ke * 1e3,
                # what a numpy user gets from ordinary pageable memory, one synchronous call per
                # block through the library's bounce pipeline (the headline e2e streams the SAME
@@ -833,6 +852,10 @@ def extra_cfg4(ctx, steps=10):
         cnt = pb.DeviceArray(torch.zeros((nbin,), dtype=torch.int64, device=dev))
     # ---- collective part: the same sequence of all-reduces on every rank, whatever happened above
     live = ok == 1.0 and err is None
+    for _ in range(2):      # untimed: NCCL sets up its channels for this message size on first use
+        sharding.allreduce_profiles(prof, cnt)
+    if live:                # (the warm-up reductions scaled the profile: start from a fresh one)
+        _, prof, cnt = local_step()
     _sync_all(ctx)
     e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     e[0].record()
