@@ -24,6 +24,15 @@ KEEP = [
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    # where the warps wait (per issued instruction)
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed",
 ]
 MODES = {"0": "FWD", "1": "MID", "2": "INV"}
 
@@ -44,7 +53,7 @@ def main(raw_csv, out_txt, traffic_json, workload, header=""):
             ("fast_pass_kernel" in r[col["Kernel Name"]] or "pass_kernel" in r[col["Kernel Name"]]
              or "downsample" in r[col["Kernel Name"]])]
     # one step = from a first-pass kernel to the next first-pass kernel: keep the last step
-    firsts = [i for i, r in enumerate(mine) if "fast_pass_kernel<0" in r[col["Kernel Name"]].replace("(int)", "")
+    firsts = [i for i, r in enumerate(mine) if "_pass_kernel<0" in r[col["Kernel Name"]].replace("(int)", "")
               and i + 1 < len(mine)]
     # the first forward pass of a step is followed by another forward pass; steps are 5-6 launches
     step_len = None
