@@ -23,6 +23,7 @@
 #include "../../include/pbk.h"
 #include "pbk_fast_launch.h"
 #include "pbk_tma_launch.h"
+#include "pbk_l2pipe_launch.h"
 #include "pbk_blue.cuh"
 #include "pbk_f64.cuh"
 #include "pbk_fft.cuh"
@@ -155,6 +156,10 @@ struct pbk_plan {
   int64_t out_rows = 0, row_elems = 0, elem_bytes = 0, full_rows = 0;
   int launches = 0;
   // L2-blocked schedule of the three middle passes of a 3-level plan (see run_passes)
+  // the three middle passes as one persistent L2-resident pipeline (pbk_l2pipe.cuh)
+  bool l2pipe = false;
+  unsigned* d_l2sync = nullptr;  // ticket | err | done[nblocks][2]
+  int l2pipe_blocks = 0;
   int l2_chunks = 0;            // 0 = plain pass-after-pass schedule
   long long l2_tiles[3] = {0, 0, 0};   // tiles per chunk of passes 1, 2, 3
   int segments = 0;             // timed segments per execution (pbk_plan_profile_read)
@@ -624,6 +629,32 @@ static int upload_tables(pbk_plan* pl, TableSet& ts) {
 }
 
 static void setup_l2_blocking(pbk_plan* pl, long long block_bytes, int nblocks);
+
+// $PBK_L2PIPE: 1 = run FWD(level 2) -> MID(level 3) -> INV(level 2) of a 3-level plan as the one
+// persistent kernel of pbk_l2pipe.cuh when the shapes are the instantiated ones (2^8 / 2^6 points,
+// wide tiles, generated chirp); unset / 0 = three launches.
+static bool l2pipe_wanted() {
+  const char* e = getenv("PBK_L2PIPE");
+  return e && strcmp(e, "0") != 0;
+}
+static int setup_l2pipe(pbk_plan* pl, int nblocks) {
+  pl->l2pipe = false;
+  if (!l2pipe_wanted() || pl->passes.size() != 5 || pl->l2_chunks > 0) return PBK_OK;
+  const Pass &a = pl->passes[1], &b = pl->passes[2], &c = pl->passes[3];
+  auto plain = [](const Pass& ps) {
+    return ps.family >= 0 && ps.in_role == ROLE_SCRATCH && ps.out_role == ROLE_SCRATCH &&
+           ps.a.load_kind == LOAD_PLANAR && ps.a.store_planar && !ps.a.final_epi && !ps.signinv;
+  };
+  if (!plain(a) || !plain(b) || !plain(c)) return PBK_OK;
+  if (a.mode != MODE_FWD || b.mode != MODE_MID || c.mode != MODE_INV) return PBK_OK;
+  if (a.a.log2L != 8 || c.a.log2L != 8 || b.a.log2L != 6 || b.a.split) return PBK_OK;
+  if (a.finfo.log2pw != 4 || b.finfo.log2pw != 5) return PBK_OK;
+  if (a.a.I % 64 || a.a.I % a.a.P || a.ntiles % nblocks || b.ntiles % (2ll * nblocks)) return PBK_OK;
+  CUDA_TRY(cudaMalloc(&pl->d_l2sync, (size_t)(2 + 2 * nblocks) * sizeof(unsigned)));
+  pl->l2pipe = true;
+  pl->l2pipe_blocks = nblocks;
+  return PBK_OK;
+}
 static void blue_free(BlueState* b);
 static int blue_exec(pbk_plan* pl, const void* d_in, void* d_out, const void* d_chirp,
                      cudaStream_t st);
@@ -996,6 +1027,7 @@ static int dedisp_plan_create_impl(const pbk_dedisp_desc* d, const RampSpec* ram
                                          : (d->sample_rate_hz / (double)N) / d->ref_freq_hz;
   }
   if (m == 3) setup_l2_blocking(pl, (N >> l[0]) * I * 8, 1 << l[0]);
+  if (m == 3 && (rc = setup_l2pipe(pl, 1 << l[0])) != PBK_OK) return cleanup(rc);
   // Out-of-place intermediate passes: a pass that reads and writes the same scratch array is
   // 2-3 % slower than one that writes another array (cfg2: 1.505 -> 1.463 ms and 1.476 -> 1.426 ms,
   // profiles/r01_pingpong_scratch.log), so when the scratch is small against the device memory
@@ -1014,7 +1046,10 @@ static int dedisp_plan_create_impl(const pbk_dedisp_desc* d, const RampSpec* ram
   }
   if (pl->l2_chunks == 0) setup_tma(pl);
   const int ds = (d->downsample > 1 && !pl->fused_tsum) ? 1 : 0;
-  if (pl->l2_chunks > 0) {
+  if (pl->l2pipe) {
+    pl->launches = 3 + ds;
+    pl->segments = 3 + ds;
+  } else if (pl->l2_chunks > 0) {
     pl->launches = 2 + 3 * pl->l2_chunks + ds;
     pl->segments = 3 + ds;
   } else {
@@ -1087,6 +1122,37 @@ static int run_passes(pbk_plan* pl, const void* d_in, void* d_out, const void* d
   int seg = 0, rc;
   const size_t np = pl->passes.size();
   const bool aligned = ((((uintptr_t)d_in | (uintptr_t)d_out | (uintptr_t)pl->scratch) & 15) == 0);
+  if (pl->l2pipe && aligned) {
+    prof_mark(pl, seg++, st);
+    if ((rc = launch_one(pl, pl->passes[0], d_in, d_out, d_chirp, 0, -1, st, 0)) != PBK_OK) return rc;
+    prof_mark(pl, seg++, st);
+    PassArgs pa[3];
+    for (int j = 0; j < 3; ++j) {      // the pointers launch_one would give passes 1..3
+      const Pass& ps = pl->passes[1 + j];
+      pa[j] = ps.a;
+      void* buf[2] = {pl->scratch, pl->scratch2 ? pl->scratch2 : pl->scratch};
+      pa[j].in = buf[pl->scratch2 ? (j + 2) & 1 : 0];
+      pa[j].out = buf[pl->scratch2 ? (j + 1) & 1 : 0];
+      pa[j].tile0 = 0;
+    }
+    const size_t sync_bytes = (size_t)(2 + 2 * pl->l2pipe_blocks) * sizeof(unsigned);
+    if (cudaMemsetAsync(pl->d_l2sync, 0, sync_bytes, st) != cudaSuccess)
+      return fail(PBK_ERR_CUDA, "l2 pipeline reset: %s", cudaGetErrorString(cudaGetLastError()));
+    L2PipeArgs q;
+    q.nblocks = pl->l2pipe_blocks;
+    q.tiles_a = pl->passes[1].ntiles / q.nblocks;
+    q.tiles_b = pl->passes[2].ntiles / q.nblocks;
+    q.ticket = pl->d_l2sync;
+    q.err = pl->d_l2sync + 1;
+    q.done = pl->d_l2sync + 2;
+    cudaError_t e = l2pipe_launch_l8_l6(pa[0], pa[1], pa[2], pl->d_ftab + pl->passes[1].ftab_off,
+                                        pl->d_ftab + pl->passes[2].ftab_off, q, pl->num_sms, st);
+    if (e != cudaSuccess) return fail(PBK_ERR_CUDA, "l2 pipeline launch: %s", cudaGetErrorString(e));
+    prof_mark(pl, seg++, st);
+    if ((rc = launch_one(pl, pl->passes[4], d_in, d_out, d_chirp, 0, -1, st, 4)) != PBK_OK) return rc;
+    prof_mark(pl, seg, st);
+    return PBK_OK;
+  }
   if (pl->l2_chunks > 0 && aligned) {
     prof_mark(pl, seg++, st);
     if ((rc = launch_one(pl, pl->passes[0], d_in, d_out, d_chirp, 0, -1, st)) != PBK_OK) return rc;
@@ -1757,6 +1823,7 @@ extern "C" void pbk_plan_destroy(pbk_plan* pl) {
   cudaFree(pl->d_ramp_zero);
   cudaFree(pl->d_tmpf);
   cudaFree(pl->d_segbins);
+  cudaFree(pl->d_l2sync);
   cudaFree(pl->h_din);
   cudaFree(pl->h_dout);
   cudaFree(pl->h_dchirp);
@@ -1789,7 +1856,7 @@ extern "C" int pbk_plan_describe(const pbk_plan* pl, char* buf, size_t n) {
     const char* mode = ps.mode == MODE_FWD ? "FWD" : ps.mode == MODE_MID ? "MID" : "INV";
     int w;
     // segments are separated by ';'; the passes of an L2-blocked group are joined by '+'
-    const bool blocked = pl->l2_chunks > 0;
+    const bool blocked = pl->l2_chunks > 0 || pl->l2pipe;
     const char* sep = i == 0 ? "" : (blocked && (i == 2 || i == 3)) ? "+" : ";";
     if (ps.family >= 0)
       w = snprintf(buf + off, n - off, "%s%s:L=2^%d:%s:W=%d:tiles=%lld:threads=%d%s%s", sep,
@@ -1802,7 +1869,10 @@ extern "C" int pbk_plan_describe(const pbk_plan* pl, char* buf, size_t n) {
                    ps.grid, kThreads);
     if (w < 0) break;
     off += (size_t)w;
-    if (blocked && i == 3 && off + 1 < n) {
+    if (pl->l2pipe && i == 3 && off + 1 < n) {
+      w = snprintf(buf + off, n - off, ":l2pipe=%d", pl->l2pipe_blocks);
+      if (w > 0) off += (size_t)w;
+    } else if (blocked && i == 3 && off + 1 < n) {
       w = snprintf(buf + off, n - off, ":l2chunks=%d", pl->l2_chunks);
       if (w > 0) off += (size_t)w;
     }
