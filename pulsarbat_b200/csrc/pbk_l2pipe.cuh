@@ -36,9 +36,12 @@ struct NamedSync {   // named barrier `id` over NT threads (id 0 is __syncthread
 };
 
 // ---- one tile of each pass kind (wide tiles, LK_PLANAR in, EPI_SCRATCH out) -------------------
-template <class C, class Sync>
+// `hook()` runs on every thread right after the tile's first barrier (the place where the plain
+// kernels prepare their next tile record): thread 0 prepares the next work item there
+template <class C, class Sync, class Hook>
 __device__ __forceinline__ void l2p_tile_fwd(const PassArgs& p, const FastTile& T, float4* tile,
-                                             const float2* tws, float4* G4, int tid, Sync sync) {
+                                             const float2* tws, float4* G4, int tid, Sync sync,
+                                             Hook hook) {
   constexpr int RL = C::RL;
   constexpr int LTASKS = (C::L / RL) * C::PW;
   constexpr int LITERS = (LTASKS + C::NT - 1) / C::NT;
@@ -50,6 +53,7 @@ __device__ __forceinline__ void l2p_tile_fwd(const PassArgs& p, const FastTile& 
   }
   fwd_first<C, LK_PLANAR, false>(T, tile, tws, tid, rb_in);
   sync();
+  hook();
   mid_stages<C, false, false>(tile, tws, tid, sync);
 #pragma unroll
   for (int it = 0; it < LITERS; ++it) {
@@ -67,9 +71,9 @@ __device__ __forceinline__ void l2p_tile_fwd(const PassArgs& p, const FastTile& 
   }
 }
 
-template <class C, bool TWOCH, class Sync>
+template <class C, bool TWOCH, class Sync, class Hook>
 __device__ __forceinline__ void l2p_tile_mid(const PassArgs& p, const FastTile& T, float4* tile,
-                                             const float2* tws, int tid, Sync sync) {
+                                             const float2* tws, int tid, Sync sync, Hook hook) {
   constexpr int RL = C::RL;
   constexpr int LTASKS = (C::L / RL) * C::PW;
   constexpr int LITERS = (LTASKS + C::NT - 1) / C::NT;
@@ -77,6 +81,7 @@ __device__ __forceinline__ void l2p_tile_mid(const PassArgs& p, const FastTile& 
   const unsigned rb_in = (unsigned)(p.min.a_row * 8), rb_out = (unsigned)(p.mout.a_row * 8);
   fwd_first<C, LK_PLANAR>(T, tile, tws, tid, rb_in);
   sync();
+  hook();
   mid_stages<C, false, false>(tile, tws, tid, sync);
 #pragma unroll
   for (int it = 0; it < LITERS; ++it) {
@@ -97,9 +102,10 @@ __device__ __forceinline__ void l2p_tile_mid(const PassArgs& p, const FastTile& 
   inv_last<C, EPI_SCRATCH>(T, tile, tws, tid, rb_out);
 }
 
-template <class C, class Sync>
+template <class C, class Sync, class Hook>
 __device__ __forceinline__ void l2p_tile_inv(const PassArgs& p, const FastTile& T, float4* tile,
-                                             const float2* tws, float4* G4, int tid, Sync sync) {
+                                             const float2* tws, float4* G4, int tid, Sync sync,
+                                             Hook hook) {
   constexpr int RL = C::RL;
   constexpr int LTASKS = (C::L / RL) * C::PW;
   constexpr int LITERS = (LTASKS + C::NT - 1) / C::NT;
@@ -110,6 +116,7 @@ __device__ __forceinline__ void l2p_tile_inv(const PassArgs& p, const FastTile& 
     G4[tid] = make_float4(g.x, g.y, g.y, g.x);
   }
   sync();
+  hook();
 #pragma unroll
   for (int it = 0; it < LITERS; ++it) {
     const int tau = tid + it * C::NT;
@@ -146,6 +153,15 @@ __device__ __forceinline__ FastTile l2p_context(const PassArgs& p, const TileInf
   return T;
 }
 
+// a decoded ticket, prepared by thread 0 one work item ahead
+struct L2Item {
+  long long t;        // ticket (>= total: no more work)
+  long long idx;      // work item within (block, pass)
+  int phase, blk;
+  int valid;          // 0: a ticket that maps to nothing (pipeline fill / drain, uneven passes)
+  int dep_ok;         // the dependency counter had already reached its target when it was polled
+};
+
 template <class CA, class CB, bool TWOCH>
 __global__ void __launch_bounds__(CA::NT, 2)
 l2pipe_kernel(const __grid_constant__ PassArgs pa, const __grid_constant__ PassArgs pb,
@@ -158,8 +174,8 @@ l2pipe_kernel(const __grid_constant__ PassArgs pa, const __grid_constant__ PassA
   float2* tws_a = reinterpret_cast<float2*>(tile + (size_t)CA::L * CA::PW);
   float2* tws_b = tws_a + CA::TW_PAD;
   float4* G4 = reinterpret_cast<float4*>(tws_b + CB::TW_PAD);
-  TileInfo* sinfo = reinterpret_cast<TileInfo*>(G4 + CA::RL);     // [2]
-  __shared__ long long s_ticket;
+  TileInfo* sinfo = reinterpret_cast<TileInfo*>(G4 + CA::RL);     // [2]: the NEXT item's tiles
+  __shared__ L2Item snext;
   const int tid = threadIdx.x;
   for (int i = tid; i < CA::TW_TOTAL; i += CA::NT) tws_a[i] = tab_a[i];
   for (int i = tid; i < CB::TW_TOTAL; i += CA::NT) tws_b[i] = tab_b[i];
@@ -170,55 +186,114 @@ l2pipe_kernel(const __grid_constant__ PassArgs pa, const __grid_constant__ PassA
   const long long total = (long long)(q.nblocks + 2) * per_slot;
   const int g = tid / CB::NT, gtid = tid - g * CB::NT;       // half-CTA groups of pass B
 
+  // ---- thread 0 only: ticket prefetch, deferred publication, preparation of the next item ----
+  unsigned tnext = 0;                    // the ticket after the prepared one (atomic in flight)
+  int pub_blk = -1, pub_phase = 0;       // finished item whose completion is not published yet
+  unsigned pub_cnt = 0;
+  auto publish = [&]() {                 // the item's stores precede a CTA barrier this thread passed
+    if (pub_blk >= 0) {
+      __threadfence();
+      atomicAdd(q.done + 2 * pub_blk + pub_phase, pub_cnt);
+      pub_blk = -1;
+    }
+  };
+  auto dep_ptr = [&](int phase, int blk) { return q.done + 2 * blk + (phase - 1); };
+  auto dep_need = [&](int phase) { return (unsigned)(phase == 1 ? q.tiles_a : q.tiles_b); };
+  auto prepare = [&](long long t) {      // decode ticket t into snext / sinfo (non-blocking)
+    L2Item it;
+    it.t = t;
+    it.valid = 0;
+    it.dep_ok = 1;
+    it.phase = 0; it.blk = 0; it.idx = 0;
+    if (t < total) {
+      const int slot = (int)(t / per_slot);
+      const long long r = t - (long long)slot * per_slot;
+      it.phase = (int)(r % 3);
+      it.idx = r / 3;
+      it.blk = slot - it.phase;
+      it.valid = it.blk >= 0 && it.blk < q.nblocks &&
+                 it.idx < (it.phase == 1 ? items_b : q.tiles_a);
+      if (it.valid) {
+        if (it.phase > 0) {
+          it.dep_ok = *(const volatile unsigned*)dep_ptr(it.phase, it.blk) >= dep_need(it.phase);
+          __threadfence();   // acquire; the CTA barrier before the tile extends it to every thread
+        }
+        if (it.phase == 0)
+          fast_tile_info<CA, EPI_SCRATCH>(pa, (long long)it.blk * q.tiles_a + it.idx, sinfo[0], 64, 8);
+        else if (it.phase == 2)
+          fast_tile_info<CA, EPI_SCRATCH>(pc, (long long)it.blk * q.tiles_a + it.idx, sinfo[0], 64, 8);
+        else
+          for (int h = 0; h < 2; ++h)
+            fast_tile_info<CB, EPI_SCRATCH>(pb, (long long)it.blk * q.tiles_b + 2 * it.idx + h,
+                                            sinfo[h], 64, 8);
+      }
+    }
+    snext = it;
+  };
+  if (tid == 0) {
+    const unsigned t0 = atomicAdd(q.ticket, 1u);
+    tnext = atomicAdd(q.ticket, 1u);
+    prepare(t0);
+  }
+
   for (;;) {
-    __syncthreads();                       // tile buffer, G, records and s_ticket are free again
-    if (tid == 0) s_ticket = atomicAdd(q.ticket, 1u);
-    __syncthreads();
-    const long long t = s_ticket;
-    if (t >= total) break;
-    const int slot = (int)(t / per_slot);
-    const long long r = t - (long long)slot * per_slot;
-    const int phase = (int)(r % 3);
-    const long long idx = r / 3;
-    const int blk = slot - phase;
-    if (blk < 0 || blk >= q.nblocks) continue;
-    if (idx >= (phase == 1 ? items_b : q.tiles_a)) continue;
-    if (tid == 0) {
-      if (phase > 0) {     // every tile of the previous pass of this block has been written
-        const volatile unsigned* d = q.done + 2 * blk + (phase - 1);
-        const unsigned need = (unsigned)(phase == 1 ? q.tiles_a : q.tiles_b);
+    __syncthreads();     // snext / sinfo are ready; tile buffer and G are free
+    const L2Item cur = snext;
+    if (cur.t >= total) break;
+    if (!cur.valid) {    // nothing to do for this ticket: prepare the next one (all have read snext)
+      __syncthreads();
+      if (tid == 0) {
+        publish();
+        const unsigned t2 = tnext;
+        tnext = atomicAdd(q.ticket, 1u);
+        prepare(t2);
+      }
+      continue;
+    }
+    TileInfo ti = sinfo[cur.phase == 1 ? g : 0];
+    // pass-B tiles only meet at half-CTA barriers: make sure the other half has read the records
+    // before thread 0 rewrites them in its hook
+    if (cur.phase == 1) __syncthreads();
+    if (!cur.dep_ok) {   // rare: the producer pass of this block was not finished at prefetch time
+      if (tid == 0) {
+        publish();       // nothing this CTA still owes may be what the producers wait for
+        const volatile unsigned* d = dep_ptr(cur.phase, cur.blk);
+        const unsigned need = dep_need(cur.phase);
         unsigned spins = 0;
         while (*d < need) {
-          __nanosleep(64);
+          __nanosleep(32);
           if (++spins > (1u << 24)) { atomicExch(q.err, 1u); break; }
         }
         __threadfence();
       }
-      if (phase == 0)
-        fast_tile_info<CA, EPI_SCRATCH>(pa, (long long)blk * q.tiles_a + idx, sinfo[0], 64, 8);
-      else if (phase == 2)
-        fast_tile_info<CA, EPI_SCRATCH>(pc, (long long)blk * q.tiles_a + idx, sinfo[0], 64, 8);
-    }
-    if (phase == 1 && gtid == 0)
-      fast_tile_info<CB, EPI_SCRATCH>(pb, (long long)blk * q.tiles_b + 2 * idx + g, sinfo[g], 64, 8);
-    __syncthreads();
-    if (phase == 0) {
-      const FastTile T = l2p_context<CA>(pa, sinfo[0], tid & (CA::PW - 1));
-      l2p_tile_fwd<CA>(pa, T, tile, tws_a, G4, tid, CtaSync());
-    } else if (phase == 2) {
-      const FastTile T = l2p_context<CA>(pc, sinfo[0], tid & (CA::PW - 1));
-      l2p_tile_inv<CA>(pc, T, tile, tws_a, G4, tid, CtaSync());
-    } else {
-      const FastTile T = l2p_context<CB>(pb, sinfo[g], gtid & (CB::PW - 1));
-      l2p_tile_mid<CB, TWOCH>(pb, T, tile + (size_t)g * CB::L * CB::PW, tws_b, gtid,
-                              NamedSync<CB::NT>{1 + g});
-    }
-    if (phase < 2) {       // publish: this thread's stores, then the block's counter
-      __threadfence();
       __syncthreads();
-      if (tid == 0) atomicAdd(q.done + 2 * blk + phase, phase == 1 ? 2u : 1u);
+    }
+    auto hook = [&]() {  // after the tile's first barrier: every thread holds cur / ti in registers
+      if (tid == 0) {
+        publish();                           // the PREVIOUS item: its stores are long since out
+        const unsigned t2 = tnext;
+        tnext = atomicAdd(q.ticket, 1u);     // (returns while this tile is being computed)
+        prepare(t2);
+      }
+    };
+    if (cur.phase == 0) {
+      const FastTile T = l2p_context<CA>(pa, ti, tid & (CA::PW - 1));
+      l2p_tile_fwd<CA>(pa, T, tile, tws_a, G4, tid, CtaSync(), hook);
+    } else if (cur.phase == 2) {
+      const FastTile T = l2p_context<CA>(pc, ti, tid & (CA::PW - 1));
+      l2p_tile_inv<CA>(pc, T, tile, tws_a, G4, tid, CtaSync(), hook);
+    } else {
+      const FastTile T = l2p_context<CB>(pb, ti, gtid & (CB::PW - 1));
+      l2p_tile_mid<CB, TWOCH>(pb, T, tile + (size_t)g * CB::L * CB::PW, tws_b, gtid,
+                              NamedSync<CB::NT>{1 + g}, hook);
+    }
+    if (tid == 0 && cur.phase < 2) {   // published one item later (or before this CTA blocks / exits)
+      pub_blk = cur.blk;
+      pub_phase = cur.phase;
+      pub_cnt = cur.phase == 1 ? 2u : 1u;
     }
   }
+  if (tid == 0) publish();
 }
 
 template <class CA, class CB>
