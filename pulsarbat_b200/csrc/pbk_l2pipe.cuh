@@ -7,7 +7,7 @@
 // launches over the whole array they cost three HBM round trips; here their tiles are handed out
 // by a ticket counter in a software-pipelined order
 //     A(b0) | A(b1) B(b0) | A(b2) B(b1) C(b0) | A(b3) B(b2) C(b1) | ...
-// (A, B, C = the three passes, interleaved tile by tile inside a slot) so that what pass A writes
+// (A, B, C = the three passes; inside a slot each pass is one run of tickets) so that what pass A writes
 // for block b is read by pass B, and what B writes by C, while it is still in L2: HBM sees one
 // read of the block (A) and one write (C).  Dependencies are per (block, pass) completion counters
 // in global memory: a tile of pass B waits until every tile of pass A of its block has been
@@ -181,8 +181,7 @@ l2pipe_kernel(const __grid_constant__ PassArgs pa, const __grid_constant__ PassA
   for (int i = tid; i < CB::TW_TOTAL; i += CA::NT) tws_b[i] = tab_b[i];
 
   const long long items_b = q.tiles_b / 2;
-  const long long per_phase = q.tiles_a > items_b ? q.tiles_a : items_b;
-  const long long per_slot = 3 * per_phase;
+  const long long per_slot = 2 * q.tiles_a + items_b;
   const long long total = (long long)(q.nblocks + 2) * per_slot;
   const int g = tid / CB::NT, gtid = tid - g * CB::NT;       // half-CTA groups of pass B
 
@@ -206,13 +205,15 @@ l2pipe_kernel(const __grid_constant__ PassArgs pa, const __grid_constant__ PassA
     it.dep_ok = 1;
     it.phase = 0; it.blk = 0; it.idx = 0;
     if (t < total) {
+      // a slot is A(slot), then B(slot - 1), then C(slot - 2), each pass as one run of tickets: by
+      // the time the first B ticket of a block is taken, the last A ticket of that block was taken
+      // two pass-runs (several waves of CTAs) earlier, so the dependency polls almost never wait
       const int slot = (int)(t / per_slot);
       const long long r = t - (long long)slot * per_slot;
-      it.phase = (int)(r % 3);
-      it.idx = r / 3;
+      it.phase = r < q.tiles_a ? 0 : r < q.tiles_a + items_b ? 1 : 2;
+      it.idx = r - (it.phase == 0 ? 0 : it.phase == 1 ? q.tiles_a : q.tiles_a + items_b);
       it.blk = slot - it.phase;
-      it.valid = it.blk >= 0 && it.blk < q.nblocks &&
-                 it.idx < (it.phase == 1 ? items_b : q.tiles_a);
+      it.valid = it.blk >= 0 && it.blk < q.nblocks;
       if (it.valid) {
         if (it.phase > 0) {
           it.dep_ok = *(const volatile unsigned*)dep_ptr(it.phase, it.blk) >= dep_need(it.phase);
