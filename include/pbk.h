@@ -16,7 +16,7 @@
  *    plan serialises its own executions).  *_device entry points take DEVICE pointers on the
  *    plan's device, enqueue on `stream` (a cudaStream_t cast to void*, NULL = legacy default
  *    stream) and do not synchronise.  A plan owns its scratch arrays (one, or two of N*C*P*8
- *    bytes each when that is at most 1/8 of the device memory; pbk_plan_info reports the total):
+ *    bytes each when that is at most 1/5 of the device memory; pbk_plan_info reports the total):
  *    executions of the same plan must be ordered on the device (same stream, or events between
  *    streams).
  *  - There is no CPU fallback: without a CUDA device every call fails with PBK_ERR_CUDA.

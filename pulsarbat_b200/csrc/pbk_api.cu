@@ -1031,7 +1031,8 @@ static int dedisp_plan_create_impl(const pbk_dedisp_desc* d, const RampSpec* ram
   // Out-of-place intermediate passes: a pass that reads and writes the same scratch array is
   // 2-3 % slower than one that writes another array (cfg2: 1.505 -> 1.463 ms and 1.476 -> 1.426 ms,
   // profiles/r01_pingpong_scratch.log), so when the scratch is small against the device memory
-  // (<= 1/8 of it, and 4x its size still free) a second one is allocated and pass i reads
+  // (<= 1/5 of it, and 3x its size still free: a 34 GB cfg5 shard qualifies on a 180 GB part) a
+  // second one is allocated and pass i reads
   // buffer (i-1)&1 and writes buffer i&1.  PBK_NO_PINGPONG=1 keeps the passes in place.
   if (pl->scratch && pl->l2_chunks == 0 && !getenv("PBK_NO_PINGPONG")) {
     bool any = false;
@@ -1039,7 +1040,7 @@ static int dedisp_plan_create_impl(const pbk_dedisp_desc* d, const RampSpec* ram
       any = any || (ps.in_role == ROLE_SCRATCH && ps.out_role == ROLE_SCRATCH);
     size_t free_b = 0, total_b = 0;
     if (any && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess &&
-        pl->scratch_bytes <= total_b / 8 && free_b >= 4 * pl->scratch_bytes &&
+        pl->scratch_bytes <= total_b / 5 && free_b >= 3 * pl->scratch_bytes &&
         cudaMalloc(&pl->scratch2, pl->scratch_bytes) != cudaSuccess)
       pl->scratch2 = nullptr;
     cudaGetLastError();
