@@ -386,8 +386,7 @@ static cudaError_t launch_variant(const Pass& ps, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr_done[dev] = true;
   }
-  kern<<<ps.grid, kThreads, ps.smem, st>>>(ps.a);
-  return cudaGetLastError();
+  return pdl_launch(kern, dim3(ps.grid), dim3(kThreads), ps.smem, st, ps.a);
 }
 
 static cudaError_t launch_pass(const Pass& ps, bool fast, cudaStream_t st) {
@@ -1747,6 +1746,7 @@ extern "C" int pbk_stft_fold_exec_device(pbk_plan* pl, const void* d_in, void* d
   fa.nbin = nbin;
   fa.nsamp = pl->det_nseg;
   fa.row_elems = pl->det_cells * pl->det_pq;
+  fold_args_finish(fa);
   fa.counts = reinterpret_cast<unsigned long long*>(d_counts);
   const unsigned blocks = (unsigned)std::min<long long>((pl->det_nseg + 255) / 256, 148 * 4);
   fold_bins_kernel<<<blocks, 256, 0, st>>>(fa, pl->d_segbins);
@@ -2056,6 +2056,7 @@ extern "C" int pbk_fold(const void* in, int64_t nsamp, int64_t row_elems, const 
   fa.nbin = nbin;
   fa.nsamp = nsamp;
   fa.row_elems = row_elems;
+  fold_args_finish(fa);
   if (on_device) {
     fa.in = reinterpret_cast<const float*>(in);
     fa.profile = reinterpret_cast<float*>(profile);

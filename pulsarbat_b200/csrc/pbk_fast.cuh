@@ -694,9 +694,11 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
   long long t = TSUM ? ts_snap(ts_total * ts_r / ts_nr) : FSUM ? 0 : p.tile0 + blockIdx.x;
   const long long t_end = TSUM ? ts_snap(ts_total * (ts_r + 1) / ts_nr) : FSUM ? fs_iters : ntiles;
   const long long t_step = (TSUM || FSUM) ? 1 : gridDim.x;
+  pdl_trigger();
   for (int i = tid; i < C::TW_TOTAL; i += C::NT) tws[i] = tables[i];
   if (tid == 0 && t < t_end) fast_tile_info<C, EPI>(p, tile_at(t), *sinfo, in_bits, out_eb);
   __syncthreads();
+  pdl_wait();   // the previous pass's output (and the array this pass overwrites) from here on
 
   // Per-thread part of the addresses.  A tile is W adjacent lanes; a lane is (row jr, column) of
   // the (.., I) array.  Normally (I a multiple of W) the tile sits inside one row (jr = 0, col0 a

@@ -29,6 +29,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace pbk {
 
@@ -51,6 +52,44 @@ enum { CHIRP_NONE = 0, CHIRP_COMPUTED = 1, CHIRP_ARRAY = 2, CHIRP_RAMP = 3 };
 
 constexpr int kThreads = 256;
 constexpr int kMaxStages = 4;
+
+// Programmatic dependent launch between the passes of a plan: every pass kernel lets the next
+// launch of the stream start as soon as all of its own CTAs are running (pdl_trigger, first
+// instruction) and waits for the previous kernel of the stream to finish and flush its stores
+// (pdl_wait) only after its prologue -- stage tables, tile records, everything that depends on
+// constants alone -- so that launch latency, CTA ramp-up and prologue overlap the previous pass's
+// tail.  EVERY CTA executes pdl_wait, work or not: a grid completes only after all of its CTAs
+// have passed it, which keeps completion transitive along the chain of passes.  Both are no-ops
+// for a launch without the attribute (PBK_PDL=0, or the profiler's serialised replay).
+__device__ __forceinline__ void pdl_trigger() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("PBK_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+// launch of a pass kernel (one that executes pdl_wait in every CTA) with the programmatic
+// stream-serialisation attribute
+template <class... KArgs, class... Args>
+inline cudaError_t pdl_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // element index = o_orig*a_o + kprev*a_kp + klow*a_kl + nrest*a_n + (col / P)*a_c + (col % P)*a_p
 //                 + row * a_row
@@ -736,6 +775,8 @@ __device__ __forceinline__ void run_last_inv(const PassArgs& p, const LaneCtx& L
 template <int MODE, bool FAST, bool SIGNINV>
 __global__ void __launch_bounds__(kThreads, 2) pass_kernel(const __grid_constant__ PassArgs p) {
   extern __shared__ float4 smem_dyn[];
+  pdl_trigger();
+  pdl_wait();
   Tile T;
   T.s = smem_dyn;
   T.log2pw = p.log2pw;

@@ -330,20 +330,58 @@ struct FoldArgs {
   long long n0;
   int nbin;
   long long nsamp, row_elems;
+  double rcp_rate;   // RN(1 / sample_rate), see fold_time
+  int fast_div;
 };
 
+// t = RN(x / sample_rate), bit-equal to numpy's float64 division, without the division sequence:
+// with y = RN(1/b) from the host, q = RN(x y) is within one ulp of x/b, r = x - q b is exact in an
+// FMA, and q' = RN(q + r y) is the correctly rounded quotient (Markstein's theorem; it needs y
+// correctly rounded, q faithful and no underflow/overflow, which fold_args_finish guarantees by
+// bounding |x| < 2^53 and 2^-60 < b < 2^200).  Three instructions instead of ~25; the phase of
+// every sample goes through here, and at 1-4 floats per sample the fold is instruction-bound.
+template <bool ALWAYS_FAST = false>
+__device__ __forceinline__ double fold_time(const FoldArgs& a, double x) {
+  if (!ALWAYS_FAST && !a.fast_div) return __ddiv_rn(x, a.sample_rate);
+  const double q = __dmul_rn(x, a.rcp_rate);
+  const double r = __fma_rn(-q, a.sample_rate, x);
+  return __fma_rn(r, a.rcp_rate, q);
+}
+
+static inline void fold_args_finish(FoldArgs& a) {
+  a.rcp_rate = 1.0 / a.sample_rate;
+  const long long lim = 1ll << 52;
+  a.fast_div = a.sample_rate > 8.7e-19 && a.sample_rate < 1.6e60 && a.n0 > -lim && a.n0 < lim &&
+               a.nsamp < lim;
+}
+
 // bit-exact restatement of numpy.polynomial.polynomial.polyval + floor binning (oracle fold_bins)
-__device__ __forceinline__ int fold_bin(const FoldArgs& a, long long n) {
-  const double t = __ddiv_rn((double)(a.n0 + n), a.sample_rate);
-  double c0 = a.coef[a.ncoef - 1];
-  for (int i = a.ncoef - 2; i >= 0; --i) c0 = __dadd_rn(a.coef[i], __dmul_rn(c0, t));
+// for the sample whose index n0 + n is x (an integer, exactly representable).  NC > 0: the number
+// of coefficients is known at compile time (the per-sample kernels are instantiated for 1..4, so
+// that the Horner chain is straight-line code on constant-bank operands), NC = 0: a.ncoef.
+template <int NC = 0, bool ALWAYS_FAST = false>
+__device__ __forceinline__ int fold_bin_at(const FoldArgs& a, double x) {
+  const double t = fold_time<ALWAYS_FAST>(a, x);
+  double c0;
+  if constexpr (NC > 0) {
+    c0 = a.coef[NC - 1];
+#pragma unroll
+    for (int i = NC - 2; i >= 0; --i) c0 = __dadd_rn(a.coef[i], __dmul_rn(c0, t));
+  } else {
+    c0 = a.coef[a.ncoef - 1];
+    for (int i = a.ncoef - 2; i >= 0; --i) c0 = __dadd_rn(a.coef[i], __dmul_rn(c0, t));
+  }
   const double fr = __dsub_rn(c0, floor(c0));
-  long long b = (long long)floor(__dmul_rn(fr, (double)a.nbin));
-  // fr*nbin can round up to nbin (-> bin 0, like the oracle's `% nbin`); a phase that is not
-  // finite (overflowing polynomial) must not index outside the histogram either
+  // fr in [0, 1): floor(fr*nbin) fits an int; fr*nbin can round up to nbin (-> bin 0, like the
+  // oracle's `% nbin`); a phase that is not finite (overflowing polynomial) gives NaN -> 0 here
+  // and must not index outside the histogram either
+  int b = __double2int_rd(__dmul_rn(fr, (double)a.nbin));
   b = b == a.nbin ? 0 : b;
-  if (!(b >= 0 && b < a.nbin)) b = 0;
-  return (int)b;
+  if ((unsigned)b >= (unsigned)a.nbin) b = 0;
+  return b;
+}
+__device__ __forceinline__ int fold_bin(const FoldArgs& a, long long n) {
+  return fold_bin_at<0>(a, (double)(a.n0 + n));
 }
 
 // Device-side PhasePredictor.__call__ (pulsar/predictor.py:121-147) for one polyco entry: the
@@ -519,6 +557,163 @@ __global__ void __launch_bounds__(256) fold_narrow_kernel(const __grid_constant_
     if (scnt[i]) atomicAdd(a.counts + i, (unsigned long long)scnt[i]);
 }
 
+// ---- rows of 1 to 8, 16 or 32 floats (a single channel's intensity, one or two pols, Stokes,
+// a few channels): one thread per sample.  The thread reads its whole row with the widest vector loads
+// the row length allows and computes its own bin, four samples per thread in flight so that the
+// FP64 Horner chains overlap; a warp whose 32 consecutive samples share one bin (the rule when a
+// bin is wider than 32 samples) adds them with shuffles and issues E shared-memory atomics, any
+// other warp adds per thread.  No barrier inside the span.
+__host__ __device__ constexpr int fold_pow2_ceil(int e) {
+  return e <= 1 ? 1 : e <= 2 ? 2 : e <= 4 ? 4 : e <= 8 ? 8 : e <= 16 ? 16 : 32;
+}
+// bytes the rows must be aligned to for fold_row_load
+__host__ __device__ constexpr int fold_row_align(int e) { return e % 4 == 0 ? 16 : e % 2 == 0 ? 8 : 4; }
+
+template <int E>
+__device__ __forceinline__ void fold_row_load(const float* __restrict__ p, float* x) {
+  if constexpr (E % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < E / 4; ++i) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p) + i);
+      x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+    }
+  } else if constexpr (E % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < E / 2; ++i) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(p) + i);
+      x[2 * i] = v.x; x[2 * i + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < E; ++i) x[i] = __ldg(p + i);
+  }
+}
+
+// samples in flight per thread (rows of 16 / 32 floats: fewer, the rows fill the registers)
+__host__ __device__ constexpr int fold_vec_unroll(int ep) { return ep <= 8 ? 4 : ep == 16 ? 2 : 1; }
+
+// sum over the 32 lanes of EP (a power of two) values per lane: lane el (< EP) ends up with the
+// total of element el.  Halving exchange: while a lane holds more than one element it keeps the
+// half selected by one bit of its lane number and hands the other half to the partner across
+// that bit, then plain butterflies over the remaining bits -- EP - 1 + (5 - log2 EP) shuffles
+// instead of 5 EP.  x is overwritten.
+template <int EP>
+__device__ __forceinline__ float fold_warp_sum(float* x, int lane) {
+#pragma unroll
+  for (int h = EP / 2; h >= 1; h >>= 1) {
+    const bool up = lane & h;                       // these lanes collect elements [h, 2h)
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float keep = up ? x[i + h] : x[i], give = up ? x[i] : x[i + h];
+      x[i] = keep + __shfl_xor_sync(0xffffffffu, give, h);
+    }
+  }
+  float s = x[0];
+#pragma unroll
+  for (int d = 16; d >= EP; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  return s;                                         // lane l holds element l & (EP - 1)
+}
+
+template <int E, int NC>
+__global__ void __launch_bounds__(256) fold_vec_kernel(const __grid_constant__ FoldArgs a,
+                                                       int span) {
+  constexpr int EP = fold_pow2_ceil(E);
+  constexpr int kFoldVecUnroll = fold_vec_unroll(EP);
+  extern __shared__ int fsm[];
+  float* hist = reinterpret_cast<float*>(fsm);              // [nbin][E]
+  int* scnt = fsm + (size_t)a.nbin * E;                     // [nbin]
+  for (int i = threadIdx.x; i < a.nbin * E; i += blockDim.x) hist[i] = 0.f;
+  for (int i = threadIdx.x; i < a.nbin; i += blockDim.x) scnt[i] = 0;
+  const long long nb = (long long)blockIdx.x * span;
+  const int nrows = (int)min((long long)span, a.nsamp - nb);
+  const float* src = a.in + nb * E;
+  const double base = (double)(a.n0 + nb);      // exact, and so is base + r (integers < 2^53)
+  const int lane = threadIdx.x & 31;
+  __syncthreads();
+  for (int r0 = 0; r0 < nrows; r0 += 256 * kFoldVecUnroll) {   // uniform trip count per CTA
+    float v[kFoldVecUnroll][EP];
+    int b[kFoldVecUnroll];
+#pragma unroll
+    for (int u = 0; u < kFoldVecUnroll; ++u) {
+      const int r = r0 + u * 256 + (int)threadIdx.x;
+#pragma unroll
+      for (int el = 0; el < EP; ++el) v[u][el] = 0.f;
+      if (r < nrows) fold_row_load<E>(src + (long long)r * E, v[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kFoldVecUnroll; ++u) {
+      const int r = r0 + u * 256 + (int)threadIdx.x;
+      b[u] = r < nrows ? fold_bin_at<NC, true>(a, __dadd_rn(base, (double)r)) : -1;
+      if (r < nrows && a.bins_out) a.bins_out[nb + r] = b[u];
+    }
+#pragma unroll
+    for (int u = 0; u < kFoldVecUnroll; ++u) {
+      // up to three rounds of "the lanes that share the first pending lane's bin add up with
+      // shuffles": one round when the warp's 32 samples share a bin, two when a bin boundary
+      // falls inside the warp; small groups and what is left after three rounds (bins narrower
+      // than ~10 samples) are added per thread, where few lanes collide on one address
+      const float* x = v[u];
+      unsigned todo = __ballot_sync(0xffffffffu, b[u] >= 0), rest = 0u;
+#pragma unroll 1
+      for (int round = 0; round < 3 && todo; ++round) {
+        const int bb = __shfl_sync(0xffffffffu, b[u], __ffs(todo) - 1);
+        const bool mine = b[u] == bb;
+        const unsigned m = __ballot_sync(0xffffffffu, mine);
+        todo &= ~m;
+        if (__popc(m) < 6) {            // few lanes in this bin: their atomics below hardly collide
+          rest |= m;
+          continue;
+        }
+        float y[EP];
+#pragma unroll
+        for (int el = 0; el < EP; ++el) y[el] = mine ? x[el] : 0.f;
+        const float s = fold_warp_sum<EP>(y, lane);
+        if (lane < E) atomicAdd(hist + bb * E + lane, s);
+        if (lane == 0) atomicAdd(scnt + bb, __popc(m));
+      }
+      if (((todo | rest) >> lane) & 1u) {
+#pragma unroll
+        for (int el = 0; el < E; ++el) atomicAdd(hist + b[u] * E + el, x[el]);
+        atomicAdd(scnt + b[u], 1);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < a.nbin * E; i += blockDim.x)
+    if (hist[i] != 0.f) atomicAdd(a.profile + i, hist[i]);
+  for (int i = threadIdx.x; i < a.nbin; i += blockDim.x)
+    if (scnt[i]) atomicAdd(a.counts + i, (unsigned long long)scnt[i]);
+}
+
+template <int E, int NC>
+static inline cudaError_t launch_fold_vec_nc(const FoldArgs& a, size_t smem, int span,
+                                             cudaStream_t st) {
+  static bool attr_done[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 16 && !attr_done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(fold_vec_kernel<E, NC>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_done[dev] = true;
+  }
+  const long long gx = (a.nsamp + span - 1) / span;
+  fold_vec_kernel<E, NC><<<(unsigned)gx, 256, smem, st>>>(a, span);
+  return cudaGetLastError();
+}
+
+template <int E>
+static inline cudaError_t launch_fold_vec(const FoldArgs& a, size_t smem, int span,
+                                          cudaStream_t st) {
+  switch (a.ncoef) {
+    case 1: return launch_fold_vec_nc<E, 1>(a, smem, span, st);
+    case 2: return launch_fold_vec_nc<E, 2>(a, smem, span, st);
+    case 3: return launch_fold_vec_nc<E, 3>(a, smem, span, st);
+    case 4: return launch_fold_vec_nc<E, 4>(a, smem, span, st);
+    default: return launch_fold_vec_nc<E, 0>(a, smem, span, st);
+  }
+}
+
 static inline int fold_pick_span(long long nsamp, long long ctas_per_span, int lo, int hi) {
   // enough CTAs to fill the 148 SMs several times over, long enough spans to amortise atomics
   long long span = hi;
@@ -541,6 +736,20 @@ static inline cudaError_t launch_fold(const FoldArgs& a, cudaStream_t st) {
     }
     // a span must be long against nbin so that the flush is amortised
     const int span = fold_pick_span(a.nsamp, 1, 4096, 65536);
+    const size_t vec_smem = ((size_t)a.nbin * a.row_elems + a.nbin) * 4;
+    // (sample rates outside fold_args_finish's range keep the division of the scalar kernel)
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(a.in);
+    if (a.fast_div)
+      switch (a.row_elems) {
+#define PBK_FOLD_VEC_CASE(E) \
+        case E: if (addr % fold_row_align(E) == 0) return launch_fold_vec<E>(a, vec_smem, span, st); \
+                break;
+        PBK_FOLD_VEC_CASE(1) PBK_FOLD_VEC_CASE(2) PBK_FOLD_VEC_CASE(3) PBK_FOLD_VEC_CASE(4)
+        PBK_FOLD_VEC_CASE(5) PBK_FOLD_VEC_CASE(6) PBK_FOLD_VEC_CASE(7) PBK_FOLD_VEC_CASE(8)
+        PBK_FOLD_VEC_CASE(16) PBK_FOLD_VEC_CASE(32)
+#undef PBK_FOLD_VEC_CASE
+        default: break;
+      }
     const long long gx = (a.nsamp + span - 1) / span;
     fold_narrow_kernel<<<(unsigned)gx, 256, narrow_smem, st>>>(a, span);
     return cudaGetLastError();

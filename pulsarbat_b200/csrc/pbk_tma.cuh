@@ -241,6 +241,7 @@ tma_pass_kernel(const __grid_constant__ PassArgs p, const __grid_constant__ CUte
     issue(tile_of(h, jj), rank + ahead);
   };
 
+  pdl_trigger();
   for (int i = threadIdx.x; i < C::TW_TOTAL; i += T_::CTA_THREADS) tws[i] = tables[i];
   if (threadIdx.x == 0) {
     for (int b = 0; b < NBUF; ++b) {
@@ -251,6 +252,7 @@ tma_pass_kernel(const __grid_constant__ PassArgs p, const __grid_constant__ CUte
   }
   if (tid == 0 && cnt[g] > 0) fast_tile_info<C, EPI>(p, tile_of(g, 0), *sinfo, in_bits, out_eb);
   __syncthreads();
+  pdl_wait();   // the first TMA loads read the previous pass's output
   if (threadIdx.x == 0) {     // ranks 0 .. NBUF-1: "ahead of the tile before the first"
     for (int a = 1; a <= NBUF; ++a) issue_ahead(NG - 1, -1, -1, a);
   }

@@ -50,8 +50,8 @@ static cudaError_t tma_launch_variant(const PassArgs& a, const CUtensorMap& tm,
   } else {
     grid = (unsigned)std::min<long long>((ntiles + NG - 1) / NG, num_sms);
   }
-  kern<<<grid, T_::CTA_THREADS, T_::SMEM_BYTES, st>>>(a, tm, d_tables, ntiles);
-  return cudaGetLastError();
+  return pdl_launch(kern, dim3(grid), dim3(T_::CTA_THREADS), T_::SMEM_BYTES, st, a, tm, d_tables,
+                    ntiles);
 }
 
 template <class C>

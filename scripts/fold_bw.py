@@ -11,7 +11,11 @@ import pulsarbat_b200 as pb  # noqa: E402
 dev = torch.device("cuda:0")
 for (n, e, nbin, f0, sr) in [(2 ** 22, 128, 1024, 29.7, 6.25e6), (2 ** 22, 128, 1024, 641.9, 6.25e6),
                              (2 ** 16, 1024, 1024, 29.7, 97656.25), (2 ** 20, 2048, 256, 641.9, 1e5),
-                             (2 ** 24, 2, 1024, 29.7, 6.25e6)]:
+                             (2 ** 24, 2, 1024, 29.7, 6.25e6), (2 ** 26, 1, 1024, 29.7, 16e6),
+                             (2 ** 26, 2, 1024, 29.7, 16e6), (2 ** 25, 4, 1024, 29.7, 16e6),
+                             (2 ** 25, 2, 1024, 641.9, 1e5), (2 ** 24, 3, 1024, 29.7, 6.25e6),
+                             (2 ** 24, 8, 1024, 29.7, 6.25e6), (2 ** 24, 16, 1024, 29.7, 6.25e6),
+                             (2 ** 23, 32, 1024, 29.7, 6.25e6), (2 ** 23, 12, 1024, 29.7, 6.25e6)]:
     x = pb.DeviceArray(torch.rand((n, e), device=dev, dtype=torch.float32))
     coeffs = [0.123, f0, 1e-6]
     for _ in range(2):

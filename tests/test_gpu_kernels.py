@@ -746,7 +746,13 @@ def test_cfg5_shard_2pow26_device_resident():
 @pytest.mark.parametrize("nsamp, elems, nbin, f0", [(100_003, 2, 1024, 29.7), (70_000, 1, 64, 641.9),
                                                     (50_000, 3, 128, 5.3), (9_001, 32, 1024, 29.7),
                                                     (20_011, 40, 256, 641.9), (4_099, 300, 1024, 29.7),
-                                                    (70_000, 2, 40000, 29.7)])
+                                                    (70_000, 2, 40000, 29.7), (33_333, 4, 512, 641.9),
+                                                    (262_144 + 5, 4, 64, 0.73), (300_001, 1, 16, 0.11),
+                                                    (150_000, 2, 8, 0.05), (25_000, 5, 128, 7.7),
+                                                    (131_000, 6, 64, 0.9), (12_345, 7, 300, 29.7),
+                                                    (160_000, 8, 512, 0.31), (140_000, 3, 32, 0.07),
+                                                    (50_000, 16, 256, 3.3), (70_000, 32, 64, 0.2),
+                                                    (30_000, 12, 128, 3.3)])
 def test_fold_shapes_bit_exact_counts(nsamp, elems, nbin, f0):
     """Both fold kernels (shared-memory histogram for narrow rows, long-span register
     accumulation for wide rows) and their edge shapes: bins and counts bit-exact, sums to float32
@@ -766,6 +772,40 @@ def test_fold_shapes_bit_exact_counts(nsamp, elems, nbin, f0):
                                   counts=counts.copy())
     assert np.array_equal(counts2, 2 * want_c)
     assert relerr(prof2, 2 * want_p) < 1e-5
+
+
+@pytest.mark.parametrize("sr", [3.3, 1e4 / 3, 7.123456789e6, 6.25e6, 0.1, 1.9999999999999998])
+def test_fold_sample_times_are_correctly_rounded_quotients(sr):
+    """t = (n0 + n) / sample_rate must be numpy's float64 quotient bit for bit (the kernels form
+    it from a host reciprocal and two FMAs instead of a division).  phase = t and 2^20 bins make
+    every ulp of t visible: at t ~ 2^43 one ulp is 2^-10 cycles = 1024 bins."""
+    from pulsarbat_b200 import kernels
+    nsamp = 150_000
+    x = np.ones((nsamp, 1), np.float32)
+    n0 = int(2 ** 43 * sr) + 12_345 if sr * 2 ** 43 < 2 ** 51 else 2 ** 51 + 12_345
+    for nbin in (2 ** 20, 2 ** 14):   # wide kernel (histogram too large for shared memory), vector kernel
+        _, counts, bins = kernels.fold(x, [0.0, 1.0], sr, nbin, n0=n0, want_bins=True)
+        assert np.array_equal(bins, orc.fold_bins(nsamp, [0.0, 1.0], sr, nbin, n0=n0))
+        assert int(counts.sum()) == nsamp
+
+
+def test_fold_of_a_row_view_that_is_not_vector_aligned():
+    """Rows of up to 8 floats are read with vector loads when the base address allows it; a
+    device view that starts at an odd float offset must take the scalar kernel and give the same
+    bins, counts and sums."""
+    import torch
+    import pulsarbat_b200 as pb
+    from pulsarbat_b200 import kernels
+    rng = np.random.default_rng(99)
+    nsamp, nbin, coeffs, sr = 40_001, 256, [0.2, 3.1, 1e-7], 2e4
+    for elems in (2, 4, 6, 8):
+        flat = torch.from_numpy(rng.random(nsamp * elems + 1, dtype=np.float32)).cuda()
+        view = flat[1:].view(nsamp, elems)                    # 4 bytes past a 256-byte boundary
+        assert view.data_ptr() % 8 != 0
+        prof, counts = kernels.fold(pb.DeviceArray(view), coeffs, sr, nbin)
+        want_p, want_c = orc.fold(view.cpu().numpy(), coeffs, sr, nbin)
+        assert np.array_equal(np.asarray(counts.numpy()), want_c)
+        assert relerr(np.asarray(prof.numpy()), want_p) < 1e-5
 
 
 @pytest.mark.parametrize("N, C", [(2 ** 18, 1), (2 ** 18, 2), (2 ** 20, 4), (2 ** 18, 8),
