@@ -525,8 +525,8 @@ static bool tma_kind_enabled(const char* kind, int log2L) {
   // measured on cfg2 / cfg3-shard sized arrays, LDG -> TMA per pass:
   //   fwd   l6 0.373->0.366  l7 1.488->1.439  l8 1.447->1.416  l9 1.910->1.884 ms
   //   inv   l7 1.478->1.473  l8 1.431->1.433  (l6 0.363->0.369)
-  //   mid   l8 1.879->1.740  (l6 1.500->1.606, l7 0.410->0.440: the extra trip of the tile
-  //         through shared memory costs more than the hidden load latency saves)
+  //   mid   l8 1.879->1.740  l10 5.41->4.85  (l6 1.500->1.606, l7 0.410->0.440: the extra trip of
+  //         the tile through shared memory costs more than the hidden load latency saves)
   //   tsum  l8 0.963->0.963  l9 1.203->1.184  (l7 0.906->1.050)
   //   final l7 1.498->1.454  l8 1.414->1.412  (l9 1.894->1.914)
   if (!strcmp(kind, "fwd")) return true;
@@ -591,6 +591,10 @@ static void setup_tma(pbk_plan* pl) {
     const PassArgs& a = ps.a;
     TmaInfo ti;
     if (!tma_info(a.log2L, &ti) || ti.log2pw != ps.finfo.log2pw) continue;
+    if (ti.mid_only && ps.mode != MODE_MID) continue;
+    // 2^10-point MID tiles: 1.348 -> 1.209 ms (32768 tiles), 5.41 -> 4.85 ms (131072 tiles), but
+    // 0.053 -> 0.059 ms at 1024 tiles, where one 512-thread CTA per SM leaves SMs idle
+    if (ti.mid_only && ps.ntiles < 4096 && !getenv("PBK_TMA")) continue;
     const long long W = 2ll << ti.log2pw, L = 1ll << a.log2L;
     if (a.I % W || W % a.P || a.Q % W) continue;                 // wide tiles only
     const bool planar_in = ps.in_role == ROLE_SCRATCH && a.load_kind == LOAD_PLANAR;

@@ -26,9 +26,9 @@
 // reversal) into registers, waits for the group, and writes the stage output back in the
 // last-stage order -- one extra barrier instead of a second buffer.
 //
-// Preconditions (host: setup_tma): wide tiles (I % W == 0), PW >= 8 (no XOR swizzle: a row of the
-// tile is >= 128 B, which is also what makes the box rows full DRAM bursts), complex64 or
-// pair-planar input, plain pass-after-pass schedule.
+// Preconditions (host: setup_tma): wide tiles (I % W == 0), complex64 or pair-planar input, plain
+// pass-after-pass schedule.  Tiles of 2^6 .. 2^9 points have rows of >= 128 B (full DRAM bursts, no
+// XOR swizzle in shared memory); the 2^10-point tile (64-byte rows) exists for the MID pass only.
 #pragma once
 #include <cuda.h>
 #include <cstdio>
@@ -97,20 +97,30 @@ struct TmaCfg {
   static constexpr size_t OFF_INFO = OFF_G + (size_t)NG * C::RL * sizeof(float4);
   static constexpr size_t OFF_BAR = OFF_INFO + (size_t)NG * 64;
   static constexpr size_t OFF_ISSUED = OFF_BAR + (size_t)NBUF * 8;   // rank last issued per buffer
-  static constexpr size_t SMEM_BYTES = OFF_ISSUED + (size_t)NBUF * 8 + 64;
-  static_assert(C::PW >= 8, "TMA tiles are row-major: rows of at least 128 B (no XOR swizzle)");
+  static constexpr size_t OFF_SEQ = OFF_ISSUED + (size_t)NBUF * 8;     // t0[NG], cnt[NG] (issuer's copy)
+  static constexpr size_t SMEM_BYTES = OFF_SEQ + (size_t)NG * 16 + 64;
+  // rows of 64 B (PW = 4): the tile arrives row-major and the first stage writes the swizzled
+  // layout the later stages expect (fwd_first_smem); only the MID kernel is instantiated there
+  static_assert(C::PW >= 4, "TMA tiles are row-major boxes of at least 64-byte rows");
   static_assert(C::NT * NG == CTA_THREADS && NG >= 2, "thread groups tile the CTA");
   static_assert(sizeof(TileInfo) <= 64, "tile record slot");
   static_assert(SMEM_BYTES <= 227 * 1024, "ring of tile buffers exceeds shared memory");
 };
 
 // first forward stage on a tile that is already in shared memory in natural row order: in place
-// (a DIF butterfly reads and writes the same R rows); complex64 input is de-interleaved here
+// (a DIF butterfly reads and writes the same R rows); complex64 input is de-interleaved here.
+// Tiles with rows shorter than 128 B keep the XOR swizzle of pbk_fast.cuh (phys_pt) from the
+// first stage's OUTPUT on: the stage then writes row b ^ 1 for some b, i.e. the rows its
+// neighbour four lanes away has read -- same warp, same iteration, so a __syncwarp between the
+// loads and the stores is all the ordering that needs.
 template <class C, int LOADK, bool SIGNINV>
 __device__ __forceinline__ void fwd_first_smem(float4* tile, const float2* tws, int tid) {
   constexpr int R = C::radix(0), S = C::stride(0);
   constexpr int TASKS = S * C::PW;
   constexpr int ITERS = (TASKS + C::NT - 1) / C::NT;
+  static_assert(C::PPB == 1 || (S % (C::RL * C::PPB) == 0 && C::PW * C::PPB <= 32 &&
+                                TASKS % C::NT == 0),
+                "swizzled first stage: partner rows are exchanged inside a warp");
   const int pr = tid & (C::PW - 1);
 #pragma unroll
   for (int it = 0; it < ITERS; ++it) {
@@ -129,10 +139,11 @@ __device__ __forceinline__ void fwd_first_smem(float4* tile, const float2* tws, 
         v[i].im = make_float2(t.y, t.w);
       }
     }
+    if constexpr (C::PPB > 1) __syncwarp();
     Butterfly<R, SIGNINV>::run(v);
     stage_twiddle<R, S, SIGNINV>(v, tws + C::tw_off(0), b);
 #pragma unroll
-    for (int i = 0; i < R; ++i) sts_c2(tile, ((b + i * S) << C::LOG2PW) + pr, v[i]);
+    for (int i = 0; i < R; ++i) sts_c2(tile, (phys_pt<C, S>(b, i) << C::LOG2PW) + pr, v[i]);
   }
 }
 
@@ -178,33 +189,62 @@ tma_pass_kernel(const __grid_constant__ PassArgs p, const __grid_constant__ CUte
     if (nr > tail) return u - nr + tail;
     return u;
   };
-  long long t0[NG], cnt[NG];
+  // Runs of the NG groups (start, count).  Every thread needs its own group's run, rank_of all
+  // counts once per tile, and the issuing thread walks all runs with a run-time group index.
+  // Two ways to hold them, chosen per kind of pass on measurements (cfg2 / 2^24 x 64 lanes):
+  //   RUNS_LOCAL  per-thread arrays; the run-time index puts them in local memory, and the loop
+  //               bound is a local load per tile.  The HBM-bound forward / inverse passes are
+  //               4-6 % faster this way (2^8: 1.43 vs 1.49 ms): anything that lets the loads run
+  //               further ahead of the stores costs them DRAM efficiency.
+  //   otherwise   own run in registers, all runs in shared memory for rank_of and the issuer.
+  //               The passes that are not HBM-bound gain: 2^10-point MID 4.85 -> 4.25 ms, fused
+  //               time sum 1.09 -> 1.04 ms.
+  constexpr bool RUNS_LOCAL = MODE != MODE_MID && !TSUM;
+  long long l_t0[RUNS_LOCAL ? NG : 1];
+  int l_cnt[RUNS_LOCAL ? NG : 1];
+  long long my_t0 = 0;
+  int my_cnt = 0;
+  long long* s_t0 = reinterpret_cast<long long*>(smem_raw + T_::OFF_SEQ);
+  int* s_cnt = reinterpret_cast<int*>(s_t0 + NG);
 #pragma unroll
   for (int gg = 0; gg < NG; ++gg) {
     const long long vb = (long long)blockIdx.x * NG + gg;
+    long long start;
+    int c;
     if (TSUM) {
       const long long total = ntiles / tq, r = vb / tq, nr = vgrid / tq;
-      t0[gg] = ts_snap(total * r / nr);
-      cnt[gg] = ts_snap(total * (r + 1) / nr) - t0[gg];
+      start = ts_snap(total * r / nr);
+      c = (int)(ts_snap(total * (r + 1) / nr) - start);
     } else {
-      t0[gg] = vb;
-      cnt[gg] = vb < ntiles ? (ntiles - vb + vgrid - 1) / vgrid : 0;
+      start = vb;
+      c = vb < ntiles ? (int)((ntiles - vb + vgrid - 1) / vgrid) : 0;
+    }
+    if constexpr (RUNS_LOCAL) {
+      l_t0[gg] = start;
+      l_cnt[gg] = c;
+    } else {
+      if (gg == g) { my_t0 = start; my_cnt = c; }
+      if (threadIdx.x == 0) { s_t0[gg] = start; s_cnt[gg] = c; }
     }
   }
+  auto run_cnt = [&](int gg) -> int { return RUNS_LOCAL ? l_cnt[RUNS_LOCAL ? gg : 0] : s_cnt[gg]; };
+  auto run_t0 = [&](int gg) -> long long { return RUNS_LOCAL ? l_t0[RUNS_LOCAL ? gg : 0] : s_t0[gg]; };
+  auto own_cnt = [&]() -> int { return RUNS_LOCAL ? l_cnt[RUNS_LOCAL ? g : 0] : my_cnt; };
+  auto own_t0 = [&]() -> long long { return RUNS_LOCAL ? l_t0[RUNS_LOCAL ? g : 0] : my_t0; };
   // rank of tile j of group gg in the CTA's sequence (rounds of the groups, exhausted ones skipped)
   auto rank_of = [&](int gg, long long j) -> long long {
     long long k = 0;
 #pragma unroll
     for (int h = 0; h < NG; ++h) {
-      const long long upto = j + (h < gg ? 1 : 0);
-      k += cnt[h] < upto ? cnt[h] : upto;
+      const long long upto = j + (h < gg ? 1 : 0), ch = run_cnt(h);
+      k += ch < upto ? ch : upto;
     }
     return k;
   };
-  // j-th tile of group gg
-  auto tile_of = [&](int gg, long long j) -> long long {
-    if (!TSUM) return t0[gg] + j * vgrid;
-    const long long i = t0[gg] + j;
+  // j-th tile of group gg whose run starts at start
+  auto tile_of = [&](int gg, long long start, long long j) -> long long {
+    if (!TSUM) return start + j * vgrid;
+    const long long i = start + j;
     const long long cb = i >> p.log2nmul, nr = i & ((1ll << p.log2nmul) - 1);
     const int cgq = (int)(((long long)blockIdx.x * NG + gg) % tq);
     return nr * ncg + cb * tq + cgq;
@@ -234,11 +274,11 @@ tma_pass_kernel(const __grid_constant__ PassArgs p, const __grid_constant__ CUte
       if (++h == NG) { h = 0; ++jj; }
       bool any = false;                 // is any group still alive in this or a later round?
 #pragma unroll
-      for (int q = 0; q < NG; ++q) any = any || jj < cnt[q];
+      for (int q = 0; q < NG; ++q) any = any || jj < run_cnt(q);
       if (!any) return;
-      if (jj < cnt[h] && ++found == ahead) break;
+      if (jj < run_cnt(h) && ++found == ahead) break;
     }
-    issue(tile_of(h, jj), rank + ahead);
+    issue(tile_of(h, run_t0(h), jj), rank + ahead);
   };
 
   pdl_trigger();
@@ -250,7 +290,8 @@ tma_pass_kernel(const __grid_constant__ PassArgs p, const __grid_constant__ CUte
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (tid == 0 && cnt[g] > 0) fast_tile_info<C, EPI>(p, tile_of(g, 0), *sinfo, in_bits, out_eb);
+  if (tid == 0 && own_cnt() > 0)
+    fast_tile_info<C, EPI>(p, tile_of(g, own_t0(), 0), *sinfo, in_bits, out_eb);
   __syncthreads();
   pdl_wait();   // the first TMA loads read the previous pass's output
   if (threadIdx.x == 0) {     // ranks 0 .. NBUF-1: "ahead of the tile before the first"
@@ -274,7 +315,7 @@ tma_pass_kernel(const __grid_constant__ PassArgs p, const __grid_constant__ CUte
   const long long ts_rowbytes = p.mout.a_n * out_eb;
   if (TSUM) tacc.clear();
 
-  for (long long j = 0; j < cnt[g]; ++j) {
+  for (long long j = 0; j < own_cnt(); ++j) {
     const long long rank = rank_of(g, j);
     const int buf = (int)(rank % NBUF);
     {
@@ -305,8 +346,8 @@ tma_pass_kernel(const __grid_constant__ PassArgs p, const __grid_constant__ CUte
         G4[tid] = make_float4(gv.x, gv.y, gv.y, gv.x);
       }
 #define PBK_TMA_NEXT_INFO()                                                      \
-  if (tid == 0 && j + 1 < cnt[g])                                                \
-    fast_tile_info<C, EPI>(p, tile_of(g, j + 1), *sinfo, in_bits, out_eb)
+  if (tid == 0 && j + 1 < own_cnt())                                             \
+    fast_tile_info<C, EPI>(p, tile_of(g, own_t0(), j + 1), *sinfo, in_bits, out_eb)
 
       while (issued[buf] < rank) {}                               // our load has been issued ...
       mbar_wait(&full[buf], (uint32_t)((rank / NBUF) & 1));       // ... and has landed

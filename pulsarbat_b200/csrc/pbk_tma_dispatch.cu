@@ -3,7 +3,7 @@
 
 namespace pbk {
 
-#define PBK_TMA_LENGTHS(X) X(6) X(7) X(8) X(9)
+#define PBK_TMA_LENGTHS(X) X(6) X(7) X(8) X(9) X(10)
 
 #define X(l)                                                                                  \
   void tma_info_l##l(TmaInfo* info);                                                          \

@@ -19,6 +19,7 @@ static void tma_cfg_info(TmaInfo* info) {
   info->threads = T_::CTA_THREADS;
   info->smem = T_::SMEM_BYTES;
   info->tsum_ok = (C::stride(0) * C::PW) % C::NT == 0;
+  info->mid_only = false;
 }
 
 template <int MODE, class C, int LOADK, int EPI, bool TWOCH = false, bool TSUM = false>
@@ -94,6 +95,19 @@ static cudaError_t tma_cfg_launch(int mode, const PassArgs& a, const CUtensorMap
                                                                           num_sms, st);
       }
   }
+}
+
+// tile lengths whose only TMA kernel is the scratch-to-scratch MID pass
+template <class C>
+static cudaError_t tma_cfg_launch_mid(int mode, const PassArgs& a, const CUtensorMap& tm,
+                                      const float2* d_tables, long long ntiles, int num_sms,
+                                      cudaStream_t st) {
+  if (mode != MODE_MID || a.final_epi) return cudaErrorInvalidValue;
+  if (a.P == 1)
+    return tma_launch_variant<MODE_MID, C, LK_PLANAR, EPI_SCRATCH, true>(a, tm, d_tables, ntiles,
+                                                                         num_sms, st);
+  return tma_launch_variant<MODE_MID, C, LK_PLANAR, EPI_SCRATCH>(a, tm, d_tables, ntiles, num_sms,
+                                                                 st);
 }
 
 }  // namespace pbk

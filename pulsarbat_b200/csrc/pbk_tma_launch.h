@@ -1,5 +1,5 @@
 // pbk_tma_launch.h -- host interface to the TMA-pipelined pass kernels (pbk_tma.cuh); the
-// instantiations live in pbk_tma_l6.cu .. pbk_tma_l9.cu.
+// instantiations live in pbk_tma_l6.cu .. pbk_tma_l10.cu.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -14,6 +14,7 @@ struct TmaInfo {
   int groups, buffers, threads;
   size_t smem;
   bool tsum_ok;
+  bool mid_only;       // only the MID kernel is instantiated for this tile length
 };
 
 // false when there is no TMA instantiation for this tile length

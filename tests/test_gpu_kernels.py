@@ -1188,6 +1188,8 @@ def test_single_column_even_odd_split(N, out_kind, crop_odd, monkeypatch):
     (20, 32, 2, 1, 8, (1000, 2 ** 20 - 3000), "8,6,6"),  # intensity, time sum with a ragged crop
     (20, 16, 2, 1, 1, None, "7,7,6"),                    # 2^7-point tiles, 4 groups per CTA
     (21, 8, 2, 0, 1, None, "9,6,6"),                     # 2^9-point tiles, two boxes per tile
+    (22, 32, 2, 1, 1, (100000, 2 ** 22 - 300000), "6,6,10"),  # 2^10-point MID: 64-byte rows, swizzled
+    (18, 64, 1, 0, 1, (77, 2 ** 18 - 101), "8,10"),      # the same with two chirps per lane pair
 ])
 def test_tma_passes_are_bit_identical_to_ldg_passes(monkeypatch, n, C, P, out_kind, ds, crop, levels):
     import torch
@@ -1217,6 +1219,42 @@ def test_tma_passes_are_bit_identical_to_ldg_passes(monkeypatch, n, C, P, out_ki
         plan.destroy()
     assert "tma-r16" not in descs[0] and descs[1].count("tma-r16") >= 2, descs
     assert torch.equal(outs[0], outs[1]), descs[1]
+
+
+def test_plan_execution_replays_from_a_cuda_graph():
+    """A plan execution only enqueues kernels (and one memset for the fused time sum) on the
+    caller's stream: it can be captured into a CUDA graph -- programmatic dependent launches
+    between the passes included -- and the replay gives the bits of the direct launches."""
+    import torch
+    L = _lib()
+    for (n, C, P, out_kind, ds) in [(20, 1, 1, 0, 1), (18, 8, 2, 0, 1), (20, 32, 2, 2, 64)]:
+        N = 2 ** n
+        sr, fcen = 6.25e6, 600e6
+        freqs = fcen + sr * (np.arange(C) + 0.5 - C / 2)
+        g = torch.Generator(device="cuda")
+        g.manual_seed(n + C)
+        x = torch.randn((N, C, P, 2), device="cuda", dtype=torch.float32, generator=g)
+        plan = L.DedispPlan(nsamp=N, nchan=C, npol=P, dm=3.0, sample_rate_hz=sr, ref_freq_hz=fcen,
+                            chan_freq_hz=freqs, crop=(0, N), out_kind=out_kind, downsample=ds)
+        nout = plan.out_rows * plan.row_elems * plan.elem_bytes
+        out = torch.zeros(nout, device="cuda", dtype=torch.uint8)
+        stream = torch.cuda.Stream()
+        with torch.cuda.stream(stream):
+            for _ in range(2):
+                plan.exec_device(x.data_ptr(), out.data_ptr(), None, stream.cuda_stream)
+            stream.synchronize()
+            want = out.clone()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=stream):
+                plan.exec_device(x.data_ptr(), out.data_ptr(), None,
+                                 torch.cuda.current_stream().cuda_stream)
+            for _ in range(3):
+                out.zero_()
+                graph.replay()
+            stream.synchronize()
+        assert torch.equal(out, want), plan.describe()
+        del graph
+        plan.destroy()
 
 
 def test_l2_pipeline_of_the_middle_passes_is_bit_identical(monkeypatch):
