@@ -525,13 +525,14 @@ static bool tma_kind_enabled(const char* kind, int log2L) {
   // measured on cfg2 / cfg3-shard sized arrays, LDG -> TMA per pass:
   //   fwd   l6 0.373->0.366  l7 1.488->1.439  l8 1.447->1.416  l9 1.910->1.884 ms
   //   inv   l7 1.478->1.473  l8 1.431->1.433  (l6 0.363->0.369)
-  //   mid   l8 1.879->1.740  l10 5.41->4.85  (l6 1.500->1.606, l7 0.410->0.440: the extra trip of
-  //         the tile through shared memory costs more than the hidden load latency saves)
+  //   mid   l6 1.537->1.522 (whole cfg2 step, passes back to back: 6.877->6.765)  l8 1.863->1.599
+  //         l10 5.41->4.25  (with the group runs in registers / shared memory, pbk_tma.cuh; with
+  //         them in local memory l6 and l7 lost: 1.500->1.606, 0.410->0.440)
   //   tsum  l8 0.963->0.963  l9 1.203->1.184  (l7 0.906->1.050)
   //   final l7 1.498->1.454  l8 1.414->1.412  (l9 1.894->1.914)
   if (!strcmp(kind, "fwd")) return true;
   if (!strcmp(kind, "inv")) return log2L >= 7;
-  if (!strcmp(kind, "mid")) return log2L >= 8;
+  if (!strcmp(kind, "mid")) return true;
   if (!strcmp(kind, "tsum")) return log2L >= 8;
   if (!strcmp(kind, "final")) return log2L == 7 || log2L == 8;
   return false;

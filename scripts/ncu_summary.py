@@ -55,11 +55,12 @@ def main(raw_csv, out_txt, traffic_json, workload, header=""):
     # one step = from a first-pass kernel to the next first-pass kernel: keep the last step
     firsts = [i for i, r in enumerate(mine) if "_pass_kernel<0" in r[col["Kernel Name"]].replace("(int)", "")
               and i + 1 < len(mine)]
-    # the first forward pass of a step is followed by another forward pass; steps are 5-6 launches
+    # a step starts at a forward pass that does not follow another forward pass
+    starts = [i for i in firsts if i == 0 or
+              "_pass_kernel<0" not in mine[i - 1][col["Kernel Name"]].replace("(int)", "")]
     step_len = None
-    for a, b in zip(firsts, firsts[1:]):
-        if b - a >= 3:
-            step_len = b - a
+    for a, b in zip(starts, starts[1:]):
+        step_len = b - a
     if step_len is None:
         step_len = len(mine)
     last = mine[-step_len:]
