@@ -18,7 +18,11 @@
  *    stream) and do not synchronise.  A plan owns its scratch arrays (one, or two of N*C*P*8
  *    bytes each when that is at most 1/5 of the device memory; pbk_plan_info reports the total):
  *    executions of the same plan must be ordered on the device (same stream, or events between
- *    streams).
+ *    streams).  A *_device execution only enqueues kernels (and a memset of a summed output):
+ *    it can be captured into a CUDA graph.  The passes of one execution are chained with
+ *    programmatic dependent launch (PBK_PDL=0 switches it off); the first pass waits for the
+ *    previous kernel of the stream to complete like any kernel, and kernels the caller enqueues
+ *    afterwards wait for the last pass.
  *  - There is no CPU fallback: without a CUDA device every call fails with PBK_ERR_CUDA.
  */
 #ifndef PBK_H_
