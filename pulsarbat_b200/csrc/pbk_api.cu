@@ -23,6 +23,7 @@
 #include "../../include/pbk.h"
 #include "pbk_fast_launch.h"
 #include "pbk_tma_launch.h"
+#include "pbk_tsumw_launch.h"
 #include "pbk_l2pipe_launch.h"
 #include "pbk_blue.cuh"
 #include "pbk_f64.cuh"
@@ -111,6 +112,8 @@ struct Pass {
   // TMA-pipelined variant of the same tile shape (pbk_tma.cuh); decided by setup_tma
   bool tma = false;
   TmaInfo tinfo{};
+  // time-summing last pass on the warp-private kernel (pbk_tsumw.cuh): two swizzled half-tile boxes
+  bool tsumw = false;
 };
 
 struct BlueState;   // arbitrary-length (Bluestein) plans, see below
@@ -561,10 +564,6 @@ static bool tma_encode(const Pass& ps, const void* base, CUtensorMap* tm) {
   if (!enc) return false;
   const PassArgs& a = ps.a;
   const cuuint64_t I = (cuuint64_t)a.I, RI = (cuuint64_t)a.RI, L = 1ull << a.log2L;
-  const cuuint64_t dims[4] = {2 * I, RI / I, L, (cuuint64_t)(a.Q / a.RI)};
-  const cuuint64_t strides[3] = {I * 8, RI * 8, L * RI * 8};
-  const cuuint32_t box[4] = {(cuuint32_t)(4u << ps.tinfo.log2pw), 1, (cuuint32_t)ps.tinfo.box_rows, 1};
-  const cuuint32_t es[4] = {1, 1, 1, 1};
   static const int promo = [] {
     const char* e = getenv("PBK_TMA_L2PROMO");
     return e ? atoi(e) : 0;
@@ -573,6 +572,21 @@ static bool tma_encode(const Pass& ps, const void* base, CUtensorMap* tm) {
                                    : promo == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
                                    : promo == 64  ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
                                                   : CU_TENSOR_MAP_L2_PROMOTION_NONE;
+  if (ps.tsumw) {
+    // warp-private time sum (pbk_tsumw.cuh): the lane axis split into 128-byte chunks, one box =
+    // 32 floats x 2 chunks x 256 rows with the 128-byte swizzle
+    const cuuint64_t dims[5] = {32, I / 16, RI / I, L, (cuuint64_t)(a.Q / a.RI)};
+    const cuuint64_t strides[4] = {128, I * 8, RI * 8, L * RI * 8};
+    const cuuint32_t box[5] = {32, 2, 1, 256, 1};
+    const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(base), dims, strides, box,
+               es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2p,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  }
+  const cuuint64_t dims[4] = {2 * I, RI / I, L, (cuuint64_t)(a.Q / a.RI)};
+  const cuuint64_t strides[3] = {I * 8, RI * 8, L * RI * 8};
+  const cuuint32_t box[4] = {(cuuint32_t)(4u << ps.tinfo.log2pw), 1, (cuuint32_t)ps.tinfo.box_rows, 1};
+  const cuuint32_t es[4] = {1, 1, 1, 1};
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box,
              es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, l2p,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -586,6 +600,7 @@ static void setup_tma(pbk_plan* pl) {
   int idx = -1;
   for (auto& ps : pl->passes) {
     ps.tma = false;
+    ps.tsumw = false;
     ++idx;
     if (only && atoi(only) != idx) continue;
     if (ps.family < 0 || ps.signinv || ps.fast_load_transposed) continue;
@@ -612,11 +627,24 @@ static void setup_tma(pbk_plan* pl) {
     if (a.Q / a.RI >= (1ll << 31) || 2ll * a.I >= (1ll << 32)) continue;
     const bool tsum = ps.mode == MODE_INV && a.tsum_log2 > 0;
     if (tsum && !ti.tsum_ok) continue;
+    // a time-summing pass has at most (tiles / q) >> (log2 M + 1) runs of tiles (a run spans two
+    // groups of summed rows); when that is fewer than two per SM, one 512-thread CTA per SM
+    // leaves SMs idle that the 256-thread CTAs of the LDG kernel would use (2^20 x 64 lanes, M = 64:
+    // 0.38 ms LDG, 0.57 ms TMA)
+    if (tsum && !getenv("PBK_TMA") &&
+        ((ps.ntiles / a.tsum_q) >> (a.tsum_log2 + 1)) * a.tsum_q < 2ll * pl->num_sms)
+      continue;
     const char* kind = ps.mode == MODE_FWD ? "fwd" : ps.mode == MODE_MID ? "mid"
                        : tsum ? "tsum" : a.final_epi ? "final" : "inv";
     if (!tma_kind_enabled(kind, a.log2L)) continue;
     ps.tma = true;
     ps.tinfo = ti;
+    // PBK_TSUMW=0: keep the thread-group kernel for the time-summing pass
+    // $PBK_TSUMW=1: the time-summing pass on the warp-private kernel (pbk_tsumw.cuh).  Opt-in: it
+    // is bit-identical but slower on B200 (cfg2: 1.13-1.18 ms against 0.95-0.97), see DESIGN.md 5.1e
+    const char* tw = getenv("PBK_TSUMW");
+    ps.tsumw = tsum && tw && tw[0] == '1' && tsumw_supported(a.log2L, ti.log2pw) &&
+               ti.box_rows == 256;
   }
 }
 
@@ -1101,8 +1129,9 @@ static int launch_one(pbk_plan* pl, const Pass& ps, const void* d_in, void* d_ou
   cudaError_t e;
   CUtensorMap tm;
   if (ps.tma && aligned && tile0 == 0 && tile_end < 0 && tma_encode(ps, p.a.in, &tm)) {
-    e = tma_launch(ps.a.log2L, ps.mode, p.a, tm, pl->d_ftab + ps.ftab_off, ps.ntiles,
-                   pl->num_sms, st);
+    e = ps.tsumw ? tsumw_launch(p.a, tm, pl->d_ftab + ps.ftab_off, ps.ntiles, pl->num_sms, st)
+                 : tma_launch(ps.a.log2L, ps.mode, p.a, tm, pl->d_ftab + ps.ftab_off, ps.ntiles,
+                              pl->num_sms, st);
   } else if (ps.family >= 0 && aligned) {
     if (ps.fast_load_transposed)
       p.a.load_kind = ps.a.load_kind == LOAD_PLANAR ? LOAD_TRANSP_PLANAR : LOAD_TRANSP;
@@ -1866,7 +1895,7 @@ extern "C" int pbk_plan_describe(const pbk_plan* pl, char* buf, size_t n) {
     const char* sep = i == 0 ? "" : (blocked && (i == 2 || i == 3)) ? "+" : ";";
     if (ps.family >= 0)
       w = snprintf(buf + off, n - off, "%s%s:L=2^%d:%s:W=%d:tiles=%lld:threads=%d%s%s", sep,
-                   mode, ps.a.log2L, ps.tma ? "tma-r16" : "fast-r16",
+                   mode, ps.a.log2L, ps.tsumw ? "tmaw-r16" : ps.tma ? "tma-r16" : "fast-r16",
                    2 << ps.finfo.log2pw, ps.ntiles, ps.tma ? ps.tinfo.threads : ps.finfo.threads,
                    ps.a.tsum_log2 > 0 ? ":timesum" : "", ps.a.split ? ":evenodd" : "");
     else
