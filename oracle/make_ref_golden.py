@@ -204,6 +204,36 @@ def main():
     xr64 = np.random.default_rng(601).standard_normal(1023)
     out["r2c_x64"], out["r2c_y64"] = xr64, pb.utils.real_to_complex(xr64)
 
+    # ---- phase predictor (pulsar/predictor.py:108-160, 276-306) on the reference's own polyco
+    # fixture: raw (integer, fractional) parts as PhasePredictor.__call__ hands them to pb.Phase
+    PhasePredictor, _, _, _ = ref_run.load_predictor()
+    polyco = os.path.join(ref_run.REF_ROOT, "tests", "data", "timing.dat")
+    if not os.path.isfile(polyco):      # a pip install of the reference carries no tests: use the
+        polyco = os.path.join(os.path.dirname(OUT), "timing.dat")       # byte-identical copy
+    pred = PhasePredictor.from_polyco(polyco)
+    t1 = Time("58245.375", format="mjd", precision=9)
+    ph = pred(t1)
+    out["pred_scalar"] = np.array([float(ph.phase1), float(ph.phase2),
+                                   pred.f0(t1).to_value(u.cycle / u.s),
+                                   pred.f0(t1, n=1).to_value(u.cycle / u.s ** 2)])
+    out["pred_rphase"] = np.asarray(pred["rphase"], dtype=np.int64)
+    ph = pred(t1 + np.arange(10000) * u.us)
+    out["pred_us_ph1"], out["pred_us_ph2"] = ph.phase1.astype(np.int64), ph.phase2
+    (a, b), = pred.intervals
+    span_s = float((b - a).to_value(u.s))
+    offs = (np.arange(400) + 0.37) / 400 * span_s                  # across all 16 entries
+    ts = a + offs * u.s
+    ph = pred(ts)
+    out["pred_span_mjd_int"], out["pred_span_mjd_frac"] = np.asarray(ts.jd1), np.asarray(ts.jd2)
+    out["pred_span_ph1"], out["pred_span_ph2"] = ph.phase1.astype(np.int64), ph.phase2
+    out["pred_span_f0"] = pred.f0(ts).to_value(u.cycle / u.s)
+    pol_t = [Time("58245.375", format="mjd"), Time("58245.0", format="mjd"),
+             Time(58245.0, 0.6180339887, format="mjd"), ts[123], ts[377]]
+    out["pred_phasepol_mjd"] = np.array([[float(t.jd1), float(t.jd2)] for t in pol_t])
+    pols = [pred.phasepol(t) for t in pol_t]
+    out["pred_phasepol_coef"] = np.stack([q.coef for q, _ in pols])
+    out["pred_phasepol_ref"] = np.array([int(r.phase1) for _, r in pols], dtype=np.int64)
+
     out["meta_json"] = np.array(json.dumps(meta))
     np.savez(OUT, **out)
     print(f"wrote {OUT}: {len(out)} arrays, {os.path.getsize(OUT) / 1e6:.2f} MB")

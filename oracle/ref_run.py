@@ -9,8 +9,10 @@ and ``isinstance`` checks, so this loader
 * creates an empty ``pulsarbat`` package whose ``__path__`` is ``/root/reference/pulsarbat`` and
   imports from it, WHERE THEY LIE, the files on the path: ``core.py``, ``fft.py``, ``utils.py``,
   ``transforms/`` (``dedispersion.py``, ``transforms.py``) and ``contrib/misc.py`` -- the same
-  star-imports the reference's ``__init__.py:9-21`` does, minus ``pulsar`` (needs astropy Table /
-  Angle) and ``readers`` (needs ``baseband``).
+  star-imports the reference's ``__init__.py:9-21`` does, minus ``readers`` (needs ``baseband``)
+  and ``pulsar``, of which ``load_predictor()`` imports ``pulsar/predictor.py`` alone (its
+  ``phase.py`` needs astropy's Angle machinery; the predictor only hands ``pb.Phase`` the two
+  parts it computed, so a two-field record stands in).
 
 Nothing is copied; /root/reference is read, never written.  Used by oracle/make_ref_golden.py to
 freeze reference outputs into tests/golden/ref_golden.npz, and by tests/test_ref_golden.py to
@@ -21,6 +23,8 @@ import importlib
 import os
 import sys
 import types
+
+import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SHIM = os.path.join(_HERE, "ref_shim")
@@ -92,3 +96,42 @@ def load():
     finally:
         sys.dont_write_bytecode = dont
     return pb, sys.modules["astropy.units"], sys.modules["astropy.time"].Time
+
+
+class _PhaseStub:
+    """What pulsar/predictor.py hands to ``pb.Phase``: (integer cycles, fractional cycles).  The
+    reference's Phase class (pulsar/phase.py) needs astropy's Angle machinery and is not loaded;
+    the predictor only constructs it from the two parts it has computed."""
+
+    def __init__(self, phase1, phase2=0.0):
+        self.phase1 = np.asarray(phase1)
+        self.phase2 = np.asarray(phase2, dtype=np.float64)
+
+
+def load_predictor():
+    """Return (PhasePredictor, PolycoEntry, u, Time): the reference's pulsar/predictor.py executed
+    where it lies, against the astropy stand-ins (QTable, array-capable Time) and with ``pb.Phase``
+    replaced by a two-field record."""
+    pb, u, Time = load()
+    if hasattr(pb, "PhasePredictor"):
+        return pb.PhasePredictor, pb.PolycoEntry, u, Time
+    if "astropy.table" not in sys.modules:
+        sys.path.insert(0, _SHIM)
+        try:
+            importlib.import_module("astropy.table")
+        finally:
+            sys.path.remove(_SHIM)
+    pb.Phase = _PhaseStub
+    pulsar = types.ModuleType("pulsarbat.pulsar")
+    pulsar.__path__ = [os.path.join(REF_ROOT, "pulsarbat", "pulsar")]
+    sys.modules["pulsarbat.pulsar"] = pulsar
+    dont = sys.dont_write_bytecode
+    sys.dont_write_bytecode = True
+    try:
+        pred = importlib.import_module("pulsarbat.pulsar.predictor")
+    finally:
+        sys.dont_write_bytecode = dont
+    pulsar.predictor = pred
+    pb.pulsar = pulsar
+    pb.PhasePredictor, pb.PolycoEntry = pred.PhasePredictor, pred.PolycoEntry
+    return pb.PhasePredictor, pb.PolycoEntry, u, Time

@@ -20,7 +20,8 @@ import math
 import numpy as np
 
 __all__ = ["Unit", "Quantity", "SpecificTypeQuantity", "UnitConversionError", "Hz", "kHz", "MHz",
-           "GHz", "s", "ms", "us", "ns", "day", "cycle", "rad", "one", "dimensionless_unscaled",
+           "GHz", "s", "ms", "us", "ns", "min", "day", "cycle", "rad", "one",
+           "dimensionless_unscaled",
            "pc", "cm", "isclose", "allclose"]
 
 
@@ -31,7 +32,7 @@ class UnitConversionError(ValueError):
 # named unit -> (SI scale, SI dims)
 _NAMED = {
     "s": (1.0, {"s": 1}), "ms": (1e-3, {"s": 1}), "us": (1e-6, {"s": 1}), "ns": (1e-9, {"s": 1}),
-    "day": (86400.0, {"s": 1}),
+    "min": (60.0, {"s": 1}), "day": (86400.0, {"s": 1}),
     "Hz": (1.0, {"s": -1}), "kHz": (1e3, {"s": -1}), "MHz": (1e6, {"s": -1}),
     "GHz": (1e9, {"s": -1}),
     "rad": (1.0, {"rad": 1}), "cycle": (2 * math.pi, {"rad": 1}),
@@ -256,6 +257,8 @@ class Quantity:
             arrs = list(args[0])
             unit = arrs[0].unit
             return Quantity(np.stack([a.to_value(unit) for a in arrs], *args[1:], **kwargs), unit)
+        if func is np.unique:
+            return Quantity(np.unique(args[0].value, *args[1:], **kwargs), args[0].unit)
         raise TypeError(f"astropy stub: numpy function {func.__name__} on a Quantity")
 
     def __repr__(self):
@@ -274,7 +277,7 @@ class SpecificTypeQuantity(Quantity):
             raise UnitConversionError(f"{type(self).__name__} needs units equivalent to {eq}")
 
 
-s, ms, us, ns, day = (Unit(n) for n in ("s", "ms", "us", "ns", "day"))
+s, ms, us, ns, min, day = (Unit(n) for n in ("s", "ms", "us", "ns", "min", "day"))
 Hz, kHz, MHz, GHz = (Unit(n) for n in ("Hz", "kHz", "MHz", "GHz"))
 cycle, rad, pc, cm = (Unit(n) for n in ("cycle", "rad", "pc", "cm"))
 one = dimensionless_unscaled = Unit()

@@ -118,6 +118,67 @@ def test_oracle_incoherent_and_real_to_complex_match_reference():
     assert relerr(orc.real_to_complex(G["r2c_x64"]), G["r2c_y64"]) < 1e-14
 
 
+POLYCO = os.path.join(HERE, "golden", "timing.dat")
+
+
+def _norm(ph1, ph2):
+    """(integer, fraction) the way pulsar/phase.py:69-77 splits what the predictor hands it."""
+    whole = np.rint(ph2)
+    return (np.asarray(ph1, dtype=np.int64) + whole.astype(np.int64)), ph2 - whole
+
+
+def test_oracle_predictor_matches_reference_predictor():
+    """pulsar/predictor.py itself (from_polyco, entry search, Polynomial evaluation, phasepol)
+    was executed on the reference's polyco fixture; the oracle restatement must give the same
+    integer cycles and the same fraction bit for bit when fed the same (day, fraction) pairs."""
+    entries = orc.parse_polyco(open(POLYCO).read())
+    assert np.array_equal([e["rphase"] for e in entries], G["pred_rphase"])
+    ph1, ph2, f0, f1 = G["pred_scalar"]
+    i, f = orc.predict_phase(entries, (58245, 0.375))
+    wi, wf = _norm(ph1, np.float64(ph2))
+    assert int(i) == int(wi) and float(f) == float(wf)
+    assert orc.spin_freq(entries, (58245, 0.375)) == f0
+    assert orc.spin_freq(entries, (58245, 0.375), n=1) == f1
+    wi, wf = _norm(G["pred_span_ph1"], G["pred_span_ph2"])
+    for k in range(len(wi)):                     # 400 times across all 16 polyco entries
+        t = (int(G["pred_span_mjd_int"][k]), float(G["pred_span_mjd_frac"][k]))
+        i, f = orc.predict_phase(entries, t)
+        assert int(i) == int(wi[k]) and float(f) == float(wf[k]), k
+        assert orc.spin_freq(entries, t) == G["pred_span_f0"][k]
+    for (d, fr), coef, ref in zip(G["pred_phasepol_mjd"], G["pred_phasepol_coef"],
+                                  G["pred_phasepol_ref"]):
+        c, r = orc.phasepol(entries, (int(d), float(fr)))
+        assert r == ref and np.array_equal(c, coef)
+    # 10000 microsecond steps: the reference adds them to the day fraction (1e-11 s granularity),
+    # the oracle to the offset in seconds -- the reference's own tests allow 1e-8 cycle here
+    i, f = orc.predict_phase(entries, (58245, 0.375), offsets_s=np.arange(10000) * 1e-6)
+    wi, wf = _norm(G["pred_us_ph1"], G["pred_us_ph2"])
+    assert np.max(np.abs((i - wi) + (f - wf))) < 1e-8
+
+
+def test_host_predictor_matches_reference_predictor():
+    """The package's PhasePredictor (host side of the fold: entry choice, phase at a time,
+    phasepol) against the reference's outputs."""
+    import pulsarbat_b200 as pb
+    from pulsarbat_b200.units import Time
+    pred = pb.PhasePredictor.from_polyco(POLYCO)
+    ph1, ph2, f0, f1 = G["pred_scalar"]
+    t1 = Time("58245.375")
+    i, f = pred(t1)
+    wi, wf = _norm(ph1, np.float64(ph2))
+    assert int(i) == int(wi) and float(f) == float(wf)
+    assert pred.f0(t1) == f0 and pred.f0(t1, n=1) == f1
+    wi, wf = _norm(G["pred_span_ph1"], G["pred_span_ph2"])
+    for k in range(0, len(wi), 7):
+        t = Time(float(G["pred_span_mjd_int"][k]), float(G["pred_span_mjd_frac"][k]))
+        i, f = pred(t)
+        assert int(i) == int(wi[k]) and float(f) == float(wf[k]), k
+    for (d, fr), coef, ref in zip(G["pred_phasepol_mjd"], G["pred_phasepol_coef"],
+                                  G["pred_phasepol_ref"]):
+        c, r = pred.phasepol(Time(float(d), float(fr)))
+        assert r == ref and np.array_equal(c, coef)
+
+
 def _check_stft_align(pb, stft_data):
     """Metadata of contrib.stft for freq_align bottom / top / center inputs with an even number
     of channels (misc.py:41 + core.py:479-484): center_freq, freq_align, channel_freqs."""
@@ -290,3 +351,30 @@ def test_cuda_incoherent_and_real_to_complex_match_reference():
     assert y32.dtype == np.complex64 and relerr(y32, G["r2c_y32"]) < TOL
     y64 = pb.utils.real_to_complex(G["r2c_x64"])
     assert relerr(y64, G["r2c_y64"]) < TOL
+
+
+@pytest.mark.gpu
+def test_cuda_phase_predictor_and_fold_bins_match_reference_predictor():
+    """Device-side phase prediction (kernels.predict_phase through PhasePredictor.sample_phases)
+    against the phases the reference's predictor returned for 10000 microsecond steps, and the
+    fold bins that follow from the reference's phasepol polynomial at the block start."""
+    import pulsarbat_b200 as pb
+    from pulsarbat_b200 import kernels
+    from pulsarbat_b200 import units as u
+    from pulsarbat_b200.units import Time
+    pred = pb.PhasePredictor.from_polyco(POLYCO)
+    ints, frac = pred.sample_phases(Time("58245.375"), 10000, 1 * u.MHz)
+    wi, wf = _norm(G["pred_us_ph1"], G["pred_us_ph2"])
+    # the kernel forms dt = dt0 + n / rate, the reference adds n microseconds to the day fraction
+    # (1e-11 s granularity x 642 Hz): the reference's own tolerance is 1e-8 cycle
+    assert np.max(np.abs((np.asarray(ints) - wi) + (np.asarray(frac) - wf))) < 1e-8
+    # fold bins of a block that starts there, from the REFERENCE's phasepol coefficients
+    coef = G["pred_phasepol_coef"][0]
+    nbin, nsamp, sr = 1024, 10000, 1e6
+    x = np.ones((nsamp, 2), np.float32)
+    _, counts, bins = kernels.fold(x, coef, sr, nbin, want_bins=True)
+    assert np.array_equal(bins, orc.fold_bins(nsamp, coef, sr, nbin))
+    ph = (wi - int(G["pred_phasepol_ref"][0])) + wf          # phase since the reference cycle
+    want = np.floor((ph - np.floor(ph)) * nbin).astype(np.int64) % nbin
+    assert np.mean(bins == want) > 0.999                     # equal except within 1e-8 cycle of an edge
+    assert int(counts.sum()) == nsamp
