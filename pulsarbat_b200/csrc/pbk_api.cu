@@ -1307,6 +1307,7 @@ struct DetectSpec {
   int pq = 0;          // floats per output cell: 0 = no detection, 1 = summed over the pair, 2 = per pol
   long long fsum = 1;
   bool split = false;  // the pair is the even / odd samples of one single-pol column (n is HALF)
+  bool volt = false;   // split with complex64 VOLTAGES out (plain stft of one single-pol channel)
 };
 
 static int build_fft_plan(long long O, long long n, long long C, long long P, bool inverse,
@@ -1387,6 +1388,24 @@ static int build_fft_plan(long long O, long long n, long long C, long long P, bo
   int rc = upload_tables(pl, ts);
   if (rc == PBK_OK) rc = setup_fast(pl);
   if (rc != PBK_OK) { pbk_plan_destroy(pl); return rc; }
+  if (det && det->volt) {
+    // plain channelizer of ONE single-pol column on the compile-time-shaped kernels: this plan
+    // transforms the (n, 2) even / odd view at half length and the last pass recombines
+    // X[k] = E + wO, X[k + n] = E - wO in registers and stores both halves of the fftshift-ed
+    // segment (pbk_fast.cuh, FWDLAST).  Needs the two-level plan with the narrow fast last pass.
+    Pass& last = pl->passes.back();
+    const bool ok = m == 2 && I == 2 && !inverse && last.family >= 0 && last.a.final_epi &&
+                    !last.a.out_transpose && last.a.load_kind == LOAD_PLANAR;
+    if (!ok) {
+      pbk_plan_destroy(pl);
+      return fail(PBK_ERR_UNSUPPORTED, "even/odd channelizer needs a two-level segment length");
+    }
+    PassArgs& a = last.a;
+    a.fsum_split = 1;
+    a.fsum_log2n = ln + 1;
+    a.log2Kmul = l[0];
+    a.mout = AddrMap{2 * n, 0, 0, 0, 0, 0, 0};      // complex64 elements per (full-length) segment
+  }
   if (det && det->pq) {
     // The epilogue sums the 2^k first-level bins that share an output cell: it needs the two-level
     // plan of a long segment (fine channel = kprev + Kprev * row), one channel (I == 2: a lane
@@ -1683,6 +1702,19 @@ static int stft_plan_create(int64_t nseg, int64_t nperseg, int64_t nchan, int64_
     return fail(PBK_ERR_INVALID, "packed input needs an even nchan * npol, got %lld",
                 (long long)(nchan * npol));
   const long long n = nperseg, C = nchan, P = npol;
+  if (!inverse && in_dtype == PBK_C64 && C == 1 && P == 1 && n % 2 == 0 && !getenv("PBK_NO_SPLIT")) {
+    // one single-pol column has no lane pair; its even and odd samples do (see
+    // pbk_stft_detect_plan_create): half-length plan on the (n/2, 2) view, recombined in the
+    // last pass.  Shapes it does not cover fall through to the plan below (generic kernels).
+    DetectSpec det;
+    det.split = det.volt = true;
+    const long long h = n / 2;
+    ExtMap in{h * 2, 2, 2, 1};
+    ExtMap om{h * 2, 2, h * 2, 1};     // unused: the recombining store has its own output map
+    const int rc = build_fft_plan(nseg, h, 1, 2, false, in, om, (float)(1.0 / (double)n), false,
+                                  false, device, plan, LOAD_C64, &det);
+    if (rc != PBK_ERR_UNSUPPORTED) return rc;
+  }
   if (!inverse) {
     // in[(s*n + t), c, p] ; out[s, c*n + shift(k), p] ; scale 1/n   (misc.py:41-52)
     ExtMap in{n * C * P, C * P, P, 1};
@@ -1897,7 +1929,8 @@ extern "C" int pbk_plan_describe(const pbk_plan* pl, char* buf, size_t n) {
       w = snprintf(buf + off, n - off, "%s%s:L=2^%d:%s:W=%d:tiles=%lld:threads=%d%s%s", sep,
                    mode, ps.a.log2L, ps.tsumw ? "tmaw-r16" : ps.tma ? "tma-r16" : "fast-r16",
                    2 << ps.finfo.log2pw, ps.ntiles, ps.tma ? ps.tinfo.threads : ps.finfo.threads,
-                   ps.a.tsum_log2 > 0 ? ":timesum" : "", ps.a.split ? ":evenodd" : "");
+                   ps.a.tsum_log2 > 0 ? ":timesum" : "",
+                   ps.a.split || ps.a.fsum_split ? ":evenodd" : "");
     else
       w = snprintf(buf + off, n - off, "%s%s:L=2^%d:%s:W=%d:tiles=%u:threads=%d", sep,
                    mode, ps.a.log2L, ps.fast ? "generic-vec" : "generic", 2 << ps.a.log2pw,

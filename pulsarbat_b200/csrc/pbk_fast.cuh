@@ -935,6 +935,25 @@ fast_pass_kernel(const __grid_constant__ PassArgs p, const float2* __restrict__ 
                 }
               }
           }
+        } else if (NARROW && p.fsum_split) {
+          // plain channelizer of ONE single-pol column run as its (even, odd) samples at half
+          // length: the pair holds E[k], O[k] at bin k = klow + Kprev * row; X[k] = E + wO goes to
+          // slot k + n/2 of the fftshift-ed segment, X[k + n/2] = E - wO to slot k (misc.py:48).
+          // The 16 lane rows of a tile are adjacent klow: 128-byte runs per store instruction.
+          float2* seg = reinterpret_cast<float2*>(T.gout);
+          const unsigned long long halfn = 1ull << (p.fsum_log2n - 1);
+#pragma unroll
+          for (int it = 0; it < LITERS; ++it)
+#pragma unroll
+            for (int i = 0; i < RL; ++i) {
+              const c2 z = v[it][i];
+              const unsigned long long k =
+                  (unsigned long long)T.klow + ((unsigned long long)(klo[it] + i * C::KS) << p.log2Kmul);
+              const float2 w = unit_root(k, p.fsum_log2n);        // exp(-2 pi i k / n)
+              const float tr = w.x * z.re.y - w.y * z.im.y, ti2 = w.x * z.im.y + w.y * z.re.y;
+              seg[k + halfn] = make_float2(z.re.x + tr, z.im.x + ti2);
+              seg[k] = make_float2(z.re.x - tr, z.im.x - ti2);
+            }
         } else if (!p.out_transpose) {
           // output lanes are adjacent in memory: one natural-order 16-byte store per row
 #pragma unroll

@@ -789,6 +789,33 @@ def test_fold_sample_times_are_correctly_rounded_quotients(sr):
         assert int(counts.sum()) == nsamp
 
 
+@pytest.mark.parametrize("log2n, nseg", [(16, 8), (14, 5), (17, 3), (13, 6), (20, 2)])
+def test_channelizer_of_one_single_pol_column_runs_as_even_odd_samples(log2n, nseg):
+    """stft of ONE channel, ONE polarisation (contrib/misc.py:41-52): no lane pair, so the plan
+    channelizes the (n/2, 2) even / odd view on the compile-time-shaped kernels and recombines
+    X[k] = E + wO, X[k + n/2] = E - wO in the last pass.  Against numpy's FFT of every segment."""
+    import torch
+    L = _lib()
+    n = 2 ** log2n
+    rng = np.random.default_rng(log2n * 10 + nseg)
+    x = crandn(rng, (nseg * n,))
+    xd = torch.from_numpy(x.view(np.float32).reshape(nseg * n, 1, 1, 2)).cuda()
+    yd = torch.empty_like(xd)
+    plan = L.STFTPlan(nseg, n, 1, 1, inverse=False)
+    desc = plan.describe()
+    plan.exec_device(xd.data_ptr(), yd.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    plan.destroy()
+    y = yd.cpu().numpy().reshape(nseg, n, 2).view(np.complex64)[..., 0]
+    want = np.fft.fftshift(scipy.fft.fft(x.astype(np.complex128).reshape(nseg, n), axis=1),
+                           axes=1) / n
+    assert relerr(y, want) < 3e-6, desc
+    if log2n >= 14:      # a two-level half-length plan exists: the recombining fast pass took it
+        assert "evenodd" in desc and "generic" not in desc.split(";")[-1], desc
+    if log2n >= 16:
+        assert "generic" not in desc, desc
+
+
 def test_fold_of_a_row_view_that_is_not_vector_aligned():
     """Rows of up to 8 floats are read with vector loads when the base address allows it; a
     device view that starts at an odd float offset must take the scalar kernel and give the same
