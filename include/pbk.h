@@ -154,7 +154,11 @@ int pbk_fft_plan_create(int64_t outer, int64_t n, int64_t inner, int32_t inverse
  *             out[s, c*n + ((k + n/2) mod n), p] = (1/n) sum_t in[s*n+t, c, p] e^{-2 pi i k t/n}
  *   inverse:  in (nseg, nchan_out*nperseg, npol) -> out (nseg*nperseg, nchan_out, npol)
  * Any nperseg >= 2 (the reference's tests use 33).  The input is never modified (the reference's
- * istft scales its input in place, misc.py:82-83).
+ * istft scales its input in place, misc.py:82-83).  A forward plan for ONE single-polarisation
+ * channel with a power-of-two nperseg >= 2^14 is built on the (nperseg/2, 2) even / odd view of the
+ * stream and recombined in the last pass (pbk_plan_describe shows ":evenodd"; PBK_NO_SPLIT=1
+ * disables it) -- same input, same output, the compile-time-shaped kernels instead of the
+ * run-time-shaped ones.
  */
 int pbk_stft_plan_create(int64_t nseg, int64_t nperseg, int64_t nchan, int64_t npol,
                          int32_t inverse, int32_t device, pbk_plan** plan);
