@@ -418,10 +418,26 @@ bool fast_info_r16(int log2L, FastInfo* info);
 void fast_tables_r16(int log2L, float2* dst);
 cudaError_t fast_launch_r16(int log2L, int mode, const PassArgs& a, const float2* d_tables,
                             long long ntiles, int num_sms, cudaStream_t st);
-bool fast_info(int family, int log2L, FastInfo* info) { return fast_info_r16(log2L, info); }
-void fast_tables(int family, int log2L, float2* dst) { fast_tables_r16(log2L, dst); }
+// ... plus half-width 2^8-point tiles for the detecting last pass of a channelizer plan
+void fast_info_l8n(FastInfo* info);
+void fast_tables_l8n(float2* dst);
+cudaError_t fast_launch_l8n(int mode, const PassArgs& a, const float2* d_tables, long long ntiles,
+                            int num_sms, cudaStream_t st);
+bool fast_info(int family, int log2L, FastInfo* info) {
+  if (family == FAMILY_R16N) {
+    if (log2L != 8) return false;
+    fast_info_l8n(info);
+    return true;
+  }
+  return fast_info_r16(log2L, info);
+}
+void fast_tables(int family, int log2L, float2* dst) {
+  if (family == FAMILY_R16N) fast_tables_l8n(dst);
+  else fast_tables_r16(log2L, dst);
+}
 cudaError_t fast_launch(int family, int log2L, int mode, const PassArgs& a, const float2* d_tables,
                         long long ntiles, int num_sms, cudaStream_t st) {
+  if (family == FAMILY_R16N) return fast_launch_l8n(mode, a, d_tables, ntiles, num_sms, st);
   return fast_launch_r16(log2L, mode, a, d_tables, ntiles, num_sms, st);
 }
 }  // namespace pbk
@@ -1428,8 +1444,26 @@ static int build_fft_plan(long long O, long long n, long long C, long long P, bo
                   (long long)det->fsum);
     }
     PassArgs& a = last.a;
+    long long rpt = rows_per_tile;
+    {
+      // half-width tiles (four 128-thread CTAs per SM instead of two of 256) when the shape allows:
+      // same stage tables, so the slot staged by setup_fast is reused.  $PBK_NO_NARROW_FSUM=1 keeps
+      // the full-width tiles.
+      FastInfo fn;
+      if (!getenv("PBK_NO_NARROW_FSUM") && fast_info(FAMILY_R16N, a.log2L, &fn) &&
+          fn.tw_count == last.finfo.tw_count) {
+        const long long Wn = 2ll << fn.log2pw, rn = Wn / I;
+        if (rn > 0 && det->fsum % rn == 0 && Kp % rn == 0 && a.Q % Wn == 0 &&
+            (a.Q / Wn) % (det->fsum / rn) == 0) {
+          last.family = FAMILY_R16N;
+          last.finfo = fn;
+          last.ntiles = a.Q / Wn;
+          rpt = rn;
+        }
+      }
+    }
     a.fsum_log2 = lf;
-    a.fsum_g_log2 = ilog2_exact(det->fsum / rows_per_tile);
+    a.fsum_g_log2 = ilog2_exact(det->fsum / rpt);
     a.fsum_row_shift = l[0] - lf;
     a.fsum_pq = det->pq;
     a.fsum_split = det->split ? 1 : 0;

@@ -7,7 +7,8 @@
 
 namespace pbk {
 
-enum { FAMILY_R8 = 0, FAMILY_R16 = 1 };
+enum { FAMILY_R8 = 0, FAMILY_R16 = 1,
+       FAMILY_R16N = 2 /* half-width 2^8-point tiles, detecting channelizer pass only */ };
 
 struct FastInfo {
   int log2pw;        // lane pairs per tile (log2)
