@@ -1,7 +1,10 @@
 // 2^8-point tiles HALF as wide as pbk_fast_l8.cu's (256 points x 16 lanes, 32 KiB, 128 threads,
 // four CTAs per SM) for the detecting last pass of a channelizer plan (FSUM, pbk_fast.cuh): that
 // pass only reads, so four small CTAs per SM in different phases overlap its load and compute
-// phases better than two large ones.  Only the two kernels that pass uses are instantiated.
+// phases better than two large ones (0.33 -> 0.30 ms).  Only the two kernels that pass uses are
+// instantiated.  (The time-summing last pass of a dedispersion plan was tried on these tiles too:
+// 0.96 -> 1.04 ms -- its tile rows are 16 MB apart, and 128-byte chunks of such rows run into the
+// chunk-rate limit of DESIGN.md 5.1.)
 #include "pbk_fast_inst.cuh"
 
 namespace pbk {
